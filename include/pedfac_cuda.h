@@ -1,0 +1,181 @@
+/*
+ * pedfac_cuda.h — C ABI of libpedfac_cuda, the B200 (sm_100a) likelihood engine for the
+ * pedFac `pedigraph` sampler's hot path: per-locus sum-product over the pedigree factor
+ * graph and per-proposal log-likelihood evaluation.
+ *
+ * The reference has no FFI seam: its MCMC driver (L2) calls the likelihood
+ * layer (L1) directly on a `ped` struct. Each entry point below replaces one L2→L1 call
+ * site of the reference binary `exec/pedigraph` (cited as pedigraph@<VM address> <symbol>).
+ *
+ * Conventions: plain C; every function returns PF_OK (0) or a negative PF_E* code and
+ * leaves a message retrievable with pf_last_error(); all pointer arguments are caller-owned
+ * HOST buffers unless the name ends in `_dev`; an engine is not thread-safe; there is no CPU
+ * fallback — without a usable CUDA device pf_create fails.
+ *
+ * Indexing: "slot" = index into the reference's ped->indiv[] / ped->mnode[] arrays
+ * (observed individuals first, unobserved after). Genotype state
+ * g in {0,1,2} = copies of the "1" allele. Triples are stored [locus][g] on the host side.
+ */
+#ifndef PEDFAC_CUDA_H
+#define PEDFAC_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PF_OK            0
+#define PF_EINVAL      (-1)   /* bad argument / malformed graph view */
+#define PF_ECUDA       (-2)   /* CUDA runtime error (message has the detail) */
+#define PF_ENOMEM      (-3)
+#define PF_ENODEVICE   (-4)   /* no usable GPU: there is deliberately no CPU fallback */
+#define PF_ECYCLE      (-5)   /* the graph view is not a forest (reference: "exceeds the acyclic upper limit") */
+
+typedef struct pf_engine pf_engine;
+
+typedef struct pf_config {
+    int32_t n_loci;       /* S: loci in the data set (prior.txt nSNP) */
+    int32_t locus_begin;  /* this engine evaluates loci [locus_begin, locus_end) — the */
+    int32_t locus_end;    /*   multi-GPU shard; (0, S) for a single GPU                */
+    int32_t cap_indiv;    /* individual slots (ped->capIndiv, _CalculateMaxSize@0x100007ba5) */
+    int32_t cap_marr;     /* marriage slots */
+    int32_t n_chains;     /* independent MCMC chains sharing the genotype arrays (>= 1) */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t reserved;
+} pf_config;
+
+/* Proposal kinds. One proposal ≙ one entry appended to the reference's `choice` list. */
+enum {
+    PF_PROP_TRIO    = 0,  /* _CalculateLikeByStubs@0x10001f260 / _CalculateLLByStubs@0x10001eef0:
+                             kid gets parents (pa, ma); -1 = a new unobserved founder (HWE prior) */
+    PF_PROP_SELFING = 1,  /* _CalculateLikeByStubsSelfing@0x10001f6d0: one parent `pa` (or -1) selfs */
+    PF_PROP_PRONG   = 2   /* _CalculateLikeByProngs@0x10001fa20: kid joins existing marriage `marr` */
+};
+
+typedef struct pf_proposal {
+    int32_t kind;
+    int32_t pa;    /* individual slot or -1 */
+    int32_t ma;    /* individual slot or -1 */
+    int32_t marr;  /* marriage slot (PF_PROP_PRONG) */
+} pf_proposal;
+
+/*
+ * The sub-forest to (re)propagate: exactly the two worklists _TurnOnSpotlight@0x10001bb90
+ * builds (active individuals whose component is dirty; active marriages whose father's
+ * component is dirty) plus the adjacency the message passes read through ped->mnode[].
+ * The view must be closed: every individual referenced by a listed marriage is listed.
+ */
+typedef struct pf_graph_view {
+    int32_t        n_indiv;
+    const int32_t *indiv;          /* [n_indiv] slots                                         */
+    const int32_t *indiv_cc;       /* [n_indiv] component label, value in [0, n_cc)           */
+    const uint8_t *indiv_founder;  /* [n_indiv] indiv->isFounder (p-node sends the HWE prior) */
+    int32_t        n_marr;
+    const int32_t *marr;           /* [n_marr] marriage slots                                 */
+    const int32_t *marr_pa;        /* [n_marr] father slot (edge 0)                           */
+    const int32_t *marr_ma;        /* [n_marr] mother slot (edge 1); ignored when selfing     */
+    const uint8_t *marr_selfing;   /* [n_marr] mnode->selfing                                 */
+    const int32_t *marr_kid_begin; /* [n_marr + 1] CSR offsets into marr_kids (edges 2..)     */
+    const int32_t *marr_kids;
+    int32_t        n_cc;           /* labels used by indiv_cc are 0..n_cc-1 (local to the view) */
+} pf_graph_view;
+
+const char *pf_last_error(void);
+
+/* Engine lifetime. ≙ _AllocIndiv@0x100007dd0 (storage), minus every per-edge message array. */
+int pf_create(pf_engine **out, const pf_config *cfg);
+int pf_destroy(pf_engine *e);
+
+/* Run the engine's work on an existing CUDA stream (cudaStream_t passed as void*); default:
+ * a private non-blocking stream. */
+int pf_set_stream(pf_engine *e, void *cuda_stream);
+
+/* Per-locus parameters: genotyping error eps[S] and "1"-allele frequency afreq[S]
+ * (prior.txt rows `epsilon`, `aFreq`). The HWE founder prior is built as
+ * _ReadPedfile@0x1000099d2-0x100009ad4 does: q = 1-a; [q*q, (2*(1-q))*q, (1-q)*(1-q)]. */
+int pf_set_locus_params(pf_engine *e, const double *eps, const double *afreq);
+
+/* Genotype data of one individual slot, all S loci of the data set (the engine keeps its
+ * shard). ≙ the emission construction in _ReadPedfile@0x10000b1ca-0x10000b6e2.
+ *   hard:  codes[s] in {0,1,2,3}; 3 = missing -> [1,1,1]; c -> e[c] = 1-eps[s], others eps[s]/2.
+ *          Stored as 2-bit codes.
+ *   soft (f32):  lik[s][3] genotype likelihoods stored as fp32 triples; emission = (double)lik.
+ *   soft (f64):  exact doubles (what strtod returned in the reference).
+ *   soft (dec16): num[s][3] / denom, the exact value of a decimal token with <= 4 fractional
+ *          digits (R writes round(x, 4): R/renderGeno.R:114-118); 6 bytes per locus.
+ *   unobserved: emission [1,1,1] (_AttachUnobsIndiv@0x100012cfa). */
+int pf_set_genotypes_hard(pf_engine *e, int32_t slot, const uint8_t *codes);
+int pf_set_genotypes_soft(pf_engine *e, int32_t slot, const float *lik);
+int pf_set_genotypes_soft_f64(pf_engine *e, int32_t slot, const double *lik);
+int pf_set_genotypes_soft_dec16(pf_engine *e, int32_t slot, const uint16_t *num, uint32_t denom);
+int pf_set_genotypes_unobserved(pf_engine *e, int32_t slot);
+
+/* ≙ _Propagating_msg@0x10001ba10 restricted to the view: recomputes the stub of every listed
+ * individual (_FillInStubs@0x10001e1a0), the prong of every listed marriage
+ * (_FillInProngs@0x10001dd70) and, per component label c, ll_cc[c] = sum over this engine's
+ * loci of log Z (_UpdateProb@0x10001da20). ll_cc has view->n_cc entries. With a locus shard
+ * the values are partial sums to be added across shards. */
+int pf_sweep(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc);
+
+/* ≙ the CalculateLikeBy* call sites in _EvalMoves@0x100015010 / _ProposeSingletMove@0x1000149d0:
+ * for focal individual `kid` and each proposal p, lsum[p] = sum over this engine's loci of
+ * log(contraction) — the data term of the reference's ll. The caller adds the component
+ * bookkeeping with pf_compose_ll(). */
+int pf_eval(pf_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_proposal *props,
+            double *lsum);
+
+/* Same as pf_sweep / pf_eval but results stay on the device (ll_cc_dev / lsum_dev are device
+ * pointers, written on the engine's stream, no host synchronisation): the form used when an
+ * NCCL all-reduce over locus shards follows. */
+int pf_sweep_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc_dev);
+int pf_eval_dev(pf_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_proposal *props,
+                double *lsum_dev);
+
+/* Batched forms: one launch sequence for several chains (config D: 64 chains per GPU).
+ * views[i] is swept on chains[i]; ll_cc receives the concatenation of the per-view outputs.
+ * Evals: request i = (chains[i], kids[i], props[prop_begin[i] .. prop_begin[i+1])). */
+int pf_sweep_batch(pf_engine *e, int32_t n, const int32_t *chains, const pf_graph_view *views,
+                   double *ll_cc);
+int pf_eval_batch(pf_engine *e, int32_t n, const int32_t *chains, const int32_t *kids,
+                  const int32_t *prop_begin, const pf_proposal *props, double *lsum);
+
+/* ≙ _RefineParentOffPair@0x100014d20 (its N_obs^2 x S _CalculateLLByStubs calls), dense form:
+ * for every kid k and every candidate c (c != kid) the score
+ *     lsum(kid k; c as the single given parent, the other parent a new founder) + cand_bias[c]
+ * where cand_bias (may be NULL = 0) carries the -LLcc terms of _CalculateLLByStubs@0x10001f183-0x10001f241.
+ * c is the father if as_father[k] else the mother (the value is the same: _TPROB is symmetric
+ * in the parents). Reduced on the device to the top_k highest scores per kid (ties: earlier
+ * candidate first; top_k <= 32). out_slot/out_score are [n_kids][top_k]; unused entries are
+ * -1 / -inf. The caller groups kids that share a candidate set (same generation time: the age
+ * window test of @0x100014dbf-0x100014def). Unsharded engines only (ranking needs all loci). */
+int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                 const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
+                 const double *cand_bias, int32_t top_k, int32_t *out_slot, double *out_score);
+
+/* Read-back of persisted per-locus results (tests, debugging): out[s][3] for this engine's loci. */
+int pf_get_stub(pf_engine *e, int32_t chain, int32_t slot, double *out);
+int pf_get_prong(pf_engine *e, int32_t chain, int32_t marr, double *out);
+
+/* Counters: kernels launched by this engine since creation. */
+int64_t pf_launch_count(const pf_engine *e);
+
+/*
+ * The scalar bookkeeping the reference wraps around the data term (host, fp64), in the
+ * reference's order (_CalculateLikeByStubs@0x10001f5df-0x10001f6ae):
+ *   ll = ((-LLcc[cc(kid)] + -(use_pa)*LLcc[cc(pa)]) + -(use_ma)*LLcc[cc(ma)]) + (LLtot + lsum)
+ * use_pa = pa != -1 && cc(pa) != cc(kid); use_ma = ma != -1 && cc(ma) != cc(pa) && cc(ma) != cc(kid).
+ */
+static inline double pf_compose_ll(double ll_tot, double lsum, double ll_cc_kid,
+                                   int use_pa, double ll_cc_pa, int use_ma, double ll_cc_ma)
+{
+    double a = -ll_cc_kid;
+    a = a + (use_pa ? -ll_cc_pa : 0.0);
+    a = a + (use_ma ? -ll_cc_ma : 0.0);
+    return a + (ll_tot + lsum);
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PEDFAC_CUDA_H */

@@ -1,0 +1,872 @@
+// pf_engine.cu — host side of libpedfac_cuda: device storage, genotype packing, the sweep plan
+// builder (graph view -> level-ordered task list) and the C ABI of include/pedfac_cuda.h.
+// There is no CPU fallback anywhere in this file: every entry point either runs the sm_100a
+// kernels of pf_kernels.cu or returns an error.
+#include "../../include/pedfac_cuda.h"
+#include "pf_kernels.cuh"
+#include "pf_prefilter.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace pf;
+
+static thread_local char g_err[1024] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return fail(PF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+// grow-only device buffer
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 2 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// ring of pinned staging buffers; a slot is reused only after the copy that read it completed
+struct Staging {
+    static constexpr int N = 4;
+    void *p[N] = {};
+    size_t cap[N] = {};
+    cudaEvent_t ev[N] = {};
+    bool used[N] = {};
+    int next = 0;
+    cudaError_t get(size_t bytes, void **out, int *slot)
+    {
+        int i = next; next = (next + 1) % N;
+        if (used[i]) { cudaError_t e = cudaEventSynchronize(ev[i]); if (e != cudaSuccess) return e; used[i] = false; }
+        if (!ev[i]) { cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming); if (e != cudaSuccess) return e; }
+        if (bytes > cap[i]) {
+            if (p[i]) cudaFreeHost(p[i]);
+            p[i] = nullptr; cap[i] = 0;
+            size_t want = bytes + bytes / 2 + 4096;
+            cudaError_t e = cudaMallocHost(&p[i], want);
+            if (e != cudaSuccess) return e;
+            cap[i] = want;
+        }
+        *out = p[i]; *slot = i;
+        return cudaSuccess;
+    }
+    cudaError_t mark(int slot, cudaStream_t st) { used[slot] = true; return cudaEventRecord(ev[slot], st); }
+    void release()
+    {
+        for (int i = 0; i < N; i++) { if (p[i]) cudaFreeHost(p[i]); if (ev[i]) cudaEventDestroy(ev[i]); p[i] = nullptr; ev[i] = nullptr; }
+    }
+};
+
+struct SoftChunk { char *base; size_t cap, used; };
+
+} // namespace
+
+struct pf_engine {
+    pf_config cfg;
+    int Sl = 0, Sp = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    double *d_rows = nullptr; size_t n_rows = 0;
+    double *d_eps = nullptr;
+    uint32_t *d_hard = nullptr;           // [cap_indiv][Sp/16]
+    uint8_t *d_kind = nullptr; void **d_eptr = nullptr; uint32_t *d_denom = nullptr;
+    std::vector<uint8_t> h_kind; std::vector<void *> h_eptr; std::vector<uint32_t> h_denom;
+    std::vector<uint8_t> soft_kind_of_row;  // kind the slot's soft row was allocated for
+    bool tables_dirty = true;
+    std::vector<SoftChunk> soft_chunks;
+    std::vector<double> h_eps;            // local shard, for validation only
+
+    DevBuf scratch, plan, partial, result;
+    Staging staging;
+    double *h_result = nullptr; size_t h_result_cap = 0;
+
+    std::vector<int> loc;                 // slot -> index in the view being planned
+    int64_t launches = 0;
+
+    size_t row_elems() const { return (size_t)3 * Sp; }
+    int stub_row(int chain, int slot) const { return ROW_CHAIN0 + chain * (cfg.cap_indiv + cfg.cap_marr) + slot; }
+    int prong_row(int chain, int m) const { return ROW_CHAIN0 + chain * (cfg.cap_indiv + cfg.cap_marr) + cfg.cap_indiv + m; }
+};
+
+// ---------------------------------------------------------------------------------------------
+
+extern "C" const char *pf_last_error(void) { return g_err; }
+
+extern "C" int pf_destroy(pf_engine *e)
+{
+    if (!e) return PF_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_rows); cudaFree(e->d_eps); cudaFree(e->d_hard);
+    cudaFree(e->d_kind); cudaFree(e->d_eptr); cudaFree(e->d_denom);
+    for (auto &c : e->soft_chunks) cudaFree(c.base);
+    e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release();
+    e->staging.release();
+    if (e->h_result) cudaFreeHost(e->h_result);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return PF_OK;
+}
+
+static __global__ void fill_kernel(double *p, size_t n, double v)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
+{
+    if (!out || !cfg) return fail(PF_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->n_loci <= 0 || cfg->locus_begin < 0 || cfg->locus_end > cfg->n_loci ||
+        cfg->locus_begin >= cfg->locus_end || cfg->cap_indiv <= 0 || cfg->cap_marr < 0 || cfg->n_chains < 1)
+        return fail(PF_EINVAL, "bad config (n_loci=%d shard=[%d,%d) cap_indiv=%d cap_marr=%d n_chains=%d)",
+                    cfg->n_loci, cfg->locus_begin, cfg->locus_end, cfg->cap_indiv, cfg->cap_marr, cfg->n_chains);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(PF_ENODEVICE, "no CUDA device available (%s); libpedfac_cuda has no CPU fallback",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(PF_EINVAL, "device %d out of range (%d devices)", cfg->device, ndev);
+    CU(cudaSetDevice(cfg->device));
+
+    pf_engine *e = new pf_engine();
+    e->cfg = *cfg;
+    e->Sl = cfg->locus_end - cfg->locus_begin;
+    e->Sp = (e->Sl + 63) / 64 * 64;
+    const size_t rows_total = (size_t)ROW_CHAIN0 + (size_t)cfg->n_chains * ((size_t)cfg->cap_indiv + cfg->cap_marr);
+    if (rows_total >= (size_t)SCRATCH_BIT) { delete e; return fail(PF_EINVAL, "too many rows"); }
+    e->n_rows = rows_total;
+
+#define CUX(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { int rc = fail(_e == cudaErrorMemoryAllocation ? PF_ENOMEM : PF_ECUDA, "%s failed: %s", #call, cudaGetErrorString(_e)); pf_destroy(e); return rc; } } while (0)
+    CUX(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    e->own_stream = true;
+    CUX(cudaMalloc(&e->d_rows, rows_total * e->row_elems() * sizeof(double)));
+    CUX(cudaMalloc(&e->d_eps, e->Sp * sizeof(double)));
+    CUX(cudaMalloc(&e->d_hard, (size_t)cfg->cap_indiv * (e->Sp / 16) * sizeof(uint32_t)));
+    CUX(cudaMalloc(&e->d_kind, cfg->cap_indiv));
+    CUX(cudaMalloc(&e->d_eptr, (size_t)cfg->cap_indiv * sizeof(void *)));
+    CUX(cudaMalloc(&e->d_denom, (size_t)cfg->cap_indiv * sizeof(uint32_t)));
+    CUX(cudaMemsetAsync(e->d_eps, 0, e->Sp * sizeof(double), e->stream));
+    // prior and ones rows start as ones (also keeps padded loci harmless)
+    fill_kernel<<<64, 256, 0, e->stream>>>(e->d_rows, 2 * e->row_elems(), 1.0);
+    e->launches++;
+    CUX(cudaGetLastError());
+    CUX(cudaStreamSynchronize(e->stream));
+#undef CUX
+    e->h_kind.assign(cfg->cap_indiv, EMIS_NONE);
+    e->h_eptr.assign(cfg->cap_indiv, nullptr);
+    e->h_denom.assign(cfg->cap_indiv, 1);
+    e->soft_kind_of_row.assign(cfg->cap_indiv, EMIS_NONE);
+    e->h_eps.assign(e->Sl, 0.0);
+    e->loc.assign(cfg->cap_indiv, -1);
+    *out = e;
+    return PF_OK;
+}
+
+extern "C" int pf_set_stream(pf_engine *e, void *cuda_stream)
+{
+    if (!e) return fail(PF_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+    e->stream = static_cast<cudaStream_t>(cuda_stream);
+    return PF_OK;
+}
+
+extern "C" int64_t pf_launch_count(const pf_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int pf_set_locus_params(pf_engine *e, const double *eps, const double *afreq)
+{
+    if (!e || !eps || !afreq) return fail(PF_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    const int Sl = e->Sl, Sp = e->Sp, s0 = e->cfg.locus_begin;
+    std::vector<double> buf((size_t)4 * Sp, 1.0);
+    for (int s = 0; s < Sl; s++) {
+        // _ReadPedfile@0x1000099d2-0x100009ad4: q = 1 - a; [q*q, (2*(1-q))*q, (1-q)*(1-q)]
+        const double q = 1.0 - afreq[s0 + s];
+        buf[s] = q * q;
+        buf[Sp + s] = (2.0 * (1.0 - q)) * q;
+        buf[2 * Sp + s] = (1.0 - q) * (1.0 - q);
+        buf[3 * Sp + s] = eps[s0 + s];
+        e->h_eps[s] = eps[s0 + s];
+    }
+    for (int s = Sl; s < Sp; s++) buf[3 * Sp + s] = 0.0;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(e->d_rows + (size_t)ROW_PRIOR * e->row_elems(), buf.data(), (size_t)3 * Sp * sizeof(double), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->d_eps, buf.data() + 3 * Sp, (size_t)Sp * sizeof(double), cudaMemcpyHostToDevice));
+    return PF_OK;
+}
+
+static int soft_row(pf_engine *e, int slot, uint8_t kind, size_t elem_bytes, void **out)
+{
+    if (e->h_eptr[slot] && e->soft_kind_of_row[slot] == kind) { *out = e->h_eptr[slot]; return PF_OK; }
+    const size_t bytes = ((size_t)3 * e->Sp * elem_bytes + 255) & ~(size_t)255;
+    if (e->soft_chunks.empty() || e->soft_chunks.back().used + bytes > e->soft_chunks.back().cap) {
+        SoftChunk c{};
+        c.cap = std::max<size_t>(bytes, (size_t)64 << 20);
+        cudaError_t ce = cudaMalloc(&c.base, c.cap);
+        if (ce != cudaSuccess) return fail(PF_ENOMEM, "cudaMalloc(%zu) for soft genotypes failed: %s", c.cap, cudaGetErrorString(ce));
+        e->soft_chunks.push_back(c);
+    }
+    SoftChunk &c = e->soft_chunks.back();
+    *out = c.base + c.used;
+    c.used += bytes;
+    e->soft_kind_of_row[slot] = kind;
+    return PF_OK;
+}
+
+template <typename T>
+static int set_soft(pf_engine *e, int32_t slot, const T *lik, uint8_t kind, uint32_t denom)
+{
+    if (!e || !lik) return fail(PF_EINVAL, "null argument");
+    if (slot < 0 || slot >= e->cfg.cap_indiv) return fail(PF_EINVAL, "slot %d out of range", slot);
+    CU(cudaSetDevice(e->cfg.device));
+    void *row = nullptr;
+    int rc = soft_row(e, slot, kind, sizeof(T), &row);
+    if (rc) return rc;
+    const int Sl = e->Sl, Sp = e->Sp, s0 = e->cfg.locus_begin;
+    std::vector<T> buf((size_t)3 * Sp, (T)1);
+    for (int s = 0; s < Sl; s++)
+        for (int g = 0; g < 3; g++) buf[(size_t)g * Sp + s] = lik[(size_t)(s0 + s) * 3 + g];
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(row, buf.data(), buf.size() * sizeof(T), cudaMemcpyHostToDevice));
+    e->h_kind[slot] = kind; e->h_eptr[slot] = row; e->h_denom[slot] = denom;
+    e->tables_dirty = true;
+    return PF_OK;
+}
+
+extern "C" int pf_set_genotypes_soft(pf_engine *e, int32_t slot, const float *lik) { return set_soft<float>(e, slot, lik, EMIS_F32, 1); }
+extern "C" int pf_set_genotypes_soft_f64(pf_engine *e, int32_t slot, const double *lik) { return set_soft<double>(e, slot, lik, EMIS_F64, 1); }
+extern "C" int pf_set_genotypes_soft_dec16(pf_engine *e, int32_t slot, const uint16_t *num, uint32_t denom)
+{
+    if (denom == 0) return fail(PF_EINVAL, "denominator 0");
+    return set_soft<uint16_t>(e, slot, num, EMIS_DEC16, denom);
+}
+
+extern "C" int pf_set_genotypes_hard(pf_engine *e, int32_t slot, const uint8_t *codes)
+{
+    if (!e || !codes) return fail(PF_EINVAL, "null argument");
+    if (slot < 0 || slot >= e->cfg.cap_indiv) return fail(PF_EINVAL, "slot %d out of range", slot);
+    CU(cudaSetDevice(e->cfg.device));
+    const int Sl = e->Sl, words = e->Sp / 16, s0 = e->cfg.locus_begin;
+    std::vector<uint32_t> buf(words, 0xffffffffu);   // padding = code 3 (missing)
+    for (int s = 0; s < Sl; s++) {
+        const uint32_t c = codes[s0 + s];
+        if (c > 3) return fail(PF_EINVAL, "Acceptable genotype values are 0, 1, 2, or 3 (slot %d, locus %d: %u)", slot, s0 + s, c);
+        buf[s >> 4] = (buf[s >> 4] & ~(3u << ((s & 15) * 2))) | (c << ((s & 15) * 2));
+    }
+    uint32_t *row = e->d_hard + (size_t)slot * words;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(row, buf.data(), (size_t)words * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    e->h_kind[slot] = EMIS_HARD; e->h_eptr[slot] = row; e->h_denom[slot] = 1;
+    e->soft_kind_of_row[slot] = EMIS_NONE;
+    e->tables_dirty = true;
+    return PF_OK;
+}
+
+extern "C" int pf_set_genotypes_unobserved(pf_engine *e, int32_t slot)
+{
+    if (!e) return fail(PF_EINVAL, "null engine");
+    if (slot < 0 || slot >= e->cfg.cap_indiv) return fail(PF_EINVAL, "slot %d out of range", slot);
+    if (e->h_kind[slot] != EMIS_NONE) { e->h_kind[slot] = EMIS_NONE; e->tables_dirty = true; }
+    return PF_OK;
+}
+
+static int sync_tables(pf_engine *e)
+{
+    if (!e->tables_dirty) return PF_OK;
+    CU(cudaMemcpyAsync(e->d_kind, e->h_kind.data(), e->h_kind.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->d_eptr, e->h_eptr.data(), e->h_eptr.size() * sizeof(void *), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->d_denom, e->h_denom.data(), e->h_denom.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));   // the sources are pageable vectors that may change next
+    e->tables_dirty = false;
+    return PF_OK;
+}
+
+static DevView dev_view(pf_engine *e)
+{
+    DevView D;
+    D.rows = e->d_rows; D.scratch = static_cast<double *>(e->scratch.p);
+    D.eps = e->d_eps; D.ekind = e->d_kind; D.eptr = e->d_eptr; D.edenom = e->d_denom;
+    D.Sl = e->Sl; D.Sp = e->Sp;
+    return D;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sweep plan builder
+
+namespace {
+
+struct PlanTask { int group, level, kind, off; };
+
+struct Plan {
+    std::vector<PlanTask> tasks;
+    std::vector<int> pool;
+    int n_levels = 1, n_groups = 1, n_out = 0, n_scratch = 0;
+};
+
+struct ViewWork {           // scratch vectors reused across calls
+    std::vector<int> adj_off, adj_m, adj_role;      // individual -> (marriage, role)
+    std::vector<int> mem_off, mem_i, mem_role;      // marriage -> members (pa, ma, kids)
+    std::vector<int> Ui, um, urole, depth_m, lvlA, comp_of_i;
+    std::vector<int> up_i_row, up_m_row, dn_row;
+    std::vector<int> bfs_m, queue;
+    std::vector<char> vis_i, vis_m, label_seen;
+};
+
+} // namespace
+
+static thread_local ViewWork g_work;
+
+// Appends the tasks of one view to `plan`. Levels are assigned in two bands: FAMILY_UP tasks get
+// their height above the leaves; ROOT/FAMILY_DOWN tasks get (band offset) + depth below the root.
+// The band offset is fixed up by the caller once every view has been added.
+static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan,
+                         int &max_up_levels, std::vector<int> &comp_task_begin)
+{
+    if (!v) return fail(PF_EINVAL, "null view");
+    const int nI = v->n_indiv, nM = v->n_marr;
+    if (nI < 0 || nM < 0 || v->n_cc < 0) return fail(PF_EINVAL, "negative count in view");
+    if (nI > 0 && (!v->indiv || !v->indiv_cc || !v->indiv_founder)) return fail(PF_EINVAL, "null individual arrays");
+    if (nM > 0 && (!v->marr || !v->marr_pa || !v->marr_ma || !v->marr_selfing || !v->marr_kid_begin)) return fail(PF_EINVAL, "null marriage arrays");
+    if (chain < 0 || chain >= e->cfg.n_chains) return fail(PF_EINVAL, "chain %d out of range", chain);
+    ViewWork &w = g_work;
+    int rc = PF_OK;
+    int registered = 0;
+
+    // slot -> local index
+    for (int i = 0; i < nI; i++) {
+        const int slot = v->indiv[i];
+        if (slot < 0 || slot >= e->cfg.cap_indiv || e->loc[slot] != -1) { rc = fail(PF_EINVAL, "bad or duplicate individual slot %d in view", slot); goto cleanup; }
+        if (v->indiv_cc[i] < 0 || v->indiv_cc[i] >= v->n_cc) { rc = fail(PF_EINVAL, "component label %d of slot %d outside [0,%d)", v->indiv_cc[i], slot, v->n_cc); goto cleanup; }
+        e->loc[slot] = i;
+        registered = i + 1;
+    }
+    {
+        // members of each marriage
+        w.mem_off.assign(nM + 1, 0); w.mem_i.clear(); w.mem_role.clear();
+        w.adj_off.assign(nI + 1, 0);
+        for (int j = 0; j < nM; j++) {
+            if (v->marr[j] < 0 || v->marr[j] >= e->cfg.cap_marr) { rc = fail(PF_EINVAL, "marriage slot %d out of range", v->marr[j]); goto cleanup; }
+            const int kb = v->marr_kid_begin[j], ke = v->marr_kid_begin[j + 1];
+            if (ke < kb) { rc = fail(PF_EINVAL, "marr_kid_begin not monotone"); goto cleanup; }
+            const int ne = 2 + (ke - kb);
+            for (int ed = 0; ed < ne; ed++) {
+                if (ed == 1 && v->marr_selfing[j]) continue;
+                const int slot = ed == 0 ? v->marr_pa[j] : ed == 1 ? v->marr_ma[j] : v->marr_kids[kb + ed - 2];
+                if (slot < 0 || slot >= e->cfg.cap_indiv || e->loc[slot] < 0) { rc = fail(PF_EINVAL, "view not closed: marriage %d references unlisted individual %d", v->marr[j], slot); goto cleanup; }
+                w.mem_i.push_back(e->loc[slot]);
+                w.mem_role.push_back(ed < 2 ? ed : 2);
+                w.adj_off[e->loc[slot] + 1]++;
+            }
+            w.mem_off[j + 1] = (int)w.mem_i.size();
+        }
+        for (int i = 0; i < nI; i++) w.adj_off[i + 1] += w.adj_off[i];
+        w.adj_m.assign(w.mem_i.size(), 0); w.adj_role.assign(w.mem_i.size(), 0);
+        std::vector<int> &fillpos = w.queue;
+        fillpos.assign(w.adj_off.begin(), w.adj_off.end() - 1);
+        for (int j = 0; j < nM; j++)
+            for (int k = w.mem_off[j]; k < w.mem_off[j + 1]; k++) {
+                const int i = w.mem_i[k];
+                w.adj_m[fillpos[i]] = j; w.adj_role[fillpos[i]] = w.mem_role[k]; fillpos[i]++;
+            }
+
+        w.Ui.assign(nI, -1); w.um.assign(nM, -1); w.urole.assign(nM, 0); w.depth_m.assign(nM, 0);
+        w.lvlA.assign(nM, 0); w.vis_i.assign(nI, 0); w.vis_m.assign(nM, 0); w.label_seen.assign(v->n_cc, 0);
+        w.up_i_row.assign(nI, -1); w.up_m_row.assign(nM, -1); w.dn_row.assign(nI, -1);
+        w.bfs_m.clear();
+        std::vector<int> roots;
+        std::vector<int> q;
+        for (int r = 0; r < nI; r++) {
+            if (w.vis_i[r]) continue;
+            const int label = v->indiv_cc[r];
+            if (w.label_seen[label]) { rc = fail(PF_EINVAL, "component label %d covers individuals that are not connected (slot %d)", label, v->indiv[r]); goto cleanup; }
+            w.label_seen[label] = 1;
+            roots.push_back(r);
+            w.vis_i[r] = 1;
+            q.clear(); q.push_back(r);
+            for (size_t h = 0; h < q.size(); h++) {
+                const int i = q[h];
+                const int di = w.Ui[i] < 0 ? 0 : w.depth_m[w.Ui[i]] + 1;
+                for (int a = w.adj_off[i]; a < w.adj_off[i + 1]; a++) {
+                    const int m = w.adj_m[a];
+                    if (m == w.Ui[i]) continue;                        // the edge we arrived by
+                    if (w.vis_m[m]) { rc = fail(PF_ECYCLE, "the graph view contains a loop through marriage %d", v->marr[m]); goto cleanup; }
+                    w.vis_m[m] = 1; w.um[m] = i; w.urole[m] = w.adj_role[a]; w.depth_m[m] = di;
+                    w.bfs_m.push_back(m);
+                    for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                        const int y = w.mem_i[k];
+                        if (y == i && w.mem_role[k] == w.adj_role[a]) continue;
+                        if (w.vis_i[y]) { rc = fail(PF_ECYCLE, "the graph view contains a loop through individual %d", v->indiv[y]); goto cleanup; }
+                        if (v->indiv_cc[y] != label) { rc = fail(PF_EINVAL, "individuals %d and %d are connected but carry different component labels", v->indiv[i], v->indiv[y]); goto cleanup; }
+                        w.vis_i[y] = 1; w.Ui[y] = m;
+                        q.push_back(y);
+                    }
+                }
+            }
+        }
+        // heights of the FAMILY_UP tasks, children first (reverse BFS order)
+        int up_levels = 0;
+        for (int b = (int)w.bfs_m.size() - 1; b >= 0; b--) {
+            const int m = w.bfs_m[b];
+            int lv = 0;
+            for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                const int x = w.mem_i[k];
+                if (x == w.um[m]) continue;
+                for (int a = w.adj_off[x]; a < w.adj_off[x + 1]; a++)
+                    if (w.adj_m[a] != m) lv = std::max(lv, w.lvlA[w.adj_m[a]] + 1);
+            }
+            w.lvlA[m] = lv;
+            up_levels = std::max(up_levels, lv + 1);
+        }
+        max_up_levels = std::max(max_up_levels, up_levels);
+
+        // scratch rows
+        int ns = plan.n_scratch;
+        for (int m = 0; m < nM; m++) w.up_m_row[m] = SCRATCH_BIT | ns++;
+        for (int i = 0; i < nI; i++) {
+            if (w.Ui[i] < 0) continue;
+            w.up_i_row[i] = SCRATCH_BIT | ns++;
+            if (w.adj_off[i + 1] - w.adj_off[i] > 1) w.dn_row[i] = SCRATCH_BIT | ns++;
+        }
+        plan.n_scratch = ns;
+
+        // emit tasks component by component (BFS order keeps a component's tasks contiguous)
+        // ROOT tasks: level -1 = "first level of the down band" (or level 0 for singletons)
+        std::vector<int> &pool = plan.pool;
+        auto below_rows = [&](int x, int except_m) {
+            int n = 0;
+            const size_t at = pool.size();
+            pool.push_back(0);
+            for (int a = w.adj_off[x]; a < w.adj_off[x + 1]; a++) {
+                const int m2 = w.adj_m[a];
+                if (m2 == except_m || m2 == w.Ui[x]) continue;
+                pool.push_back(w.up_m_row[m2]); n++;
+            }
+            pool[at] = n;
+        };
+        size_t bfs_pos = 0;
+        // marriages of a component are contiguous in bfs_m, in root order
+        for (size_t ri = 0; ri < roots.size(); ri++) {
+            const int r = roots[ri];
+            comp_task_begin.push_back((int)plan.tasks.size());
+            const bool has_m = w.adj_off[r + 1] > w.adj_off[r];
+            PlanTask tr{0, has_m ? -1 : 0, TASK_ROOT, (int)pool.size()};
+            pool.push_back(v->indiv[r]); pool.push_back(v->indiv_founder[r] ? 1 : 0);
+            pool.push_back(e->stub_row(chain, v->indiv[r])); pool.push_back(out_base + v->indiv_cc[r]);
+            below_rows(r, -1);
+            plan.tasks.push_back(tr);
+            // marriages whose root is r: walk bfs_m until a marriage of another component shows up
+            while (bfs_pos < w.bfs_m.size()) {
+                const int m = w.bfs_m[bfs_pos];
+                // component membership: follow um upward is O(depth); use label instead
+                if (v->indiv_cc[w.um[m]] != v->indiv_cc[r]) break;
+                bfs_pos++;
+                const int flags = (v->marr_selfing[m] ? 1 : 0) | (w.urole[m] << 1);
+                const int u = w.um[m];
+                // FAMILY_UP
+                PlanTask tu{0, w.lvlA[m], TASK_FAMILY_UP, (int)pool.size()};
+                pool.push_back(flags); pool.push_back(w.up_m_row[m]);
+                const size_t nd_at = pool.size(); pool.push_back(0);
+                int nd = 0;
+                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                    const int x = w.mem_i[k];
+                    if (x == u) continue;
+                    pool.push_back(w.mem_role[k]); pool.push_back(v->indiv[x]); pool.push_back(v->indiv_founder[x] ? 1 : 0);
+                    pool.push_back(w.up_i_row[x]);
+                    below_rows(x, m);
+                    nd++;
+                }
+                pool[nd_at] = nd;
+                plan.tasks.push_back(tu);
+                // FAMILY_DOWN: level = -(2 + depth) marks the down band
+                PlanTask td{0, -(2 + w.depth_m[m]), TASK_FAMILY_DOWN, (int)pool.size()};
+                pool.push_back(flags); pool.push_back(e->prong_row(chain, v->marr[m]));
+                pool.push_back(v->indiv[u]); pool.push_back(v->indiv_founder[u] ? 1 : 0);
+                pool.push_back(w.Ui[u] < 0 ? -1 : w.dn_row[u]);
+                below_rows(u, m);
+                pool.push_back(nd);
+                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                    const int x = w.mem_i[k];
+                    if (x == u) continue;
+                    pool.push_back(w.mem_role[k]); pool.push_back(w.up_i_row[x]);
+                    pool.push_back(e->stub_row(chain, v->indiv[x])); pool.push_back(w.dn_row[x]);
+                }
+                plan.tasks.push_back(td);
+            }
+        }
+        if (bfs_pos != w.bfs_m.size()) { rc = fail(PF_EINVAL, "internal: marriage ordering"); goto cleanup; }
+        for (int m = 0; m < nM; m++)
+            if (!w.vis_m[m]) { rc = fail(PF_EINVAL, "marriage %d not reachable", v->marr[m]); goto cleanup; }
+    }
+cleanup:
+    for (int i = 0; i < registered; i++) e->loc[v->indiv[i]] = -1;
+    return rc;
+}
+
+// Upload the plan and launch sweep + reduce. out_dev receives n_out doubles.
+static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph_view *views, double *out_dev, int *n_out_total)
+{
+    CU(cudaSetDevice(e->cfg.device));
+    Plan plan;
+    int max_up = 0;
+    std::vector<int> comp_begin;
+    int out_base = 0;
+    for (int i = 0; i < n; i++) {
+        int rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up, comp_begin);
+        if (rc) return rc;
+        out_base += views[i].n_cc;
+    }
+    plan.n_out = out_base;
+    *n_out_total = out_base;
+    if (plan.tasks.empty()) return PF_OK;
+    comp_begin.push_back((int)plan.tasks.size());
+
+    // levels: up band [0, max_up), down band starts at max_up
+    int n_levels = 1;
+    for (auto &t : plan.tasks) {
+        if (t.level == -1) t.level = max_up;
+        else if (t.level <= -2) t.level = max_up + (-t.level - 2);
+        n_levels = std::max(n_levels, t.level + 1);
+    }
+    // groups: split whole components over thread-block groups so large sweeps fill the GPU
+    const int n_tiles = (e->Sl + TILE_LOCI - 1) / TILE_LOCI;
+    const int n_comp = (int)comp_begin.size() - 1;
+    const int total = (int)plan.tasks.size();
+    int G = std::min(n_comp, std::max(1, std::min((592 + n_tiles - 1) / n_tiles, total / 8)));
+    G = std::max(1, std::min(G, 65535));
+    for (int c = 0; c < n_comp; c++) {
+        const int g = (int)(((long long)comp_begin[c] * G) / total);
+        for (int t = comp_begin[c]; t < comp_begin[c + 1]; t++) plan.tasks[t].group = g;
+    }
+    plan.n_groups = G; plan.n_levels = n_levels;
+
+    // counting sort by (group, level)
+    std::vector<int> level_off((size_t)G * (n_levels + 1) + 1, 0);
+    for (auto &t : plan.tasks) level_off[(size_t)t.group * (n_levels + 1) + t.level + 1]++;
+    // per group prefix, with the group's base added
+    std::vector<int> start((size_t)G * n_levels, 0);
+    {
+        int base = 0;
+        for (int g = 0; g < G; g++) {
+            int *lo = &level_off[(size_t)g * (n_levels + 1)];
+            int run = base;
+            for (int l = 0; l < n_levels; l++) { const int c = lo[l + 1]; start[(size_t)g * n_levels + l] = run; lo[l] = run; run += c; }
+            lo[n_levels] = run;
+            base = run;
+        }
+    }
+    const size_t bytes_tasks = plan.tasks.size() * sizeof(SweepTask);
+    const size_t bytes_pool = plan.pool.size() * sizeof(int);
+    const size_t bytes_loff = (size_t)G * (n_levels + 1) * sizeof(int);
+    const size_t off_pool = (bytes_tasks + 15) & ~(size_t)15;
+    const size_t off_loff = (off_pool + bytes_pool + 15) & ~(size_t)15;
+    const size_t blob = off_loff + bytes_loff;
+
+    void *hp = nullptr; int slot = 0;
+    CU(e->staging.get(blob, &hp, &slot));
+    SweepTask *ht = static_cast<SweepTask *>(hp);
+    for (auto &t : plan.tasks) {
+        const int pos = start[(size_t)t.group * n_levels + t.level]++;
+        ht[pos].kind = t.kind; ht[pos].off = t.off;
+    }
+    memcpy(static_cast<char *>(hp) + off_pool, plan.pool.data(), bytes_pool);
+    memcpy(static_cast<char *>(hp) + off_loff, level_off.data(), bytes_loff);
+
+    int rc = sync_tables(e);
+    if (rc) return rc;
+    CU(e->plan.reserve(blob));
+    CU(e->scratch.reserve((size_t)plan.n_scratch * e->row_elems() * sizeof(double)));
+    CU(e->partial.reserve((size_t)n_tiles * std::max(plan.n_out, 1) * sizeof(double)));
+    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    CU(e->staging.mark(slot, e->stream));
+
+    SweepParams P;
+    P.D = dev_view(e);
+    P.tasks = reinterpret_cast<const SweepTask *>(e->plan.p);
+    P.pool = reinterpret_cast<const int *>(static_cast<char *>(e->plan.p) + off_pool);
+    P.level_off = reinterpret_cast<const int *>(static_cast<char *>(e->plan.p) + off_loff);
+    P.n_groups = G; P.n_levels = n_levels;
+    P.partial = static_cast<double *>(e->partial.p);
+    P.n_out = plan.n_out;
+    launch_sweep(P, n_tiles, e->stream);
+    e->launches++;
+    CU(cudaGetLastError());
+    if (plan.n_out > 0) {
+        ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_tiles, plan.n_out};
+        launch_reduce(R, e->stream);
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return PF_OK;
+}
+
+static int fetch_result(pf_engine *e, double *host_out, int n)
+{
+    if (n <= 0) { CU(cudaStreamSynchronize(e->stream)); return PF_OK; }
+    if ((size_t)n * sizeof(double) > e->h_result_cap) {
+        if (e->h_result) cudaFreeHost(e->h_result);
+        e->h_result = nullptr; e->h_result_cap = 0;
+        const size_t want = (size_t)n * sizeof(double) * 2 + 4096;
+        CU(cudaMallocHost(&e->h_result, want));
+        e->h_result_cap = want;
+    }
+    CU(cudaMemcpyAsync(e->h_result, e->result.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    memcpy(host_out, e->h_result, (size_t)n * sizeof(double));
+    return PF_OK;
+}
+
+static int total_cc(int n, const pf_graph_view *views)
+{
+    long long t = 0;
+    for (int i = 0; i < n; i++) t += views[i].n_cc > 0 ? views[i].n_cc : 0;
+    return (int)t;
+}
+
+extern "C" int pf_sweep_batch(pf_engine *e, int32_t n, const int32_t *chains, const pf_graph_view *views, double *ll_cc)
+{
+    if (!e || !views || n < 0) return fail(PF_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    const int tot = total_cc(n, views);
+    if (tot > 0 && !ll_cc) return fail(PF_EINVAL, "null output");
+    CU(e->result.reserve((size_t)std::max(tot, 1) * sizeof(double)));
+    int n_out = 0;
+    int rc = run_sweeps(e, n, chains, views, static_cast<double *>(e->result.p), &n_out);
+    if (rc) return rc;
+    return fetch_result(e, ll_cc, n_out);
+}
+
+extern "C" int pf_sweep(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc)
+{
+    return pf_sweep_batch(e, 1, &chain, view, ll_cc);
+}
+
+extern "C" int pf_sweep_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc_dev)
+{
+    if (!e || !view) return fail(PF_EINVAL, "null argument");
+    int n_out = 0;
+    return run_sweeps(e, 1, &chain, view, ll_cc_dev, &n_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Proposal evaluation
+
+static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *kids, const int32_t *prop_begin,
+                     const pf_proposal *props, double *out_dev)
+{
+    CU(cudaSetDevice(e->cfg.device));
+    const int n_props = prop_begin[n];
+    if (n_props <= 0) return PF_OK;
+    int n_groups = 0;
+    for (int i = 0; i < n; i++) {
+        const int c = prop_begin[i + 1] - prop_begin[i];
+        if (c < 0) return fail(PF_EINVAL, "prop_begin not monotone");
+        n_groups += (c + EVAL_G - 1) / EVAL_G;
+    }
+    const size_t bytes_groups = (size_t)n_groups * sizeof(EvalGroup);
+    const size_t off_props = (bytes_groups + 15) & ~(size_t)15;
+    const size_t blob = off_props + (size_t)n_props * sizeof(EvalProp);
+    void *hp = nullptr; int slot = 0;
+    CU(e->staging.get(blob, &hp, &slot));
+    EvalGroup *hg = static_cast<EvalGroup *>(hp);
+    EvalProp *hq = reinterpret_cast<EvalProp *>(static_cast<char *>(hp) + off_props);
+    int gi = 0;
+    for (int i = 0; i < n; i++) {
+        const int chain = chains ? chains[i] : 0, kid = kids[i];
+        if (chain < 0 || chain >= e->cfg.n_chains) return fail(PF_EINVAL, "chain %d out of range", chain);
+        if (kid < 0 || kid >= e->cfg.cap_indiv) return fail(PF_EINVAL, "kid slot %d out of range", kid);
+        for (int p = prop_begin[i]; p < prop_begin[i + 1]; p++) {
+            const pf_proposal &q = props[p];
+            EvalProp d{q.kind, ROW_PRIOR, ROW_PRIOR, 0};
+            if (q.kind == PF_PROP_TRIO || q.kind == PF_PROP_SELFING) {
+                if (q.pa < -1 || q.pa >= e->cfg.cap_indiv || q.ma < -1 || q.ma >= e->cfg.cap_indiv)
+                    return fail(PF_EINVAL, "proposal %d: parent slot out of range", p);
+                if (q.pa >= 0) d.row_p = e->stub_row(chain, q.pa);
+                if (q.kind == PF_PROP_TRIO && q.ma >= 0) d.row_m = e->stub_row(chain, q.ma);
+            } else if (q.kind == PF_PROP_PRONG) {
+                if (q.marr < 0 || q.marr >= e->cfg.cap_marr) return fail(PF_EINVAL, "proposal %d: marriage slot out of range", p);
+                d.row_p = e->prong_row(chain, q.marr);
+            } else return fail(PF_EINVAL, "proposal %d: unknown kind %d", p, q.kind);
+            hq[p] = d;
+        }
+        for (int b = prop_begin[i]; b < prop_begin[i + 1]; b += EVAL_G)
+            hg[gi++] = EvalGroup{e->stub_row(chain, kid), b, std::min(EVAL_G, prop_begin[i + 1] - b), 0};
+    }
+    // chunking: enough (chunk x group-block) CTAs to fill the GPU, at most 16 lane-iterations per chunk
+    const int group_blocks = (n_groups + EVAL_WARPS - 1) / EVAL_WARPS;
+    int want_chunks = std::max(1, (592 + group_blocks - 1) / group_blocks);
+    int chunk_loci = ((e->Sl + want_chunks - 1) / want_chunks + 31) / 32 * 32;
+    chunk_loci = std::max(32, std::min(chunk_loci, 512));
+    const int n_chunks = (e->Sl + chunk_loci - 1) / chunk_loci;
+
+    int rc = sync_tables(e);
+    if (rc) return rc;
+    CU(e->plan.reserve(blob));
+    CU(e->partial.reserve((size_t)n_chunks * n_props * sizeof(double)));
+    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    CU(e->staging.mark(slot, e->stream));
+    EvalParams P;
+    P.D = dev_view(e);
+    P.groups = reinterpret_cast<const EvalGroup *>(e->plan.p);
+    P.props = reinterpret_cast<const EvalProp *>(static_cast<char *>(e->plan.p) + off_props);
+    P.n_groups = n_groups; P.n_props = n_props; P.chunk_loci = chunk_loci;
+    P.partial = static_cast<double *>(e->partial.p);
+    launch_eval(P, n_chunks, e->stream);
+    e->launches++;
+    CU(cudaGetLastError());
+    ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_chunks, n_props};
+    launch_reduce(R, e->stream);
+    e->launches++;
+    CU(cudaGetLastError());
+    return PF_OK;
+}
+
+extern "C" int pf_eval_batch(pf_engine *e, int32_t n, const int32_t *chains, const int32_t *kids,
+                             const int32_t *prop_begin, const pf_proposal *props, double *lsum)
+{
+    if (!e || n < 0 || !kids || !prop_begin) return fail(PF_EINVAL, "null argument");
+    const int n_props = prop_begin[n];
+    if (n_props > 0 && (!props || !lsum)) return fail(PF_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(e->result.reserve((size_t)std::max(n_props, 1) * sizeof(double)));
+    int rc = run_evals(e, n, chains, kids, prop_begin, props, static_cast<double *>(e->result.p));
+    if (rc) return rc;
+    return fetch_result(e, lsum, n_props);
+}
+
+extern "C" int pf_eval(pf_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_proposal *props, double *lsum)
+{
+    const int32_t pb[2] = {0, n};
+    return pf_eval_batch(e, 1, &chain, &kid, pb, props, lsum);
+}
+
+extern "C" int pf_eval_dev(pf_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_proposal *props, double *lsum_dev)
+{
+    if (!e || n < 0 || (n > 0 && (!props || !lsum_dev))) return fail(PF_EINVAL, "null argument");
+    const int32_t pb[2] = {0, n};
+    return run_evals(e, 1, &chain, &kid, pb, props, lsum_dev);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Prefilter (_RefineParentOffPair@0x100014d20)
+
+extern "C" int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                            const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
+                            const double *cand_bias, int32_t top_k, int32_t *out_slot, double *out_score)
+{
+    if (!e || n_kids < 0 || n_cands < 0 || !kids || !as_father || !out_slot || !out_score) return fail(PF_EINVAL, "null argument");
+    if (n_cands > 0 && !cands) return fail(PF_EINVAL, "null candidates");
+    if (top_k <= 0 || top_k > PREF_MAX_TOPK) return fail(PF_EINVAL, "top_k must be in [1, %d]", PREF_MAX_TOPK);
+    if (chain < 0 || chain >= e->cfg.n_chains) return fail(PF_EINVAL, "chain %d out of range", chain);
+    if (e->Sl != e->cfg.n_loci) return fail(PF_EINVAL, "pf_prefilter needs an unsharded engine (ranking requires all loci)");
+    CU(cudaSetDevice(e->cfg.device));
+    if (n_kids == 0) return PF_OK;
+    for (int k = 0; k < n_kids; k++)
+        if (kids[k] < 0 || kids[k] >= e->cfg.cap_indiv) return fail(PF_EINVAL, "kid slot %d out of range", kids[k]);
+    for (int j = 0; j < n_cands; j++)
+        if (cands[j] < 0 || cands[j] >= e->cfg.cap_indiv) return fail(PF_EINVAL, "candidate slot %d out of range", cands[j]);
+    int rc = sync_tables(e);
+    if (rc) return rc;
+
+    // device inputs: kid rows, candidate rows, bias
+    const size_t b_kid = (size_t)n_kids * sizeof(int), b_cand = (size_t)n_cands * sizeof(int);
+    const size_t o_cand = (b_kid + 15) & ~(size_t)15, o_bias = (o_cand + b_cand + 15) & ~(size_t)15;
+    const size_t blob = o_bias + (size_t)n_cands * sizeof(double);
+    void *hp = nullptr; int slot = 0;
+    CU(e->staging.get(blob, &hp, &slot));
+    char *h = static_cast<char *>(hp);
+    int *hk = reinterpret_cast<int *>(h), *hc = reinterpret_cast<int *>(h + o_cand);
+    double *hbias = reinterpret_cast<double *>(h + o_bias);
+    for (int k = 0; k < n_kids; k++) hk[k] = e->stub_row(chain, kids[k]);
+    for (int j = 0; j < n_cands; j++) { hc[j] = e->stub_row(chain, cands[j]); hbias[j] = cand_bias ? cand_bias[j] : 0.0; }
+    CU(e->plan.reserve(blob));
+    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    CU(e->staging.mark(slot, e->stream));
+
+    const size_t out_bytes = (size_t)n_kids * top_k * (sizeof(double) + sizeof(int));
+    CU(e->result.reserve(out_bytes));
+    CU(e->partial.reserve(std::max<size_t>((size_t)n_kids * n_cands, 1) * sizeof(double)));
+    PrefilterParams P;
+    P.D = dev_view(e);
+    char *d = static_cast<char *>(e->plan.p);
+    P.kid_rows = reinterpret_cast<const int *>(d);
+    P.cand_rows = reinterpret_cast<const int *>(d + o_cand);
+    P.cand_bias = reinterpret_cast<const double *>(d + o_bias);
+    P.n_kids = n_kids; P.n_cands = n_cands; P.top_k = top_k;
+    P.scores = static_cast<double *>(e->partial.p);
+    P.out_score = static_cast<double *>(e->result.p);
+    P.out_idx = reinterpret_cast<int *>(static_cast<char *>(e->result.p) + (size_t)n_kids * top_k * sizeof(double));
+    e->launches += launch_prefilter(P, e->stream);
+    CU(cudaGetLastError());
+
+    std::vector<char> hout(out_bytes);
+    CU(cudaMemcpyAsync(hout.data(), e->result.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    const double *sc = reinterpret_cast<const double *>(hout.data());
+    const int *ix = reinterpret_cast<const int *>(hout.data() + (size_t)n_kids * top_k * sizeof(double));
+    for (int k = 0; k < n_kids; k++)
+        for (int t = 0; t < top_k; t++) {
+            const int j = ix[(size_t)k * top_k + t];
+            out_slot[(size_t)k * top_k + t] = j < 0 ? -1 : cands[j];
+            out_score[(size_t)k * top_k + t] = j < 0 ? -INFINITY : sc[(size_t)k * top_k + t];
+        }
+    return PF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Read-back
+
+static int get_row(pf_engine *e, int row, double *out)
+{
+    CU(cudaSetDevice(e->cfg.device));
+    std::vector<double> buf(e->row_elems());
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaMemcpy(buf.data(), e->d_rows + (size_t)row * e->row_elems(), buf.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int s = 0; s < e->Sl; s++)
+        for (int g = 0; g < 3; g++) out[(size_t)s * 3 + g] = buf[(size_t)g * e->Sp + s];
+    return PF_OK;
+}
+
+extern "C" int pf_get_stub(pf_engine *e, int32_t chain, int32_t slot, double *out)
+{
+    if (!e || !out) return fail(PF_EINVAL, "null argument");
+    if (chain < 0 || chain >= e->cfg.n_chains || slot < 0 || slot >= e->cfg.cap_indiv) return fail(PF_EINVAL, "index out of range");
+    return get_row(e, e->stub_row(chain, slot), out);
+}
+
+extern "C" int pf_get_prong(pf_engine *e, int32_t chain, int32_t marr, double *out)
+{
+    if (!e || !out) return fail(PF_EINVAL, "null argument");
+    if (chain < 0 || chain >= e->cfg.n_chains || marr < 0 || marr >= e->cfg.cap_marr) return fail(PF_EINVAL, "index out of range");
+    return get_row(e, e->prong_row(chain, marr), out);
+}

@@ -1,0 +1,308 @@
+"""GPU parity tests (-m gpu): libpedfac_cuda through its C ABI against the CPU oracle on the same
+seeded inputs, against exhaustive enumeration, against the golden known answers, and — at the
+BASELINE.json sizes — through size-independent properties.
+
+Tolerances (fp64 path; north_star: per-proposal log-likelihoods within 1e-9 relative):
+  * stubs / prongs (raw message products):        1e-12 relative
+  * data terms lsum and component LLs:            1e-12 relative (+1e-11 absolute near 0)
+The GPU multiplies messages in a different association order and takes one log per chunk of
+loci instead of one per locus, so bit equality is not expected; 1e-12 is ~4 decimal digits
+tighter than the bar."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import checks
+from oracle.binding import OracleEngine
+from pedfac_b200 import (PF_PROP_PRONG, PF_PROP_SELFING, PF_PROP_TRIO, Engine, GraphView, PedfacError,
+                         Pedigree, compose_ll, synth)
+from scenarios import random_forest
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).parent / "golden"
+
+
+def test_golden_known_answers_on_gpu():
+    k = json.loads((GOLDEN / "survey_appendix_e.json").read_text())
+    e = Engine(1, 8, 4)
+    e.set_locus_params([0.02], [0.3])
+    ped = Pedigree(8, 4)
+    for slot, (code, founder) in enumerate([(0, True), (2, True), (1, False)]):
+        ped.add_individual(slot, founder)
+        e.set_hard(slot, [code])
+    view, _ = ped.view()
+    llcc = e.sweep(view)
+    np.testing.assert_allclose(llcc, k["kat1"]["ll_cc"], rtol=1e-13, atol=1e-15)
+    lltot = float(np.sum(llcc))
+    lsum = e.eval(2, [(PF_PROP_TRIO, 0, 1, -1), (PF_PROP_TRIO, -1, -1, -1), (PF_PROP_TRIO, 0, -1, -1)])
+    ll = [compose_ll(lltot, lsum[0], llcc[2], True, llcc[0], True, llcc[1]),
+          compose_ll(lltot, lsum[1], llcc[2], False, 0.0, False, 0.0),
+          compose_ll(lltot, lsum[2], llcc[2], True, llcc[0], False, 0.0)]
+    np.testing.assert_allclose(ll, [k["kat1"]["ll_pa_ma"], k["kat1"]["ll_new_new"], k["kat1"]["ll_pa_new"]], rtol=1e-13)
+    # KAT 2: family + joining kid
+    e = Engine(1, 8, 4)
+    e.set_locus_params([0.02], [0.3])
+    ped = Pedigree(8, 4)
+    ped.add_individual(0, True); e.set_hard(0, [0])
+    ped.add_individual(1, True); e.set_hard(1, [2])
+    ped.add_individual(2, False); e.set_hard(2, [1])
+    ped.add_individual(3, False); e.set_soft(3, [[0.1, 0.7, 0.2]], "f64")
+    ped.add_individual(4, False); e.set_hard(4, [2])
+    ped.add_marriage(0, 0, 1, [2, 3])
+    view, _ = ped.view()
+    llcc = e.sweep(view)
+    np.testing.assert_allclose(llcc[0], k["kat2"]["ll_cc_family"], rtol=1e-13)
+    for slot, name in [(0, "pa"), (1, "ma"), (2, "k1"), (3, "k2")]:
+        np.testing.assert_allclose(e.get_stub(slot)[0], k["kat2"]["stub_" + name], rtol=1e-12)
+    np.testing.assert_allclose(e.get_prong(0)[0], k["kat2"]["prong"], rtol=1e-12)
+    np.testing.assert_allclose(e.eval(4, [(PF_PROP_PRONG, -1, -1, 0)])[0], k["kat2"]["contraction_prong_k3"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_gpu_matches_bruteforce(seed):
+    rng = np.random.default_rng(300 + seed)
+    sc = random_forest(rng, n_indiv=int(rng.integers(3, 12)), S=3, max_kids=3,
+                       p_selfing=0.2 if seed % 3 == 0 else 0.0, max_comp=8)
+    e = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(e)
+    checks.check_sweep_against_bruteforce(e, sc)
+    sc2 = random_forest(rng, n_indiv=10, S=2, max_kids=2, n_marr_target=3, p_selfing=0.25, max_comp=3)
+    e2 = Engine(sc2.S, sc2.ped.cap_indiv, sc2.ped.cap_marr)
+    sc2.upload(e2)
+    assert checks.check_eval_against_bruteforce(e2, sc2, rng) > 0
+
+
+@pytest.mark.parametrize("seed,n_indiv,S,max_kids,p_self", [
+    (0, 1, 1, 1, 0.0), (1, 2, 5, 1, 0.0), (2, 12, 31, 3, 0.0), (3, 40, 33, 4, 0.1), (4, 120, 64, 6, 0.05),
+    (5, 300, 65, 5, 0.0), (6, 64, 257, 12, 0.0), (7, 500, 100, 3, 0.02)])
+def test_gpu_matches_oracle_random_forests(seed, n_indiv, S, max_kids, p_self):
+    """Ragged sizes: S around the 32-locus tile and 64-locus padding edges, deep and wide families."""
+    rng = np.random.default_rng(400 + seed)
+    sc = random_forest(rng, n_indiv=n_indiv, S=S, max_kids=max_kids, p_selfing=p_self)
+    g = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    o = OracleEngine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(g); sc.upload(o)
+    checks.check_engines_agree(g, o, sc, rng)
+
+
+def test_gpu_incremental_sweeps_follow_graph_edits():
+    """Prune a kid, sweep only the dirty components, re-attach elsewhere: the sequence of calls a
+    Gibbs step makes (_MCMC_sampling@0x100019ec0) must track the oracle step by step."""
+    rng = np.random.default_rng(77)
+    sc = random_forest(rng, n_indiv=60, S=48, max_kids=4)
+    g = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    o = OracleEngine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(g); sc.upload(o)
+    checks.check_engines_agree(g, o, sc, rng)
+    kids = sorted({k for mm in sc.ped.marriages.values() for k in mm.kids})
+    for kid in kids[:12]:
+        old_label = sc.ped.components()[0][kid]
+        pa, ma, m = sc.ped.detach_kid(kid)
+        labels, _ = sc.ped.components()
+        dirty = {int(labels[kid]), int(labels[pa]), int(labels[ma])}
+        checks.check_engines_agree(g, o, sc, rng, dirty=dirty, n_kids=3)
+        if m is None:
+            m = max(list(sc.ped.marriages) + [-1]) + 1
+            sc.ped.add_marriage(m, pa, ma, [kid], selfing=(pa == ma))
+        else:
+            sc.ped.marriages[m].kids.append(kid)
+        labels, _ = sc.ped.components()
+        checks.check_engines_agree(g, o, sc, rng, dirty={int(labels[kid])}, n_kids=2)
+
+
+def test_gpu_locus_shards_add_up_to_the_unsharded_engine():
+    rng = np.random.default_rng(9)
+    sc = random_forest(rng, n_indiv=50, S=150, max_kids=4)
+    full = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    parts = [Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr, locus_range=r) for r in [(0, 37), (37, 101), (101, 150)]]
+    view, _ = sc.ped.view()
+    for e in [full] + parts:
+        sc.upload(e)
+    want = full.sweep(view)
+    np.testing.assert_allclose(sum(p.sweep(view) for p in parts), want, rtol=1e-12)
+    props = [(PF_PROP_TRIO, 1, 2, -1), (PF_PROP_TRIO, -1, 3, -1), (PF_PROP_SELFING, 4, -1, -1)]
+    np.testing.assert_allclose(sum(p.eval(0, props) for p in parts), full.eval(0, props), rtol=1e-12)
+    np.testing.assert_array_equal(np.concatenate([p.get_stub(5) for p in parts]), full.get_stub(5))
+
+
+def test_gpu_multi_chain_batches_match_single_chain_oracles():
+    rng = np.random.default_rng(11)
+    scs = [random_forest(np.random.default_rng(500 + c), n_indiv=30, S=40, max_kids=3) for c in range(3)]
+    # same genotype data for all chains, different graphs: reuse scenario 0's data
+    base = scs[0]
+    cap_i = max(s.ped.cap_indiv for s in scs); cap_m = max(s.ped.cap_marr for s in scs)
+    g = Engine(base.S, cap_i, cap_m, n_chains=3)
+    base.upload(g)
+    os_ = []
+    for sc in scs:
+        o = OracleEngine(base.S, cap_i, cap_m)
+        base.upload(o)
+        os_.append(o)
+    views = [sc.ped.view()[0] for sc in scs]
+    got = g.sweep_batch([0, 1, 2], views)
+    want = np.concatenate([o.sweep(v) for o, v in zip(os_, views)])
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12)
+    kids, pb, props = [], [0], []
+    for c in range(3):
+        kids.append(int(rng.integers(0, 30)))
+        for _ in range(int(rng.integers(1, 9))):
+            props.append((PF_PROP_TRIO, int(rng.integers(-1, 30)), int(rng.integers(-1, 30)), -1))
+        pb.append(len(props))
+    got = g.eval_batch([0, 1, 2], kids, pb, props)
+    want = np.concatenate([os_[c].eval(kids[c], props[pb[c]:pb[c + 1]]) for c in range(3)])
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-11)
+    for c in range(3):
+        np.testing.assert_allclose(g.get_stub(7, chain=c), os_[c].get_stub(7), rtol=1e-12)
+
+
+def test_gpu_zero_likelihoods_give_minus_infinity_like_the_reference():
+    """eps = 0 makes Mendelian-impossible trios exactly 0: log(0) = -inf in the reference; the
+    product-accumulating kernels must not turn that into a finite number or nan."""
+    S = 40
+    g = Engine(S, 4, 2); o = OracleEngine(S, 4, 2)
+    for e in (g, o):
+        e.set_locus_params(np.zeros(S), np.full(S, 0.25))
+        e.set_hard(0, np.zeros(S, np.uint8)); e.set_hard(1, np.zeros(S, np.uint8)); e.set_hard(2, np.full(S, 2, np.uint8))
+    ped = Pedigree(4, 2)
+    for i in range(3):
+        ped.add_individual(i, i < 2)
+    view, _ = ped.view()
+    np.testing.assert_allclose(g.sweep(view), o.sweep(view), rtol=1e-12)
+    props = [(PF_PROP_TRIO, 0, 1, -1), (PF_PROP_TRIO, 0, -1, -1), (PF_PROP_TRIO, -1, -1, -1)]
+    a, b = g.eval(2, props), o.eval(2, props)
+    assert a[0] == -np.inf and b[0] == -np.inf and a[1] == -np.inf and b[1] == -np.inf
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-12)
+
+
+def test_gpu_tiny_values_do_not_underflow_in_the_log_product():
+    """Unnormalised stubs shrink geometrically with component size: feed values
+    around 1e-290 and check the log path agrees with the oracle."""
+    S = 70
+    g = Engine(S, 4, 2); o = OracleEngine(S, 4, 2)
+    lik = np.full((S, 3), 1e-290); lik[:, 1] = 3e-291
+    for e in (g, o):
+        e.set_locus_params(np.full(S, 0.01), np.full(S, 0.3))
+        e.set_soft(0, lik, "f64"); e.set_hard(1, np.ones(S, np.uint8))
+    ped = Pedigree(4, 2)
+    ped.add_individual(0, True); ped.add_individual(1, False)
+    view, _ = ped.view()
+    np.testing.assert_allclose(g.sweep(view), o.sweep(view), rtol=1e-13)
+    np.testing.assert_allclose(g.eval(1, [(PF_PROP_TRIO, 0, -1, -1)]), o.eval(1, [(PF_PROP_TRIO, 0, -1, -1)]), rtol=1e-13)
+
+
+def test_gpu_rejects_bad_views_like_the_oracle():
+    e = Engine(4, 6, 4)
+    e.set_locus_params(np.full(4, 0.02), np.full(4, 0.3))
+    ped = Pedigree(6, 4)
+    for i in range(4):
+        ped.add_individual(i, i < 2)
+    ped.add_marriage(0, 0, 1, [2, 3])
+    ped.add_marriage(1, 2, 3, [])
+    view, _ = ped.view(labels=np.zeros(6, np.int32))
+    with pytest.raises(PedfacError) as ei:
+        e.sweep(view)
+    assert ei.value.code == -5
+    open_view = GraphView([0, 1], [0, 0], [1, 1], [0], [0], [1], [0], [0, 1], [2], 1)
+    with pytest.raises(PedfacError) as ei:
+        e.sweep(open_view)
+    assert ei.value.code == -1
+    with pytest.raises(PedfacError):
+        e.set_hard(0, np.array([0, 1, 2, 7], np.uint8))
+    empty = GraphView([], [], [], [], [], [], [], [0], [], 0)
+    assert len(e.sweep(empty)) == 0 and len(e.eval(0, [])) == 0
+
+
+def test_gpu_prefilter_matches_oracle():
+    rng = np.random.default_rng(5)
+    sc = random_forest(rng, n_indiv=90, S=130, n_marr_target=0, kinds=("hard", "dec16", "f32"))
+    g = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr); o = OracleEngine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(g); sc.upload(o)
+    view, _ = sc.ped.view()
+    llcc = o.sweep(view); g.sweep(view)
+    kids = list(range(0, 70)); cands = list(range(20, 90))
+    role = rng.integers(0, 2, size=len(kids))
+    bias = -llcc[cands]
+    gs, gv = g.prefilter(kids, role, cands, bias, top_k=15)
+    os_, ov = o.prefilter(kids, role, cands, bias, top_k=15)
+    np.testing.assert_allclose(gv, ov, rtol=1e-12)
+    # ranks may only differ where the oracle's scores tie to 1e-12
+    diff = gs != os_
+    assert diff.mean() < 0.02
+    for k, t in zip(*np.nonzero(diff)):
+        assert abs(ov[k, t] - gv[k, t]) <= 1e-9 * abs(ov[k, t])
+
+
+@pytest.mark.parametrize("name,n,S,soft", [("A_1k_x_500_hard", 1000, 500, False), ("B_5k_x_2k_soft", 5000, 2000, True)])
+def test_gpu_full_size_properties(name, n, S, soft):
+    """BASELINE.json sizes, where the oracle is too slow to be the checker: size-independent
+    properties. (1) additivity over locus shards (a checksum of checksums); (2) the joined-family
+    identity: attaching a kid to its true parents changes the total LL by exactly
+    lsum - LLcc[kid] - LLcc[pa] - LLcc[ma], verified by re-sweeping the edited graph; (3) an
+    oracle spot-check on a bounded sub-sample of individuals and loci."""
+    d = synth.simulate(n, S, soft=soft, seed=46)
+    cap_i, cap_m = d.n_total + 16, d.n_total
+    full = Engine(S, cap_i, cap_m)
+    synth.upload(full, d)
+    ped = synth.truth_pedigree(d, cap_i, cap_m)
+    labels, ncc = ped.components()
+    view, glob = ped.view(labels)
+    ll = full.sweep(view)
+    assert np.isfinite(ll).all()
+    halves = [Engine(S, cap_i, cap_m, locus_range=r) for r in [(0, S // 3), (S // 3, S)]]
+    for h in halves:
+        synth.upload(h, d)
+    np.testing.assert_allclose(sum(h.sweep(view) for h in halves), ll, rtol=1e-12)
+    # (2) detach 20 kids one at a time, evaluate "re-attach to the same marriage" and compare with a re-sweep
+    rng = np.random.default_rng(3)
+    kids_truth = rng.choice(np.flatnonzero(d.pa >= 0), size=20, replace=False)
+    lab_pos = {int(g): j for j, g in enumerate(glob)}
+    for kt in kids_truth:
+        kid = int(d.slot[kt])
+        before = ll[lab_pos[int(labels[kid])]]
+        pa, ma, m = ped.detach_kid(kid)
+        lab2, _ = ped.components()
+        dirty = sorted({int(lab2[kid]), int(lab2[pa]), int(lab2[ma])})
+        v2, g2 = ped.view(lab2, only=dirty)
+        l2 = dict(zip([int(x) for x in g2], full.sweep(v2)))
+        if m is None:
+            prop = (PF_PROP_TRIO, pa, ma, -1)
+        else:
+            prop = (PF_PROP_PRONG, pa, ma, m)
+        lsum = full.eval(kid, [prop])[0]
+        parts = {int(lab2[kid]), int(lab2[pa]), int(lab2[ma])} if m is None else {int(lab2[kid]), int(lab2[pa])}
+        # new component LL = lsum (the data term is the log partition value of the joined component)
+        # restore the graph and re-sweep the same component
+        if m is None:
+            mnew = max(ped.marriages) + 1 if ped.marriages else 0
+            ped.add_marriage(mnew, pa, ma, [kid])
+        else:
+            ped.marriages[m].kids.append(kid)
+        lab3, _ = ped.components()
+        v3, g3 = ped.view(lab3, only=[int(lab3[kid])])
+        after = full.sweep(v3)[0]
+        np.testing.assert_allclose(after, before, rtol=1e-12)
+        np.testing.assert_allclose(lsum, after, rtol=1e-11)
+        assert len(parts) >= 2
+    # (3) oracle spot check: first 64 loci, the 40 individuals of a few small components
+    Ss = 64
+    o = OracleEngine(S, cap_i, cap_m, locus_range=(0, Ss))
+    gsub = Engine(S, cap_i, cap_m, locus_range=(0, Ss))
+    labels, _ = ped.components()
+    sizes = np.bincount(labels[labels >= 0])
+    pick = [int(c) for c in np.argsort(sizes)[::-1][:3]]
+    vs, gl = ped.view(labels, only=pick)
+    for e in (o, gsub):
+        e.set_locus_params(d.eps, d.afreq)
+    for i in np.flatnonzero(d.observed):
+        s = int(d.slot[i])
+        if s in set(vs.indiv.tolist()):
+            for e in (o, gsub):
+                if soft:
+                    e.set_soft(s, d.soft_num[i], "dec16", 10000)
+                else:
+                    e.set_hard(s, d.codes[i])
+    np.testing.assert_allclose(gsub.sweep(vs), o.sweep(vs), rtol=1e-12)
+    for x in vs.indiv[:10]:
+        np.testing.assert_allclose(gsub.get_stub(int(x)), o.get_stub(int(x)), rtol=1e-12)
