@@ -160,6 +160,13 @@ int pf_get_prong(pf_engine *e, int32_t chain, int32_t marr, double *out);
 /* Counters: kernels launched by this engine since creation. */
 int64_t pf_launch_count(const pf_engine *e);
 
+/* Measurement aid: while enabled, every kernel launch is bracketed by CUDA events on the
+ * engine's stream. pf_profile_read synchronises, returns the summed device time in
+ * milliseconds and the launch count per kernel kind (0 sweep, 1 eval, 2 reduce, 3 prefilter;
+ * ms[4], count[4]) and clears the records. */
+int pf_profile(pf_engine *e, int32_t enable);
+int pf_profile_read(pf_engine *e, double *ms, int64_t *count);
+
 /*
  * The scalar bookkeeping the reference wraps around the data term (host, fp64), in the
  * reference's order (_CalculateLikeByStubs@0x10001f5df-0x10001f6ae):

@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "prefilter", "get_stub", "get_prong", "launch_count",
+    "eval_batch", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read",
 ]
 
 
@@ -91,6 +91,8 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("get_stub", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
     sig("get_prong", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
     sig("launch_count", C.c_int64, vp)
+    sig("profile", C.c_int, vp, C.c_int32)
+    sig("profile_read", C.c_int, vp, _f64p, C.POINTER(C.c_int64))
 
 
 _cuda_lib = None
@@ -277,6 +279,17 @@ class CEngine:
         out = np.empty((self.n_local, 3), dtype=np.float64)
         self._check(self._fn("get_prong")(self._h, chain, marr, ptr(out, _f64p)))
         return out
+
+    def profile(self, enable: bool):
+        self._check(self._fn("profile")(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """-> ({kind: ms}, {kind: launches}) for kinds sweep / eval / reduce / prefilter."""
+        ms = np.zeros(4, dtype=np.float64)
+        cnt = np.zeros(4, dtype=np.int64)
+        self._check(self._fn("profile_read")(self._h, ptr(ms, _f64p), ptr(cnt, C.POINTER(C.c_int64))))
+        names = ["sweep", "eval", "reduce", "prefilter"]
+        return dict(zip(names, ms.tolist())), dict(zip(names, cnt.tolist()))
 
     def launch_count(self) -> int:
         fn = getattr(self._lib, self._prefix + "launch_count", None)

@@ -110,6 +110,20 @@ struct pf_engine {
     std::vector<int> loc;                 // slot -> index in the view being planned
     int64_t launches = 0;
 
+    // optional per-launch CUDA-event timing (pf_profile): kind 0 sweep, 1 eval, 2 reduce, 3 prefilter
+    bool prof_on = false;
+    struct ProfRec { int kind; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    void prof_begin(int kind)
+    {
+        if (!prof_on) return;
+        ProfRec r{kind, nullptr, nullptr};
+        cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, stream);
+        prof.push_back(r);
+    }
+    void prof_end() { if (prof_on && !prof.empty()) cudaEventRecord(prof.back().b, stream); }
+
     size_t row_elems() const { return (size_t)3 * Sp; }
     int stub_row(int chain, int slot) const { return ROW_CHAIN0 + chain * (cfg.cap_indiv + cfg.cap_marr) + slot; }
     int prong_row(int chain, int m) const { return ROW_CHAIN0 + chain * (cfg.cap_indiv + cfg.cap_marr) + cfg.cap_indiv + m; }
@@ -203,6 +217,33 @@ extern "C" int pf_set_stream(pf_engine *e, void *cuda_stream)
 }
 
 extern "C" int64_t pf_launch_count(const pf_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int pf_profile(pf_engine *e, int32_t enable)
+{
+    if (!e) return fail(PF_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    for (auto &r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->prof.clear();
+    e->prof_on = enable != 0;
+    return PF_OK;
+}
+
+extern "C" int pf_profile_read(pf_engine *e, double *ms, int64_t *count)
+{
+    if (!e || !ms || !count) return fail(PF_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaStreamSynchronize(e->stream));
+    for (int k = 0; k < 4; k++) { ms[k] = 0.0; count[k] = 0; }
+    for (auto &r : e->prof) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, r.a, r.b));
+        ms[r.kind] += t; count[r.kind]++;
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    e->prof.clear();
+    return PF_OK;
+}
 
 extern "C" int pf_set_locus_params(pf_engine *e, const double *eps, const double *afreq)
 {
@@ -618,12 +659,16 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     P.n_groups = G; P.n_levels = n_levels;
     P.partial = static_cast<double *>(e->partial.p);
     P.n_out = plan.n_out;
+    e->prof_begin(0);
     launch_sweep(P, n_tiles, e->stream);
+    e->prof_end();
     e->launches++;
     CU(cudaGetLastError());
     if (plan.n_out > 0) {
         ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_tiles, plan.n_out};
+        e->prof_begin(2);
         launch_reduce(R, e->stream);
+        e->prof_end();
         e->launches++;
         CU(cudaGetLastError());
     }
@@ -741,11 +786,15 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     P.props = reinterpret_cast<const EvalProp *>(static_cast<char *>(e->plan.p) + off_props);
     P.n_groups = n_groups; P.n_props = n_props; P.chunk_loci = chunk_loci;
     P.partial = static_cast<double *>(e->partial.p);
+    e->prof_begin(1);
     launch_eval(P, n_chunks, e->stream);
+    e->prof_end();
     e->launches++;
     CU(cudaGetLastError());
     ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_chunks, n_props};
+    e->prof_begin(2);
     launch_reduce(R, e->stream);
+    e->prof_end();
     e->launches++;
     CU(cudaGetLastError());
     return PF_OK;
@@ -826,7 +875,9 @@ extern "C" int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const i
     P.scores = static_cast<double *>(e->partial.p);
     P.out_score = static_cast<double *>(e->result.p);
     P.out_idx = reinterpret_cast<int *>(static_cast<char *>(e->result.p) + (size_t)n_kids * top_k * sizeof(double));
+    e->prof_begin(3);
     e->launches += launch_prefilter(P, e->stream);
+    e->prof_end();
     CU(cudaGetLastError());
 
     std::vector<char> hout(out_bytes);

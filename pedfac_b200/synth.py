@@ -37,7 +37,8 @@ class SynthData:
 
 def simulate(n_total: int, n_loci: int, *, soft: bool, seed: int = 46, n_gen: int = 3,
              mean_kids: float = 2.5, geno_err: float = 0.02, observe_frac: float = 0.8,
-             missing_frac: float = 0.02, remate_frac: float = 0.1) -> SynthData:
+             missing_frac: float = 0.02, remate_frac: float = 0.1,
+             max_component: int = 150) -> SynthData:
     rng = np.random.default_rng(seed)
     # generation sizes: each couple has Poisson(mean_kids) kids, so sizes grow by mean_kids/2
     growth = mean_kids / 2.0
@@ -50,6 +51,27 @@ def simulate(n_total: int, n_loci: int, *, soft: bool, seed: int = 46, n_gen: in
     pa = np.full(n_total, -1, np.int32)
     ma = np.full(n_total, -1, np.int32)
     start = np.concatenate([[0], np.cumsum(sizes)])
+    # The sampler's state is always a forest (default -c 0 rejects loop-closing proposals,
+    # _checkMatchingCC@0x1000241b0) and its unnormalised messages underflow fp64 beyond a few
+    # hundred individuals per component, so the synthetic truth is generated
+    # loop-free with bounded components: a couple is formed only across two different components
+    # whose joint size stays below `max_component`.
+    uf = np.arange(n_total)
+    csize = np.ones(n_total, dtype=np.int64)
+
+    def find(x):
+        while uf[x] != x:
+            uf[x] = uf[uf[x]]
+            x = uf[x]
+        return x
+
+    def union(a, b):
+        ra, rb = find(a), find(b)
+        if ra != rb:
+            uf[rb] = ra
+            csize[ra] += csize[rb]
+        return ra
+
     for k in range(n_gen - 1):                                   # parents in block k, kids in block k+1
         par = np.arange(start[k], start[k + 1])
         kids = np.arange(start[k + 1], start[k + 2])
@@ -58,13 +80,32 @@ def simulate(n_total: int, n_loci: int, *, soft: bool, seed: int = 46, n_gen: in
             sex[par[0]], sex[par[-1]] = 1, 2
             males, females = par[sex[par] == 1], par[sex[par] == 2]
         n_couples = max(1, int(round(len(kids) / mean_kids)))
-        # monogamous-ish: permute both sexes, then let a fraction re-mate with a random partner
-        m_idx = rng.permutation(males)[np.arange(n_couples) % len(males)]
-        f_idx = rng.permutation(females)[np.arange(n_couples) % len(females)]
-        re = rng.random(n_couples) < remate_frac
-        f_idx[re] = rng.choice(females, size=int(re.sum()))
-        couple_of_kid = np.sort(rng.integers(0, n_couples, size=len(kids)))
-        pa[kids], ma[kids] = m_idx[couple_of_kid], f_idx[couple_of_kid]
+        # monogamous-ish: walk a permutation of the males; a fraction of them re-mates
+        order = list(rng.permutation(males))
+        order += [int(x) for x in rng.choice(males, size=int(remate_frac * len(males)) + 1)]
+        fpool = list(rng.permutation(females))
+        couples = []
+        budget = int(max_component - mean_kids - 1)
+        for m_ in order:
+            if len(couples) >= n_couples or not fpool:
+                break
+            for tries in range(min(8, len(fpool))):
+                f_ = fpool[-1 - tries]
+                rm, rf = find(int(m_)), find(int(f_))
+                if rm != rf and csize[rm] + csize[rf] <= budget:
+                    fpool.pop(-1 - tries)
+                    if rng.random() < remate_frac:
+                        fpool.insert(int(rng.integers(0, len(fpool) + 1)), f_)
+                    couples.append((int(m_), int(f_)))
+                    union(int(m_), int(f_))
+                    break
+        if not couples:
+            couples = [(int(males[0]), int(females[0]))]
+        couple_of_kid = np.sort(rng.integers(0, len(couples), size=len(kids)))
+        carr = np.array(couples, dtype=np.int32)
+        pa[kids], ma[kids] = carr[couple_of_kid, 0], carr[couple_of_kid, 1]
+        for kk, c in zip(kids, couple_of_kid):
+            union(couples[c][0], int(kk))
 
     # allele frequencies and gene drop (two haplotypes per individual)
     af = rng.beta(10.0, 10.0, size=n_loci)
