@@ -164,6 +164,9 @@ int64_t pf_launch_count(const pf_engine *e);
  * engine's stream. pf_profile_read synchronises, returns the summed device time in
  * milliseconds and the launch count per kernel kind (0 sweep, 1 eval, 2 reduce, 3 prefilter;
  * ms[4], count[4]) and clears the records. */
+/* Shape of the most recent sweep plan, out[8] = { levels, task groups, tasks, shared-memory bytes
+ * per block, transient message rows, of which in shared memory, up-band levels, locus tiles }. */
+int pf_plan_stats(const pf_engine *e, int32_t *out);
 int pf_profile(pf_engine *e, int32_t enable);
 int pf_profile_read(pf_engine *e, double *ms, int64_t *count);
 

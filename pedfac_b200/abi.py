@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read",
+    "eval_batch", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -91,6 +91,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("get_stub", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
     sig("get_prong", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
     sig("launch_count", C.c_int64, vp)
+    sig("plan_stats", C.c_int, vp, _i32p)
     sig("profile", C.c_int, vp, C.c_int32)
     sig("profile_read", C.c_int, vp, _f64p, C.POINTER(C.c_int64))
 
@@ -279,6 +280,12 @@ class CEngine:
         out = np.empty((self.n_local, 3), dtype=np.float64)
         self._check(self._fn("get_prong")(self._h, chain, marr, ptr(out, _f64p)))
         return out
+
+    def plan_stats(self) -> dict:
+        out = np.zeros(8, dtype=np.int32)
+        self._check(self._fn("plan_stats")(self._h, ptr(out, _i32p)))
+        keys = ["levels", "groups", "tasks", "smem_bytes", "rows", "rows_smem", "up_levels", "tiles"]
+        return dict(zip(keys, out.tolist()))
 
     def profile(self, enable: bool):
         self._check(self._fn("profile")(self._h, 1 if enable else 0))

@@ -145,6 +145,8 @@ __device__ __forceinline__ Tri mat_to_kid(const Mat3 &W)
                0.5 * s01 + s02 + 0.5 * W.m[4] + 0.5 * s12,
                0.25 * W.m[4] + 0.5 * s12 + W.m[8]};
 }
+// Selfing marriage on the same 3x3 tensor: only the diagonal gm == gp is meaningful.
+__device__ __forceinline__ Tri mat_diag(const Mat3 &W) { return Tri{W.m[0], W.m[4], W.m[8]}; }
 // Selfing marriage: one parent state g, T[gk][g][g] = {1,.25,0 | 0,.5,0 | 0,.25,1} over g.
 __device__ __forceinline__ Tri self_kid_factor(Tri k)   // K(g,g)
 {
@@ -163,6 +165,10 @@ struct LogProd { double m; int e; double slow; };
 
 __device__ __forceinline__ void lp_init(LogProd &a) { a.m = 1.0; a.e = 0; a.slow = 0.0; }
 
+// out of line on purpose: log() is ~1 KB of SASS and this path is cold (zero, denormal, negative,
+// inf or nan factor); inlining it at every product site blew the kernels past the instruction cache
+static __device__ __noinline__ double lp_slow_log(double x) { return log(x); }
+
 __device__ __forceinline__ void lp_mul(LogProd &a, double x)
 {
     const int hi = __double2hiint(x);
@@ -172,7 +178,7 @@ __device__ __forceinline__ void lp_mul(LogProd &a, double x)
         a.m *= mant;
         a.e += (int)se - 1023;
     } else {
-        a.slow += log(x);
+        a.slow += lp_slow_log(x);
     }
 }
 // bring the mantissa back to [1,2); call at least every 512 lp_mul

@@ -109,6 +109,7 @@ struct pf_engine {
 
     std::vector<int> loc;                 // slot -> index in the view being planned
     int64_t launches = 0;
+    int32_t last_plan[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // see pf_plan_stats
 
     // optional per-launch CUDA-event timing (pf_profile): kind 0 sweep, 1 eval, 2 reduce, 3 prefilter
     bool prof_on = false;
@@ -217,6 +218,13 @@ extern "C" int pf_set_stream(pf_engine *e, void *cuda_stream)
 }
 
 extern "C" int64_t pf_launch_count(const pf_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int pf_plan_stats(const pf_engine *e, int32_t *out)
+{
+    if (!e || !out) return fail(PF_EINVAL, "null argument");
+    memcpy(out, e->last_plan, sizeof e->last_plan);
+    return PF_OK;
+}
 
 extern "C" int pf_profile(pf_engine *e, int32_t enable)
 {
@@ -372,14 +380,32 @@ struct PlanTask { int group, level, kind, off; };
 struct Plan {
     std::vector<PlanTask> tasks;
     std::vector<int> pool;
-    int n_levels = 1, n_groups = 1, n_out = 0, n_scratch = 0;
+    std::vector<EmisEnt> emis;
+    std::vector<SweepGroup> groups;
+    std::vector<int> row_ref_pos;        // pool positions holding transient row references
+    int n_levels = 1, n_out = 0;
+    int target_tasks_per_group = 1 << 30;
+    int scratch_rows = 0;
+
+    // Whole components are appended to the open group; a new group starts once the open one has
+    // reached the target size (components are never split: their tasks depend on each other).
+    void begin_component()
+    {
+        if (groups.empty() || groups.back().task_end >= target_tasks_per_group) {
+            SweepGroup g{};
+            g.pool_begin = (int)pool.size();
+            g.emis_begin = (int)emis.size();
+            groups.push_back(g);
+        }
+    }
+    SweepGroup &cur() { return groups.back(); }
 };
 
 struct ViewWork {           // scratch vectors reused across calls
     std::vector<int> adj_off, adj_m, adj_role;      // individual -> (marriage, role)
     std::vector<int> mem_off, mem_i, mem_role;      // marriage -> members (pa, ma, kids)
-    std::vector<int> Ui, um, urole, depth_m, lvlA, comp_of_i;
-    std::vector<int> up_i_row, up_m_row, dn_row;
+    std::vector<int> Ui, um, urole, depth_m, lvlA;
+    std::vector<int> up_i_row, up_m_row, dn_row, in_u_row, emis_idx;
     std::vector<int> bfs_m, queue;
     std::vector<char> vis_i, vis_m, label_seen;
 };
@@ -390,9 +416,10 @@ static thread_local ViewWork g_work;
 
 // Appends the tasks of one view to `plan`. Levels are assigned in two bands: FAMILY_UP tasks get
 // their height above the leaves; ROOT/FAMILY_DOWN tasks get (band offset) + depth below the root.
-// The band offset is fixed up by the caller once every view has been added.
-static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan,
-                         int &max_up_levels, std::vector<int> &comp_task_begin)
+// The band offset is fixed up by the caller once every view has been added. While a group is
+// being filled, SweepGroup::task_end counts its tasks and n_rows / emis_count its transient rows
+// and genotype entries.
+static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels)
 {
     if (!v) return fail(PF_EINVAL, "null view");
     const int nI = v->n_indiv, nM = v->n_marr;
@@ -443,9 +470,10 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
 
         w.Ui.assign(nI, -1); w.um.assign(nM, -1); w.urole.assign(nM, 0); w.depth_m.assign(nM, 0);
         w.lvlA.assign(nM, 0); w.vis_i.assign(nI, 0); w.vis_m.assign(nM, 0); w.label_seen.assign(v->n_cc, 0);
-        w.up_i_row.assign(nI, -1); w.up_m_row.assign(nM, -1); w.dn_row.assign(nI, -1);
+        w.up_i_row.assign(nI, -1); w.up_m_row.assign(nM, -1); w.in_u_row.assign(nM, -1); w.dn_row.assign(nI, -1); w.emis_idx.assign(nI, -1);
         w.bfs_m.clear();
-        std::vector<int> roots;
+        std::vector<int> roots, comp_members_end;   // BFS order of individuals per component
+        std::vector<int> order_i;
         std::vector<int> q;
         for (int r = 0; r < nI; r++) {
             if (w.vis_i[r]) continue;
@@ -474,7 +502,11 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                     }
                 }
             }
+            order_i.insert(order_i.end(), q.begin(), q.end());
+            comp_members_end.push_back((int)order_i.size());
         }
+        for (int m = 0; m < nM; m++)
+            if (!w.vis_m[m]) { rc = fail(PF_EINVAL, "marriage %d not reachable", v->marr[m]); goto cleanup; }
         // heights of the FAMILY_UP tasks, children first (reverse BFS order)
         int up_levels = 0;
         for (int b = (int)w.bfs_m.size() - 1; b >= 0; b--) {
@@ -491,19 +523,14 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         }
         max_up_levels = std::max(max_up_levels, up_levels);
 
-        // scratch rows
-        int ns = plan.n_scratch;
-        for (int m = 0; m < nM; m++) w.up_m_row[m] = SCRATCH_BIT | ns++;
-        for (int i = 0; i < nI; i++) {
-            if (w.Ui[i] < 0) continue;
-            w.up_i_row[i] = SCRATCH_BIT | ns++;
-            if (w.adj_off[i + 1] - w.adj_off[i] > 1) w.dn_row[i] = SCRATCH_BIT | ns++;
-        }
-        plan.n_scratch = ns;
-
-        // emit tasks component by component (BFS order keeps a component's tasks contiguous)
-        // ROOT tasks: level -1 = "first level of the down band" (or level 0 for singletons)
+        // emit tasks component by component (BFS order keeps a component's marriages contiguous)
         std::vector<int> &pool = plan.pool;
+        // transient row references are recorded so they can be tagged "in shared memory" once the
+        // group's budget is known (see run_sweeps)
+        auto push_row = [&](int ref) {
+            if (ref & SCRATCH_BIT) plan.row_ref_pos.push_back((int)pool.size());
+            pool.push_back(ref);
+        };
         auto below_rows = [&](int x, int except_m) {
             int n = 0;
             const size_t at = pool.size();
@@ -511,63 +538,101 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             for (int a = w.adj_off[x]; a < w.adj_off[x + 1]; a++) {
                 const int m2 = w.adj_m[a];
                 if (m2 == except_m || m2 == w.Ui[x]) continue;
-                pool.push_back(w.up_m_row[m2]); n++;
+                push_row(w.up_m_row[m2]); n++;
             }
             pool[at] = n;
         };
+        // height of the up message of individual x: 0 if nothing hangs below it
+        auto lvl_in = [&](int x, int except_m) {
+            int lv = 0;
+            for (int a = w.adj_off[x]; a < w.adj_off[x + 1]; a++)
+                if (w.adj_m[a] != except_m) lv = std::max(lv, w.lvlA[w.adj_m[a]] + 1);
+            return lv;
+        };
+        auto member = [&](int x, int role) { return role | (v->indiv_founder[x] ? 4 : 0) | (w.emis_idx[x] << 3); };
         size_t bfs_pos = 0;
-        // marriages of a component are contiguous in bfs_m, in root order
         for (size_t ri = 0; ri < roots.size(); ri++) {
             const int r = roots[ri];
-            comp_task_begin.push_back((int)plan.tasks.size());
+            plan.begin_component();
+            SweepGroup &G = plan.cur();
+            const int gid = (int)plan.groups.size() - 1;
+            const int ib = ri == 0 ? 0 : comp_members_end[ri - 1], ie = comp_members_end[ri];
+            // the component's marriages: the run of bfs_m whose up-individual carries this label
+            size_t mb = bfs_pos, me = bfs_pos;
+            while (me < w.bfs_m.size() && v->indiv_cc[w.um[w.bfs_m[me]]] == v->indiv_cc[r]) me++;
+            bfs_pos = me;
+            // group-local transient rows: marriage messages first (they sit on every dependency
+            // chain), then in_u and the down messages, then the per-member up messages
+            for (size_t b = mb; b < me; b++) w.up_m_row[w.bfs_m[b]] = SCRATCH_BIT | G.n_rows++;
+            for (size_t b = mb; b < me; b++) w.in_u_row[w.bfs_m[b]] = SCRATCH_BIT | G.n_rows++;
+            for (int oi = ib; oi < ie; oi++) {
+                const int i = order_i[oi];
+                if (w.Ui[i] >= 0 && w.adj_off[i + 1] - w.adj_off[i] > 1) w.dn_row[i] = SCRATCH_BIT | G.n_rows++;
+            }
+            for (int oi = ib; oi < ie; oi++) {
+                const int i = order_i[oi];
+                if (w.Ui[i] >= 0) w.up_i_row[i] = SCRATCH_BIT | G.n_rows++;
+                // genotype entry
+                const int slot = v->indiv[i];
+                EmisEnt E{};
+                E.kind = e->h_kind[slot]; E.denom = e->h_denom[slot]; E.rcp = 1.0 / (double)e->h_denom[slot];
+                const unsigned long long pp = (unsigned long long)(uintptr_t)e->h_eptr[slot];
+                E.ptr_lo = (unsigned)(pp & 0xffffffffu); E.ptr_hi = (unsigned)(pp >> 32);
+                const int bytes = emis_tile_bytes(E.kind);
+                if (bytes > 0 && G.emis_bytes + bytes <= SWEEP_EMIS_SMEM_MAX) { E.smem_off = (unsigned)G.emis_bytes; G.emis_bytes += (bytes + 7) & ~7; }
+                else E.smem_off = EMIS_NOT_STAGED;
+                w.emis_idx[i] = G.emis_count++;
+                plan.emis.push_back(E);
+            }
+            auto add_task = [&](int level, int kind) { plan.tasks.push_back(PlanTask{gid, level, kind, (int)pool.size()}); G.task_end++; };
+            // levels: >= 0 = up band; -1 = first level of the down band; -(2 + k) = down band level k
             const bool has_m = w.adj_off[r + 1] > w.adj_off[r];
-            PlanTask tr{0, has_m ? -1 : 0, TASK_ROOT, (int)pool.size()};
-            pool.push_back(v->indiv[r]); pool.push_back(v->indiv_founder[r] ? 1 : 0);
+            add_task(has_m ? -1 : 0, TASK_ROOT);
+            pool.push_back(member(r, 0));
             pool.push_back(e->stub_row(chain, v->indiv[r])); pool.push_back(out_base + v->indiv_cc[r]);
             below_rows(r, -1);
-            plan.tasks.push_back(tr);
-            // marriages whose root is r: walk bfs_m until a marriage of another component shows up
-            while (bfs_pos < w.bfs_m.size()) {
-                const int m = w.bfs_m[bfs_pos];
-                // component membership: follow um upward is O(depth); use label instead
-                if (v->indiv_cc[w.um[m]] != v->indiv_cc[r]) break;
-                bfs_pos++;
+            for (size_t b = mb; b < me; b++) {
+                const int m = w.bfs_m[b];
                 const int flags = (v->marr_selfing[m] ? 1 : 0) | (w.urole[m] << 1);
                 const int u = w.um[m];
-                // FAMILY_UP
-                PlanTask tu{0, w.lvlA[m], TASK_FAMILY_UP, (int)pool.size()};
-                pool.push_back(flags); pool.push_back(w.up_m_row[m]);
-                const size_t nd_at = pool.size(); pool.push_back(0);
                 int nd = 0;
                 for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
                     const int x = w.mem_i[k];
                     if (x == u) continue;
-                    pool.push_back(w.mem_role[k]); pool.push_back(v->indiv[x]); pool.push_back(v->indiv_founder[x] ? 1 : 0);
-                    pool.push_back(w.up_i_row[x]);
-                    below_rows(x, m);
                     nd++;
+                    add_task(2 * lvl_in(x, m), TASK_UP_IN);
+                    pool.push_back(member(x, w.mem_role[k])); push_row(w.up_i_row[x]);
+                    below_rows(x, m);
                 }
-                pool[nd_at] = nd;
-                plan.tasks.push_back(tu);
-                // FAMILY_DOWN: level = -(2 + depth) marks the down band
-                PlanTask td{0, -(2 + w.depth_m[m]), TASK_FAMILY_DOWN, (int)pool.size()};
-                pool.push_back(flags); pool.push_back(e->prong_row(chain, v->marr[m]));
-                pool.push_back(v->indiv[u]); pool.push_back(v->indiv_founder[u] ? 1 : 0);
-                pool.push_back(w.Ui[u] < 0 ? -1 : w.dn_row[u]);
+                add_task(2 * w.lvlA[m] + 1, TASK_UP_M);
+                pool.push_back(flags); push_row(w.up_m_row[m]); pool.push_back(nd);
+                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
+                    if (w.mem_i[k] != u) { pool.push_back(w.mem_role[k]); push_row(w.up_i_row[w.mem_i[k]]); }
+                add_task(-(2 + 2 * w.depth_m[m]), TASK_DN_IN);
+                pool.push_back(member(u, w.urole[m])); push_row(w.in_u_row[m]);
+                if (w.Ui[u] < 0) pool.push_back(-1); else push_row(w.dn_row[u]);
                 below_rows(u, m);
-                pool.push_back(nd);
                 for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
                     const int x = w.mem_i[k];
                     if (x == u) continue;
-                    pool.push_back(w.mem_role[k]); pool.push_back(w.up_i_row[x]);
-                    pool.push_back(e->stub_row(chain, v->indiv[x])); pool.push_back(w.dn_row[x]);
+                    add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_DN_OUT);
+                    pool.push_back(flags | (w.mem_role[k] << 3)); push_row(w.in_u_row[m]); push_row(w.up_i_row[x]);
+                    pool.push_back(e->stub_row(chain, v->indiv[x]));
+                    if (w.dn_row[x] < 0) pool.push_back(-1); else push_row(w.dn_row[x]);
+                    pool.push_back(nd - 1);
+                    for (int k2 = w.mem_off[m]; k2 < w.mem_off[m + 1]; k2++) {
+                        const int y = w.mem_i[k2];
+                        if (y == u || k2 == k) continue;
+                        pool.push_back(w.mem_role[k2]); push_row(w.up_i_row[y]);
+                    }
                 }
-                plan.tasks.push_back(td);
+                add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_PRONG);
+                pool.push_back(flags); push_row(w.in_u_row[m]); pool.push_back(e->prong_row(chain, v->marr[m])); pool.push_back(nd);
+                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
+                    if (w.mem_i[k] != u) { pool.push_back(w.mem_role[k]); push_row(w.up_i_row[w.mem_i[k]]); }
             }
+            G.pool_len = (int)pool.size() - G.pool_begin;
         }
-        if (bfs_pos != w.bfs_m.size()) { rc = fail(PF_EINVAL, "internal: marriage ordering"); goto cleanup; }
-        for (int m = 0; m < nM; m++)
-            if (!w.vis_m[m]) { rc = fail(PF_EINVAL, "marriage %d not reachable", v->marr[m]); goto cleanup; }
     }
 cleanup:
     for (int i = 0; i < registered; i++) e->loc[v->indiv[i]] = -1;
@@ -578,43 +643,44 @@ cleanup:
 static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph_view *views, double *out_dev, int *n_out_total)
 {
     CU(cudaSetDevice(e->cfg.device));
+    int rc = sync_tables(e);
+    if (rc) return rc;
+    const int n_tiles = (e->Sl + TILE_LOCI - 1) / TILE_LOCI;
     Plan plan;
+    // tasks = one ROOT per component + two per marriage: known before any traversal
+    long long est_tasks = 0, est_comp = 0;
+    for (int i = 0; i < n; i++) { est_tasks += (long long)std::max(views[i].n_cc, 0) + 2LL * std::max(views[i].n_marr, 0); est_comp += std::max(views[i].n_cc, 0); }
+    {
+        // enough groups that (tiles x groups) fills the GPU, but no more than 256 tasks per group
+        const long long want_groups = std::max<long long>((592 + n_tiles - 1) / n_tiles, (est_tasks + 255) / 256);
+        const long long G = std::max<long long>(1, std::min<long long>(std::min<long long>(want_groups, est_comp), 65535));
+        plan.target_tasks_per_group = (int)std::max<long long>(1, (est_tasks + G - 1) / G);
+    }
     int max_up = 0;
-    std::vector<int> comp_begin;
     int out_base = 0;
     for (int i = 0; i < n; i++) {
-        int rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up, comp_begin);
+        rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up);
         if (rc) return rc;
         out_base += views[i].n_cc;
     }
     plan.n_out = out_base;
     *n_out_total = out_base;
     if (plan.tasks.empty()) return PF_OK;
-    comp_begin.push_back((int)plan.tasks.size());
 
-    // levels: up band [0, max_up), down band starts at max_up
+    // levels: up band [0, 2 * max_up), down band starts at 2 * max_up
     int n_levels = 1;
     for (auto &t : plan.tasks) {
-        if (t.level == -1) t.level = max_up;
-        else if (t.level <= -2) t.level = max_up + (-t.level - 2);
+        if (t.level == -1) t.level = 2 * max_up;
+        else if (t.level <= -2) t.level = 2 * max_up + (-t.level - 2);
         n_levels = std::max(n_levels, t.level + 1);
     }
-    // groups: split whole components over thread-block groups so large sweeps fill the GPU
-    const int n_tiles = (e->Sl + TILE_LOCI - 1) / TILE_LOCI;
-    const int n_comp = (int)comp_begin.size() - 1;
-    const int total = (int)plan.tasks.size();
-    int G = std::min(n_comp, std::max(1, std::min((592 + n_tiles - 1) / n_tiles, total / 8)));
-    G = std::max(1, std::min(G, 65535));
-    for (int c = 0; c < n_comp; c++) {
-        const int g = (int)(((long long)comp_begin[c] * G) / total);
-        for (int t = comp_begin[c]; t < comp_begin[c + 1]; t++) plan.tasks[t].group = g;
-    }
-    plan.n_groups = G; plan.n_levels = n_levels;
+    plan.n_levels = n_levels;
+    const int G = (int)plan.groups.size();
+    if (G > 65535) return fail(PF_EINVAL, "too many task groups (%d)", G);
 
-    // counting sort by (group, level)
+    // counting sort by (group, level); groups own contiguous task ranges in emission order already
     std::vector<int> level_off((size_t)G * (n_levels + 1) + 1, 0);
     for (auto &t : plan.tasks) level_off[(size_t)t.group * (n_levels + 1) + t.level + 1]++;
-    // per group prefix, with the group's base added
     std::vector<int> start((size_t)G * n_levels, 0);
     {
         int base = 0;
@@ -623,15 +689,50 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
             int run = base;
             for (int l = 0; l < n_levels; l++) { const int c = lo[l + 1]; start[(size_t)g * n_levels + l] = run; lo[l] = run; run += c; }
             lo[n_levels] = run;
+            plan.groups[g].task_begin = base;
+            plan.groups[g].task_end = run;
             base = run;
         }
     }
+    // shared-memory budget per group: stage the plan slice if it is small, then as many transient
+    // rows as fit; the launch uses the largest layout
+    int smem_bytes = 0, scratch_rows = 0;
+    for (int g = 0; g < G; g++) {
+        SweepGroup &sg = plan.groups[g];
+        const int slice = (sg.task_end - sg.task_begin) * 8 + sg.pool_len * 4 + sg.emis_count * (int)sizeof(EmisEnt);
+        sg.staged = slice <= SWEEP_PLAN_SMEM_MAX ? 1 : 0;
+        sg.n_rows_smem = 0;
+        const SweepSmem L0 = sweep_smem_layout(sg, n_levels);
+        if (L0.total > SWEEP_SMEM_MAX) return fail(PF_EINVAL, "sweep plan too deep for shared memory (%d levels)", n_levels);
+        sg.n_rows_smem = std::min(sg.n_rows, (SWEEP_SMEM_MAX - L0.total) / SMEM_ROW_BYTES);
+        sg.scratch_base = scratch_rows;
+        scratch_rows += sg.n_rows;
+        smem_bytes = std::max(smem_bytes, sweep_smem_layout(sg, n_levels).total);
+    }
+    // tag the transient rows that live in shared memory (row_ref_pos is sorted; groups own
+    // consecutive pool slices)
+    {
+        size_t rp = 0;
+        for (int g = 0; g < G; g++) {
+            const SweepGroup &sg = plan.groups[g];
+            const int pend = sg.pool_begin + sg.pool_len;
+            for (; rp < plan.row_ref_pos.size() && plan.row_ref_pos[rp] < pend; rp++) {
+                int &ref = plan.pool[plan.row_ref_pos[rp]];
+                if ((ref & ~SCRATCH_BIT) < sg.n_rows_smem) ref |= SMEM_ROW_BIT;
+            }
+        }
+    }
+
     const size_t bytes_tasks = plan.tasks.size() * sizeof(SweepTask);
     const size_t bytes_pool = plan.pool.size() * sizeof(int);
     const size_t bytes_loff = (size_t)G * (n_levels + 1) * sizeof(int);
+    const size_t bytes_emis = plan.emis.size() * sizeof(EmisEnt);
+    const size_t bytes_groups = (size_t)G * sizeof(SweepGroup);
     const size_t off_pool = (bytes_tasks + 15) & ~(size_t)15;
     const size_t off_loff = (off_pool + bytes_pool + 15) & ~(size_t)15;
-    const size_t blob = off_loff + bytes_loff;
+    const size_t off_emis = (off_loff + bytes_loff + 15) & ~(size_t)15;
+    const size_t off_groups = (off_emis + bytes_emis + 15) & ~(size_t)15;
+    const size_t blob = off_groups + bytes_groups;
 
     void *hp = nullptr; int slot = 0;
     CU(e->staging.get(blob, &hp, &slot));
@@ -642,25 +743,34 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     }
     memcpy(static_cast<char *>(hp) + off_pool, plan.pool.data(), bytes_pool);
     memcpy(static_cast<char *>(hp) + off_loff, level_off.data(), bytes_loff);
+    memcpy(static_cast<char *>(hp) + off_emis, plan.emis.data(), bytes_emis);
+    memcpy(static_cast<char *>(hp) + off_groups, plan.groups.data(), bytes_groups);
 
-    int rc = sync_tables(e);
-    if (rc) return rc;
     CU(e->plan.reserve(blob));
-    CU(e->scratch.reserve((size_t)plan.n_scratch * e->row_elems() * sizeof(double)));
+    CU(e->scratch.reserve((size_t)std::max(scratch_rows, 1) * e->row_elems() * sizeof(double)));
     CU(e->partial.reserve((size_t)n_tiles * std::max(plan.n_out, 1) * sizeof(double)));
     CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
     CU(e->staging.mark(slot, e->stream));
 
     SweepParams P;
     P.D = dev_view(e);
-    P.tasks = reinterpret_cast<const SweepTask *>(e->plan.p);
-    P.pool = reinterpret_cast<const int *>(static_cast<char *>(e->plan.p) + off_pool);
-    P.level_off = reinterpret_cast<const int *>(static_cast<char *>(e->plan.p) + off_loff);
+    char *dp = static_cast<char *>(e->plan.p);
+    P.tasks = reinterpret_cast<const SweepTask *>(dp);
+    P.pool = reinterpret_cast<const int *>(dp + off_pool);
+    P.level_off = reinterpret_cast<const int *>(dp + off_loff);
+    P.emis = reinterpret_cast<const EmisEnt *>(dp + off_emis);
+    P.groups = reinterpret_cast<const SweepGroup *>(dp + off_groups);
     P.n_groups = G; P.n_levels = n_levels;
     P.partial = static_cast<double *>(e->partial.p);
     P.n_out = plan.n_out;
+    {
+        int rows = 0, rows_smem = 0;
+        for (auto &sg : plan.groups) { rows += sg.n_rows; rows_smem += sg.n_rows_smem; }
+        const int32_t st[8] = {n_levels, G, (int)plan.tasks.size(), smem_bytes, rows, rows_smem, max_up, n_tiles};
+        memcpy(e->last_plan, st, sizeof st);
+    }
     e->prof_begin(0);
-    launch_sweep(P, n_tiles, e->stream);
+    launch_sweep(P, n_tiles, smem_bytes, e->stream);
     e->prof_end();
     e->launches++;
     CU(cudaGetLastError());

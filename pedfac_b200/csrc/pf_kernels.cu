@@ -8,28 +8,105 @@ namespace pf {
 
 // ---- sweep ----------------------------------------------------------------------------------
 
-__device__ __forceinline__ Tri prod_rows(const DevView &D, const int *rows, int n, int s, Tri acc)
+// Per-thread context: where the staged plan, genotype tiles and transient rows live. The three
+// row bases already include this thread's locus, so resolving a reference is one multiply-add.
+struct SweepCtx {
+    const EmisEnt *emis;      // group's genotype entries (shared or global)
+    const char *edata;        // staged genotype tiles
+    const double *prior;      // [3][32] staged HWE prior of the tile
+    const double *eps;        // [32]
+    double *smem_lane;        // transient rows in shared memory, + lane
+    double *scratch_lane;     // spilled transient rows of this group, + locus
+    double *rows_lane;        // persistent rows, + locus
+    int Sp, Sl, s, lane, tile;
+};
+
+// A row reference resolved for this thread: element of state g is p[g * stride].
+struct RowRef { double *p; int stride; };
+
+__device__ __forceinline__ RowRef resolve(const SweepCtx &C, int ref)
 {
-    for (int j = 0; j < n; j++) acc = mul(acc, ld_tri(row_ptr(D, rows[j]), D.Sp, s));
+    // branch-free: three address spaces (persistent rows, spilled transient rows, shared memory)
+    const bool sm = ref & SMEM_ROW_BIT, tr = ref & SCRATCH_BIT;
+    double *base = sm ? C.smem_lane : tr ? C.scratch_lane : C.rows_lane;
+    const int stride = sm ? TILE_LOCI : C.Sp;
+    return RowRef{base + (size_t)(ref & (SMEM_ROW_BIT - 1)) * (size_t)(3 * stride), stride};
+}
+__device__ __forceinline__ Tri ld(RowRef r) { return Tri{r.p[0], r.p[r.stride], r.p[2 * r.stride]}; }
+__device__ __forceinline__ void st(RowRef r, Tri v) { r.p[0] = v.x; r.p[r.stride] = v.y; r.p[2 * r.stride] = v.z; }
+
+// exact num / den for 16-bit numerators: Markstein's correction step on the rounded reciprocal
+__device__ __forceinline__ double div_exact(double num, double den, double rcp)
+{
+    const double q = num * rcp;
+    return fma(fma(-den, q, num), rcp, q);
+}
+
+// local(i) = emission x (founder ? HWE prior : 1) from the staged genotype tile
+// (_ReadPedfile@0x10000b1ca-0x10000b6e2 emission model; _PassingOFtoIV@0x10001c2d0)
+__device__ __forceinline__ Tri local_of(const SweepCtx &C, int member)
+{
+    const EmisEnt &E = C.emis[member >> 3];
+    const unsigned kind = E.kind, off = E.smem_off;
+    Tri e{1.0, 1.0, 1.0};
+    const int l = C.lane;
+    if (kind != EMIS_NONE) {
+        const bool staged = off != EMIS_NOT_STAGED;
+        // staged tile: planes of 32 loci; global row: planes of Sp loci
+        const char *p = staged ? C.edata + off
+                               : reinterpret_cast<const char *>(((unsigned long long)E.ptr_hi << 32) | E.ptr_lo);
+        const int i = staged ? l : C.s, ps = staged ? TILE_LOCI : C.Sp;
+        if (kind == EMIS_HARD) {
+            const uint32_t w = reinterpret_cast<const uint32_t *>(p)[i >> 4];
+            const int c = (w >> ((i & 15) * 2)) & 3;
+            if (c != 3) {
+                const double ep = C.eps[l], lo = ep / 2.0, hi = 1.0 - ep;
+                e = Tri{c == 0 ? hi : lo, c == 1 ? hi : lo, c == 2 ? hi : lo};
+            }
+        } else if (kind == EMIS_DEC16) {
+            const uint16_t *u = reinterpret_cast<const uint16_t *>(p);
+            const double den = (double)E.denom, rcp = E.rcp;
+            e = Tri{div_exact((double)u[i], den, rcp), div_exact((double)u[ps + i], den, rcp), div_exact((double)u[2 * ps + i], den, rcp)};
+        } else if (kind == EMIS_F32) {
+            const float *f = reinterpret_cast<const float *>(p);
+            e = Tri{(double)f[i], (double)f[ps + i], (double)f[2 * ps + i]};
+        } else {
+            const double *f = reinterpret_cast<const double *>(p);
+            e = Tri{f[i], f[ps + i], f[2 * ps + i]};
+        }
+    }
+    if (member & 4) e = mul(e, Tri{C.prior[l], C.prior[TILE_LOCI + l], C.prior[2 * TILE_LOCI + l]});
+    return e;
+}
+
+__device__ __forceinline__ Tri prod_rows(const SweepCtx &C, const int *rows, int n, Tri acc)
+{
+    for (int j = 0; j < n; j++) acc = mul(acc, ld(resolve(C, rows[j])));
     return acc;
 }
 
-// fold one member's incoming message into the family tensor
+// fold one member's incoming message into the family tensor W[gm][gp]; one code path for all
+// roles: the member's factor matrix is in[gp] (father), in[gm] (mother) or K(gm,gp) (kid).
+// A selfing marriage uses the same tensor and reads only its diagonal (gm == gp).
 __device__ __forceinline__ void fold(Mat3 &W, int role, Tri in)
 {
-    if (role == 0) mat_mul_pa(W, in);
-    else if (role == 1) mat_mul_ma(W, in);
-    else mat_mul_kid(W, in);
+    const Sym3 K = kid_matrix(in);
+    const bool kid = role == 2, pa = role == 0;
+    W.m[0] *= kid ? K.a00 : in.x;
+    W.m[1] *= kid ? K.a01 : pa ? in.y : in.x;
+    W.m[2] *= kid ? K.a02 : pa ? in.z : in.x;
+    W.m[3] *= kid ? K.a01 : pa ? in.x : in.y;
+    W.m[4] *= kid ? K.a11 : in.y;
+    W.m[5] *= kid ? K.a12 : pa ? in.z : in.y;
+    W.m[6] *= kid ? K.a02 : pa ? in.x : in.z;
+    W.m[7] *= kid ? K.a12 : pa ? in.y : in.z;
+    W.m[8] *= kid ? K.a22 : in.z;
 }
-__device__ __forceinline__ Tri emit(const Mat3 &W, int role)
+__device__ __forceinline__ Tri emit(const Mat3 &W, int role, int selfing)
 {
+    if (selfing) return role == 0 ? mat_diag(W) : self_to_kid(mat_diag(W));
     return role == 0 ? mat_to_pa(W) : role == 1 ? mat_to_ma(W) : mat_to_kid(W);
 }
-__device__ __forceinline__ void fold_self(Tri &w, int role, Tri in)
-{
-    w = mul(w, role == 0 ? in : self_kid_factor(in));
-}
-__device__ __forceinline__ Tri emit_self(Tri w, int role) { return role == 0 ? w : self_to_kid(w); }
 
 __device__ __forceinline__ void ones9(Mat3 &W)
 {
@@ -37,113 +114,160 @@ __device__ __forceinline__ void ones9(Mat3 &W)
     for (int i = 0; i < 9; i++) W.m[i] = 1.0;
 }
 
-__device__ void task_root(const SweepParams &P, const int *t, int s, bool valid, int tile, int lane)
+// fold the listed { role, up_i_row } members into W
+__device__ __forceinline__ void fold_members(const SweepCtx &C, Mat3 &W, const int *mem, int n)
 {
-    const DevView &D = P.D;
-    const int slot = t[0], founder = t[1], stub_row = t[2], out_idx = t[3], nD = t[4];
-    LogProd z; lp_init(z);
-    if (valid) {
-        Tri v = prod_rows(D, t + 5, nD, s, local_factor(D, slot, founder, s));
-        st_tri(row_ptr(D, stub_row), D.Sp, s, v);
-        lp_mul(z, (v.x + v.y) + v.z);
-    }
-    if (out_idx >= 0) {
+    for (int y = 0; y < n; y++) fold(W, mem[2 * y], ld(resolve(C, mem[2 * y + 1])));
+}
+
+__device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &C, const int *t)
+{
+    const Tri v = prod_rows(C, t + 4, t[3], local_of(C, t[0]));
+    st(resolve(C, t[1]), v);
+    if (t[2] >= 0) {
+        LogProd z; lp_init(z);
+        if (C.s < C.Sl) lp_mul(z, (v.x + v.y) + v.z);
         z = lp_warp_reduce(z);
-        if (lane == 0) P.partial[(size_t)tile * P.n_out + out_idx] = lp_log(z);
+        if (C.lane == 0) P.partial[(size_t)C.tile * P.n_out + t[2]] = lp_log(z);
     }
 }
 
-__device__ void task_family_up(const SweepParams &P, const int *t, int s, bool valid)
+__device__ __forceinline__ void task_up_in(const SweepCtx &C, const int *t)
 {
-    if (!valid) return;
-    const DevView &D = P.D;
-    const int flags = t[0], up_m_row = t[1], n_down = t[2];
-    const int selfing = flags & 1, urole = flags >> 1;
-    const int *q = t + 3;
-    Mat3 W; Tri w{1.0, 1.0, 1.0};
-    ones9(W);
-    for (int x = 0; x < n_down; x++) {
-        const int role = q[0], slot = q[1], founder = q[2], up_i_row = q[3], nD = q[4];
-        Tri in = prod_rows(D, q + 5, nD, s, local_factor(D, slot, founder, s));
-        st_tri(row_ptr(D, up_i_row), D.Sp, s, in);
-        if (selfing) fold_self(w, role, in); else fold(W, role, in);
-        q += 5 + nD;
-    }
-    st_tri(row_ptr(D, up_m_row), D.Sp, s, selfing ? emit_self(w, urole) : emit(W, urole));
+    st(resolve(C, t[1]), prod_rows(C, t + 3, t[2], local_of(C, t[0])));
 }
 
-__device__ void task_family_down(const SweepParams &P, const int *t, int s, bool valid)
+__device__ __forceinline__ void task_up_m(const SweepCtx &C, const int *t)
 {
-    if (!valid) return;
-    const DevView &D = P.D;
-    const int flags = t[0], prong_row = t[1], u_slot = t[2], u_founder = t[3], u_dn_row = t[4], nSib = t[5];
-    const int selfing = flags & 1, urole = flags >> 1;
-    Tri in_u = local_factor(D, u_slot, u_founder, s);
-    if (u_dn_row >= 0) in_u = mul(in_u, ld_tri(row_ptr(D, u_dn_row), D.Sp, s));
-    in_u = prod_rows(D, t + 6, nSib, s, in_u);
-    const int *q = t + 6 + nSib;
-    const int n_down = q[0];
-    const int *mem = q + 1;   // { role, up_i_row, stub_row, dn_row } * n_down
+    Mat3 W; ones9(W);
+    fold_members(C, W, t + 3, t[2]);
+    st(resolve(C, t[1]), emit(W, t[0] >> 1, t[0] & 1));
+}
 
-    if (!selfing) {
-        Mat3 Wu; ones9(Wu); fold(Wu, urole, in_u);
-        Mat3 Wall = Wu;
-        for (int x = 0; x < n_down; x++) {
-            Mat3 W = Wu;
-            for (int y = 0; y < n_down; y++) {
-                if (y == x) continue;
-                fold(W, mem[4 * y], ld_tri(row_ptr(D, mem[4 * y + 1]), D.Sp, s));
-            }
-            const Tri up = ld_tri(row_ptr(D, mem[4 * x + 1]), D.Sp, s);
-            const Tri dn = emit(W, mem[4 * x]);
-            st_tri(row_ptr(D, mem[4 * x + 2]), D.Sp, s, mul(up, dn));
-            if (mem[4 * x + 3] >= 0) st_tri(row_ptr(D, mem[4 * x + 3]), D.Sp, s, dn);
-            fold(Wall, mem[4 * x], up);
-        }
-        st_tri(row_ptr(D, prong_row), D.Sp, s, mat_to_kid(Wall));
-    } else {
-        Tri wu{1.0, 1.0, 1.0}; fold_self(wu, urole, in_u);
-        Tri wall = wu;
-        for (int x = 0; x < n_down; x++) {
-            Tri w = wu;
-            for (int y = 0; y < n_down; y++) {
-                if (y == x) continue;
-                fold_self(w, mem[4 * y], ld_tri(row_ptr(D, mem[4 * y + 1]), D.Sp, s));
-            }
-            const Tri up = ld_tri(row_ptr(D, mem[4 * x + 1]), D.Sp, s);
-            const Tri dn = emit_self(w, mem[4 * x]);
-            st_tri(row_ptr(D, mem[4 * x + 2]), D.Sp, s, mul(up, dn));
-            if (mem[4 * x + 3] >= 0) st_tri(row_ptr(D, mem[4 * x + 3]), D.Sp, s, dn);
-            fold_self(wall, mem[4 * x], up);
-        }
-        st_tri(row_ptr(D, prong_row), D.Sp, s, self_to_kid(wall));
-    }
+__device__ __forceinline__ void task_dn_in(const SweepCtx &C, const int *t)
+{
+    Tri in_u = local_of(C, t[0]);
+    if (t[2] >= 0) in_u = mul(in_u, ld(resolve(C, t[2])));
+    st(resolve(C, t[1]), prod_rows(C, t + 4, t[3], in_u));
+}
+
+__device__ __forceinline__ void task_dn_out(const SweepCtx &C, const int *t)
+{
+    const int flags = t[0];
+    Mat3 W; ones9(W);
+    fold(W, (flags >> 1) & 3, ld(resolve(C, t[1])));
+    fold_members(C, W, t + 6, t[5]);
+    const Tri dn = emit(W, flags >> 3, flags & 1);
+    st(resolve(C, t[3]), mul(ld(resolve(C, t[2])), dn));
+    if (t[4] >= 0) st(resolve(C, t[4]), dn);
+}
+
+__device__ __forceinline__ void task_prong(const SweepCtx &C, const int *t)
+{
+    const int flags = t[0];
+    Mat3 W; ones9(W);
+    fold(W, (flags >> 1) & 3, ld(resolve(C, t[1])));
+    fold_members(C, W, t + 4, t[3]);
+    st(resolve(C, t[2]), (flags & 1) ? self_to_kid(mat_diag(W)) : mat_to_kid(W));
 }
 
 __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(const __grid_constant__ SweepParams P)
 {
-    const int tile = blockIdx.x, group = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = tile * TILE_LOCI + lane;
-    const bool valid = s < P.D.Sl;
-    const int *loff = P.level_off + (size_t)group * (P.n_levels + 1);
+    extern __shared__ __align__(16) char smem[];
+    const DevView &D = P.D;
+    const int tile = blockIdx.x;
+    const SweepGroup G = P.groups[blockIdx.y];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nthr = SWEEP_WARPS * 32;
+    const SweepSmem L = sweep_smem_layout(G, P.n_levels);
+
+    // ---- stage the plan slice, the tile's prior/eps and every individual's genotype tile ----
+    int *s_loff = reinterpret_cast<int *>(smem + L.loff);
+    for (int i = tid; i <= P.n_levels; i += nthr) s_loff[i] = P.level_off[(size_t)blockIdx.y * (P.n_levels + 1) + i];
+    double *s_prior = reinterpret_cast<double *>(smem + L.prior);
+    double *s_eps = reinterpret_cast<double *>(smem + L.eps);
+    if (tid < 3 * TILE_LOCI) s_prior[tid] = D.rows[(size_t)ROW_PRIOR * 3 * D.Sp + (size_t)(tid / TILE_LOCI) * D.Sp + tile * TILE_LOCI + (tid % TILE_LOCI)];
+    else if (tid < 4 * TILE_LOCI) s_eps[tid - 3 * TILE_LOCI] = D.eps[tile * TILE_LOCI + (tid - 3 * TILE_LOCI)];
+    const SweepTask *tasks = P.tasks + G.task_begin;
+    const int *pool = P.pool + G.pool_begin;
+    const EmisEnt *emis = P.emis + G.emis_begin;
+    if (G.staged) {
+        int *d;
+        const int *src;
+        d = reinterpret_cast<int *>(smem + L.tasks); src = reinterpret_cast<const int *>(tasks);
+        for (int i = tid; i < (G.task_end - G.task_begin) * 2; i += nthr) d[i] = src[i];
+        d = reinterpret_cast<int *>(smem + L.pool);
+        for (int i = tid; i < G.pool_len; i += nthr) d[i] = pool[i];
+        d = reinterpret_cast<int *>(smem + L.emis); src = reinterpret_cast<const int *>(emis);
+        for (int i = tid; i < G.emis_count * (int)(sizeof(EmisEnt) / 4); i += nthr) d[i] = src[i];
+        tasks = reinterpret_cast<const SweepTask *>(smem + L.tasks);
+        pool = reinterpret_cast<const int *>(smem + L.pool);
+        emis = reinterpret_cast<const EmisEnt *>(smem + L.emis);
+    }
+    // genotype tiles: one warp per individual, lanes along the loci (global entries: the copy in
+    // shared memory may not be visible yet, so read the entry from global memory here)
+    {
+        const EmisEnt *gemis = P.emis + G.emis_begin;
+        char *edata = smem + L.edata;
+        const int s = tile * TILE_LOCI + lane;
+        for (int i = warp; i < G.emis_count; i += SWEEP_WARPS) {
+            const EmisEnt E = gemis[i];
+            if (E.smem_off == EMIS_NOT_STAGED || E.kind == EMIS_NONE) continue;
+            const void *gp = reinterpret_cast<const void *>(((unsigned long long)E.ptr_hi << 32) | E.ptr_lo);
+            char *dst = edata + E.smem_off;
+            if (E.kind == EMIS_HARD) {
+                if (lane < 2) reinterpret_cast<uint32_t *>(dst)[lane] = static_cast<const uint32_t *>(gp)[tile * 2 + lane];
+            } else if (E.kind == EMIS_DEC16) {
+                const uint16_t *u = static_cast<const uint16_t *>(gp);
+                uint16_t *o = reinterpret_cast<uint16_t *>(dst);
+                o[lane] = u[s]; o[TILE_LOCI + lane] = u[D.Sp + s]; o[2 * TILE_LOCI + lane] = u[2 * D.Sp + s];
+            } else if (E.kind == EMIS_F32) {
+                const float *f = static_cast<const float *>(gp);
+                float *o = reinterpret_cast<float *>(dst);
+                o[lane] = f[s]; o[TILE_LOCI + lane] = f[D.Sp + s]; o[2 * TILE_LOCI + lane] = f[2 * D.Sp + s];
+            } else {
+                const double *f = static_cast<const double *>(gp);
+                double *o = reinterpret_cast<double *>(dst);
+                o[lane] = f[s]; o[TILE_LOCI + lane] = f[D.Sp + s]; o[2 * TILE_LOCI + lane] = f[2 * D.Sp + s];
+            }
+        }
+    }
+    __syncthreads();
+
+    SweepCtx C;
+    C.emis = emis; C.edata = smem + L.edata; C.prior = s_prior; C.eps = s_eps;
+    C.lane = lane; C.tile = tile; C.s = tile * TILE_LOCI + lane; C.Sp = D.Sp; C.Sl = D.Sl;
+    C.smem_lane = reinterpret_cast<double *>(smem + L.rows) + lane;
+    C.scratch_lane = D.scratch + (size_t)G.scratch_base * 3 * D.Sp + C.s;
+    C.rows_lane = D.rows + C.s;
+
     for (int lev = 0; lev < P.n_levels; lev++) {
-        const int beg = loff[lev], end = loff[lev + 1];
+        const int beg = s_loff[lev] - G.task_begin, end = s_loff[lev + 1] - G.task_begin;
         for (int ti = beg + warp; ti < end; ti += SWEEP_WARPS) {
-            const SweepTask tk = P.tasks[ti];
-            const int *t = P.pool + tk.off;
-            if (tk.kind == TASK_ROOT) task_root(P, t, s, valid, tile, lane);
-            else if (tk.kind == TASK_FAMILY_UP) task_family_up(P, t, s, valid);
-            else task_family_down(P, t, s, valid);
+            const SweepTask tk = tasks[ti];
+            const int *t = pool + (tk.off - G.pool_begin);
+            switch (tk.kind) {
+            case TASK_ROOT: task_root(P, C, t); break;
+            case TASK_UP_IN: task_up_in(C, t); break;
+            case TASK_UP_M: task_up_m(C, t); break;
+            case TASK_DN_IN: task_dn_in(C, t); break;
+            case TASK_DN_OUT: task_dn_out(C, t); break;
+            default: task_prong(C, t); break;
+            }
         }
         if (lev + 1 < P.n_levels) __syncthreads();
     }
 }
 
-void launch_sweep(const SweepParams &P, int n_tiles, cudaStream_t st)
+void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, cudaStream_t st)
 {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_MAX);
+        attr_set = true;
+    }
     dim3 grid(n_tiles, P.n_groups);
-    sweep_kernel<<<grid, SWEEP_WARPS * 32, 0, st>>>(P);
+    sweep_kernel<<<grid, SWEEP_WARPS * 32, smem_bytes, st>>>(P);
 }
 
 // ---- proposal evaluation ---------------------------------------------------------------------

@@ -19,28 +19,102 @@ namespace pf {
 // walks the levels with __syncthreads() between them; its warps share the tasks of a level.
 // Independent components are spread over groups so large sweeps fill the GPU.
 //
-// Task records live in an int32 pool:
-//   ROOT:        slot, founder, stub_row, out_idx, nD, up_m_row[nD]
-//   FAMILY_UP:   flags, up_m_row, n_down, { role, slot, founder, up_i_row, nD, up_m_row[nD] } * n_down
-//   FAMILY_DOWN: flags, prong_row, u_slot, u_founder, u_dn_row (-1 = root), nSib, sib_up_m_row[nSib],
-//                n_down, { role, up_i_row, stub_row, dn_row (-1 = not needed) } * n_down
-// flags = selfing | (role of u(m) in m) << 1, roles: 0 father, 1 mother, 2 kid.
-enum TaskKind : int { TASK_ROOT = 0, TASK_FAMILY_UP = 1, TASK_FAMILY_DOWN = 2 };
+// A block first stages, in shared memory, its group's slice of the plan and the genotype data
+// of every individual of the group for its 32 loci (one fully parallel load phase); transient
+// message rows live in shared memory too (as many as fit; the rest spill to an L2-resident
+// scratch array). The level loop therefore runs on shared-memory latency; the only global
+// traffic inside it is the streaming store of stubs and prongs.
+//
+// Fine-grained tasks keep every dependency step short (a step is executed by ONE warp per
+// 32-locus tile, so its length is the critical path) and let the idle warps of a block run the
+// independent pieces of a family in parallel:
+//   UP_IN(x)     up_i(x) = local(x) * prod up_m(below x)                 level 2h
+//   UP_M(m)      up_m(m) from the up_i of its down members                level 2h+1
+//   ROOT(r)      stub(r), log Z                                           first level of the down band
+//   DN_IN(m)     in_u(m) = local(u) * dn_m(u) * prod up_m(other below u)  level base+2d
+//   DN_OUT(m,x)  dn_m(x), stub(x) = up_i(x) * dn_m(x)                     level base+2d+1
+//   PRONG(m)     prong(m)                                                 level base+2d+1
+// Task records live in an int32 pool. Row references: plain = persistent row index; bit 30 =
+// transient row (group-local index), and bit 29 as well when that row lives in shared memory.
+//   ROOT:    member, stub_row, out_idx, nD, up_m_row[nD]
+//   UP_IN:   member, up_i_row, nD, up_m_row[nD]
+//   UP_M:    flags, up_m_row, n, { role, up_i_row } * n
+//   DN_IN:   member(u), in_u_row, u_dn_row (-1 = root), nSib, sib_up_m_row[nSib]
+//   DN_OUT:  flags | x_role << 3, in_u_row, x_up_i_row, stub_row, dn_row (-1 = not needed), n, { role, up_i_row } * n
+//   PRONG:   flags, in_u_row, prong_row, n, { role, up_i_row } * n
+// member = role | founder << 2 | (group-local genotype entry index) << 3; roles: 0 father,
+// 1 mother, 2 kid. flags = selfing | (role of u(m) in m) << 1.
+enum TaskKind : int { TASK_ROOT = 0, TASK_UP_IN = 1, TASK_UP_M = 2, TASK_DN_IN = 3, TASK_DN_OUT = 4, TASK_PRONG = 5 };
+constexpr int SMEM_ROW_BIT = 1 << 29;
 
 struct SweepTask { int kind; int off; };
+
+// genotype entry of one individual of a group
+struct EmisEnt {
+    unsigned kind;        // EmisKind
+    unsigned denom;       // EMIS_DEC16 denominator
+    unsigned ptr_lo, ptr_hi;   // device pointer of the slot's genotype row
+    unsigned smem_off;    // byte offset of the staged 32-locus tile, or EMIS_NOT_STAGED
+    unsigned pad;
+    double rcp;           // RN(1 / denom): num / denom is evaluated exactly as q = num * rcp;
+                          // q += fma(-denom, q, num) * rcp (verified exhaustively on the host)
+};
+constexpr unsigned EMIS_NOT_STAGED = 0xffffffffu;
+
+struct SweepGroup {
+    int task_begin, task_end;     // sorted task range
+    int pool_begin, pool_len;     // slice of the int pool
+    int emis_begin, emis_count;   // slice of the genotype entries
+    int emis_bytes;               // staged genotype bytes
+    int n_rows, n_rows_smem;      // transient rows, and how many of them live in shared memory
+    int scratch_base;             // first global scratch row of the group
+    int staged;                   // plan slice staged in shared memory?
+    int pad;
+};
 
 struct SweepParams {
     DevView D;
     const SweepTask *tasks;
     const int *pool;
     const int *level_off;   // [n_groups][n_levels + 1] offsets into tasks
+    const EmisEnt *emis;
+    const SweepGroup *groups;
     int n_groups, n_levels;
     double *partial;        // [n_tiles][n_out] per-tile log Z sums
     int n_out;
 };
 
-constexpr int SWEEP_WARPS = 8;
+constexpr int SWEEP_WARPS = 16;
 constexpr int TILE_LOCI = 32;
+constexpr int SMEM_ROW_BYTES = 3 * TILE_LOCI * 8;
+constexpr int SWEEP_SMEM_MAX = 220 * 1024;       // dynamic shared memory budget of one block
+constexpr int SWEEP_PLAN_SMEM_MAX = 56 * 1024;   // larger plan slices are read from global memory
+constexpr int SWEEP_EMIS_SMEM_MAX = 72 * 1024;
+
+// staged bytes of one individual's 32-locus genotype tile
+__host__ __device__ inline int emis_tile_bytes(unsigned kind)
+{
+    return kind == EMIS_HARD ? 8 : kind == EMIS_DEC16 ? 3 * TILE_LOCI * 2 : kind == EMIS_F32 ? 3 * TILE_LOCI * 4
+         : kind == EMIS_F64 ? 3 * TILE_LOCI * 8 : 0;
+}
+
+// shared-memory layout of a sweep block (same arithmetic on host and device)
+struct SweepSmem { int tasks, pool, loff, emis, prior, eps, edata, rows, total; };
+__host__ __device__ inline SweepSmem sweep_smem_layout(const SweepGroup &g, int n_levels)
+{
+    SweepSmem L;
+    int o = 0;
+    L.prior = o; o += 3 * TILE_LOCI * 8;
+    L.eps = o; o += TILE_LOCI * 8;
+    L.loff = o; o += ((n_levels + 1) * 4 + 15) & ~15;
+    L.tasks = o; if (g.staged) o += ((g.task_end - g.task_begin) * 8 + 15) & ~15;
+    L.pool = o; if (g.staged) o += (g.pool_len * 4 + 15) & ~15;
+    L.emis = o; if (g.staged) o += (g.emis_count * (int)sizeof(EmisEnt) + 15) & ~15;
+    L.edata = o; o += (g.emis_bytes + 15) & ~15;
+    L.rows = o; o += g.n_rows_smem * SMEM_ROW_BYTES;
+    L.total = o;
+    return L;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Eval plan. A group = up to EVAL_G proposals of the same focal kid, handled by one warp over
@@ -70,7 +144,7 @@ struct ReduceParams {
     int n_parts, n;
 };
 
-void launch_sweep(const SweepParams &P, int n_tiles, cudaStream_t st);
+void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, cudaStream_t st);
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st);
 void launch_reduce(const ReduceParams &P, cudaStream_t st);
 
