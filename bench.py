@@ -36,13 +36,7 @@ WORKLOADS = {
     "C": (20000, 10000, False, 1, "synthetic 20k individuals x 10k SNPs, hard calls, loci sharded across GPUs"),
     "D": (5000, 2000, True, 64, "synthetic 5k x 2k soft, 64 independent chains batched per GPU"),
 }
-LOCUS_BLOCK = 50
-
-
-def shard_range(S, rank, world):
-    nb = (S + LOCUS_BLOCK - 1) // LOCUS_BLOCK
-    b0, b1 = rank * nb // world, (rank + 1) * nb // world
-    return min(b0 * LOCUS_BLOCK, S), min(b1 * LOCUS_BLOCK, S)
+from pedfac_b200.sharding import shard_range  # noqa: E402
 
 
 # ---------------------------------------------------------------------------------------------
@@ -253,7 +247,7 @@ def main():
     if wl == "D" and world > 1:
         s0, s1 = 0, S            # replicas: every GPU runs its own 64 chains on all loci
 
-    data = synth.simulate(n_ind, S, soft=soft, seed=46)
+    data = synth.simulate(n_ind, S, soft=soft, seed=46, locus_range=(s0, s1))
     trace = Trace(data, args.trace_steps)
     eng = Engine(S, trace.cap_i, trace.cap_m, locus_range=(s0, s1), n_chains=chains, device=local_rank)
     stream = torch.cuda.current_stream()
@@ -272,6 +266,33 @@ def main():
     base_ptr = d_out.data_ptr()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     sharded = world > 1 and (s1 - s0) != S
+
+    # multi-chain batching (config D): one sweep launch and one eval launch serve all chains
+    if chains > 1:
+        import ctypes as C
+        from pedfac_b200.abi import PfGraphView
+        chain_ids = np.arange(chains, dtype=np.int32)
+        batch_views = [(PfGraphView * chains)(*[v.struct for _ in range(chains)]) for v, _, _ in trace.steps]
+        final_views = (PfGraphView * chains)(*[trace.final_view.struct for _ in range(chains)])
+        batch_kids = [np.full(chains, k, dtype=np.int32) for _, k, _ in trace.steps]
+        batch_pb = [np.arange(chains + 1, dtype=np.int32) * len(p) for _, _, p in trace.steps]
+        batch_props = [np.ascontiguousarray(np.tile(p, chains)) for _, _, p in trace.steps]
+
+    def step_device_batched():
+        for t, ((view, kid, props), o) in enumerate(zip(trace.steps, offs)):
+            eng.sweep_batch_dev(chain_ids, batch_views[t], chains, base_ptr + 8 * chains * o)
+            eng.eval_batch_dev(chain_ids, batch_kids[t], batch_pb[t], batch_props[t], base_ptr + 8 * chains * (o + view.n_cc))
+        eng.sweep_batch_dev(chain_ids, final_views, chains, base_ptr + 8 * chains * off_final)
+
+    def step_e2e_batched():
+        nbytes_in = nbytes_out = 0
+        for t, (view, kid, props) in enumerate(trace.steps):
+            eng.sweep_batch(chain_ids, [view] * chains)
+            eng.eval_batch(chain_ids, batch_kids[t], batch_pb[t], batch_props[t])
+            nbytes_in += chains * view_bytes(view) + batch_props[t].nbytes
+            nbytes_out += 8 * chains * (view.n_cc + len(props))
+        eng.sweep_batch(chain_ids, [trace.final_view] * chains)
+        return nbytes_in + chains * view_bytes(trace.final_view), nbytes_out + 8 * chains * trace.final_view.n_cc
 
     def step_device():
         """T Gibbs-step passes, results stay on the device (plus the NCCL all-reduce when sharded)."""
@@ -346,16 +367,17 @@ def main():
     clocks = ClockSampler(local_rank)
     clocks.start()
     l0 = eng.launch_count()
-    dev_ms, _ = timed(step_device, wall=False)
+    dev_fn, e2e_fn = (step_device_batched, step_e2e_batched) if chains > 1 else (step_device, step_e2e)
+    dev_ms, _ = timed(dev_fn, wall=False)
     launches = (eng.launch_count() - l0) * args.steps // (args.steps + args.warmup)
     clk = clocks.stop()
-    e2e_ms, io = timed(step_e2e, wall=True)
+    e2e_ms, io = timed(e2e_fn, wall=True)
 
     # per-kernel device time of the same step (separate pass: events around every launch)
     eng.profile(True)
     for _ in range(2):
         flush.fill_(1)
-        step_device()
+        dev_fn()
     k_ms, k_n = eng.profile_read()
     eng.profile(False)
 

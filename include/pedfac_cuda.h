@@ -139,6 +139,11 @@ int pf_sweep_batch(pf_engine *e, int32_t n, const int32_t *chains, const pf_grap
                    double *ll_cc);
 int pf_eval_batch(pf_engine *e, int32_t n, const int32_t *chains, const int32_t *kids,
                   const int32_t *prop_begin, const pf_proposal *props, double *lsum);
+/* device-output forms of the batched calls (no host synchronisation) */
+int pf_sweep_batch_dev(pf_engine *e, int32_t n, const int32_t *chains, const pf_graph_view *views,
+                       double *ll_cc_dev);
+int pf_eval_batch_dev(pf_engine *e, int32_t n, const int32_t *chains, const int32_t *kids,
+                      const int32_t *prop_begin, const pf_proposal *props, double *lsum_dev);
 
 /* ≙ _RefineParentOffPair@0x100014d20 (its N_obs^2 x S _CalculateLLByStubs calls), dense form:
  * for every kid k and every candidate c (c != kid) the score

@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
+    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -86,6 +86,8 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("eval_dev", C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp)
     sig("sweep_batch", C.c_int, vp, C.c_int32, _i32p, C.POINTER(PfGraphView), _f64p)
     sig("eval_batch", C.c_int, vp, C.c_int32, _i32p, _i32p, _i32p, vp, _f64p)
+    sig("sweep_batch_dev", C.c_int, vp, C.c_int32, _i32p, C.POINTER(PfGraphView), vp)
+    sig("eval_batch_dev", C.c_int, vp, C.c_int32, _i32p, _i32p, _i32p, vp, vp)
     sig("prefilter", C.c_int, vp, C.c_int32, C.c_int32, _i32p, _u8p, C.c_int32, _i32p, _f64p,
         C.c_int32, _i32p, _f64p)
     sig("get_stub", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
@@ -258,6 +260,14 @@ class CEngine:
         self._check(self._fn("eval_batch")(self._h, len(kids), ptr(chains, _i32p), ptr(kids, _i32p),
                                            ptr(prop_begin, _i32p), C.c_void_p(props.ctypes.data), ptr(out, _f64p)))
         return out[:len(props)]
+
+    def sweep_batch_dev(self, chains: np.ndarray, view_array, n: int, out_dev_ptr: int):
+        """chains: int32 array; view_array: ctypes array of PfGraphView (kept alive by the caller)."""
+        self._check(self._fn("sweep_batch_dev")(self._h, n, ptr(chains, _i32p), view_array, C.c_void_p(out_dev_ptr)))
+
+    def eval_batch_dev(self, chains: np.ndarray, kids: np.ndarray, prop_begin: np.ndarray, props: np.ndarray, out_dev_ptr: int):
+        self._check(self._fn("eval_batch_dev")(self._h, len(kids), ptr(chains, _i32p), ptr(kids, _i32p),
+                                               ptr(prop_begin, _i32p), C.c_void_p(props.ctypes.data), C.c_void_p(out_dev_ptr)))
 
     def prefilter(self, kids, as_father, cands, cand_bias=None, top_k: int = 15, chain: int = 0):
         kids, cands = as_i32(kids), as_i32(cands)

@@ -406,7 +406,7 @@ struct ViewWork {           // scratch vectors reused across calls
     std::vector<int> mem_off, mem_i, mem_role;      // marriage -> members (pa, ma, kids)
     std::vector<int> Ui, um, urole, depth_m, lvlA;
     std::vector<int> up_i_row, up_m_row, dn_row, in_u_row, emis_idx;
-    std::vector<int> bfs_m, queue;
+    std::vector<int> bfs_m, queue, cnt_a, cnt_b;
     std::vector<char> vis_i, vis_m, label_seen;
 };
 
@@ -475,13 +475,11 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         std::vector<int> roots, comp_members_end;   // BFS order of individuals per component
         std::vector<int> order_i;
         std::vector<int> q;
-        for (int r = 0; r < nI; r++) {
-            if (w.vis_i[r]) continue;
-            const int label = v->indiv_cc[r];
-            if (w.label_seen[label]) { rc = fail(PF_EINVAL, "component label %d covers individuals that are not connected (slot %d)", label, v->indiv[r]); goto cleanup; }
-            w.label_seen[label] = 1;
-            roots.push_back(r);
-            w.vis_i[r] = 1;
+        const size_t no_m = (size_t)-1;
+        // BFS over the bipartite tree from individual r: fills Ui / um / urole / depth_m, appends
+        // the marriages to bfs_m, leaves the individuals in q. Returns an error code.
+        auto bfs = [&](int r, int label) -> int {
+            w.vis_i[r] = 1; w.Ui[r] = -1;
             q.clear(); q.push_back(r);
             for (size_t h = 0; h < q.size(); h++) {
                 const int i = q[h];
@@ -489,19 +487,51 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 for (int a = w.adj_off[i]; a < w.adj_off[i + 1]; a++) {
                     const int m = w.adj_m[a];
                     if (m == w.Ui[i]) continue;                        // the edge we arrived by
-                    if (w.vis_m[m]) { rc = fail(PF_ECYCLE, "the graph view contains a loop through marriage %d", v->marr[m]); goto cleanup; }
+                    if (w.vis_m[m]) return fail(PF_ECYCLE, "the graph view contains a loop through marriage %d", v->marr[m]);
                     w.vis_m[m] = 1; w.um[m] = i; w.urole[m] = w.adj_role[a]; w.depth_m[m] = di;
                     w.bfs_m.push_back(m);
                     for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
                         const int y = w.mem_i[k];
                         if (y == i && w.mem_role[k] == w.adj_role[a]) continue;
-                        if (w.vis_i[y]) { rc = fail(PF_ECYCLE, "the graph view contains a loop through individual %d", v->indiv[y]); goto cleanup; }
-                        if (v->indiv_cc[y] != label) { rc = fail(PF_EINVAL, "individuals %d and %d are connected but carry different component labels", v->indiv[i], v->indiv[y]); goto cleanup; }
+                        if (w.vis_i[y]) return fail(PF_ECYCLE, "the graph view contains a loop through individual %d", v->indiv[y]);
+                        if (v->indiv_cc[y] != label) return fail(PF_EINVAL, "individuals %d and %d are connected but carry different component labels", v->indiv[i], v->indiv[y]);
                         w.vis_i[y] = 1; w.Ui[y] = m;
                         q.push_back(y);
                     }
                 }
             }
+            return PF_OK;
+        };
+        auto unvisit = [&](size_t m_from) {
+            for (int i : q) w.vis_i[i] = 0;
+            for (size_t b = m_from; b < w.bfs_m.size(); b++) w.vis_m[w.bfs_m[b]] = 0;
+            w.bfs_m.resize(m_from);
+        };
+        (void)no_m;
+        for (int r0 = 0; r0 < nI; r0++) {
+            if (w.vis_i[r0]) continue;
+            const int label = v->indiv_cc[r0];
+            if (w.label_seen[label]) { rc = fail(PF_EINVAL, "component label %d covers individuals that are not connected (slot %d)", label, v->indiv[r0]); goto cleanup; }
+            w.label_seen[label] = 1;
+            const size_t m_from = w.bfs_m.size();
+            rc = bfs(r0, label);
+            if (rc) goto cleanup;
+            int r = r0;
+            if (w.bfs_m.size() - m_from >= 3) {
+                // re-root at the centre of the tree: the number of levels is the tree's radius
+                // instead of up to its diameter. Two more traversals: farthest node from r0, then
+                // the farthest from that one; the centre is half way along that path.
+                const int a_end = q.back();
+                unvisit(m_from);
+                bfs(a_end, label);
+                int c = q.back();
+                const int diam = w.Ui[c] < 0 ? 0 : w.depth_m[w.Ui[c]] + 1;
+                for (int step = 0; step < diam / 2; step++) c = w.um[w.Ui[c]];
+                unvisit(m_from);
+                bfs(c, label);
+                r = c;
+            }
+            roots.push_back(r);
             order_i.insert(order_i.end(), q.begin(), q.end());
             comp_members_end.push_back((int)order_i.size());
         }
@@ -561,17 +591,41 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             size_t mb = bfs_pos, me = bfs_pos;
             while (me < w.bfs_m.size() && v->indiv_cc[w.um[w.bfs_m[me]]] == v->indiv_cc[r]) me++;
             bfs_pos = me;
-            // group-local transient rows: marriage messages first (they sit on every dependency
-            // chain), then in_u and the down messages, then the per-member up messages
+            // group-local transient rows. up_m (one per marriage) and up_i (only for individuals
+            // with marriages below them: a leaf's up message is its local factor, recomputed from
+            // the staged genotype tile) live for the whole sweep. in_u(m) and dn_m(x) are written
+            // and consumed within two consecutive levels of the down band, so every depth reuses
+            // the same small bank of rows.
             for (size_t b = mb; b < me; b++) w.up_m_row[w.bfs_m[b]] = SCRATCH_BIT | G.n_rows++;
-            for (size_t b = mb; b < me; b++) w.in_u_row[w.bfs_m[b]] = SCRATCH_BIT | G.n_rows++;
-            for (int oi = ib; oi < ie; oi++) {
-                const int i = order_i[oi];
-                if (w.Ui[i] >= 0 && w.adj_off[i + 1] - w.adj_off[i] > 1) w.dn_row[i] = SCRATCH_BIT | G.n_rows++;
+            {
+                int max_depth = 0;
+                for (size_t b = mb; b < me; b++) max_depth = std::max(max_depth, w.depth_m[w.bfs_m[b]]);
+                std::vector<int> &cnt_m = w.cnt_a, &cnt_d = w.cnt_b;
+                cnt_m.assign(max_depth + 1, 0); cnt_d.assign(max_depth + 1, 0);
+                int bank_m = 0, bank_d = 0;
+                for (size_t b = mb; b < me; b++) {
+                    const int m = w.bfs_m[b], d = w.depth_m[m];
+                    w.in_u_row[m] = cnt_m[d]++;                         // index inside the bank
+                    bank_m = std::max(bank_m, cnt_m[d]);
+                    for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                        const int x = w.mem_i[k];
+                        if (x == w.um[m] || w.adj_off[x + 1] - w.adj_off[x] <= 1) continue;
+                        w.dn_row[x] = cnt_d[d]++;
+                        bank_d = std::max(bank_d, cnt_d[d]);
+                    }
+                }
+                const int base_m = G.n_rows, base_d = G.n_rows + bank_m;
+                G.n_rows += bank_m + bank_d;
+                for (size_t b = mb; b < me; b++) w.in_u_row[w.bfs_m[b]] = SCRATCH_BIT | (base_m + w.in_u_row[w.bfs_m[b]]);
+                for (int oi = ib; oi < ie; oi++) {
+                    const int i = order_i[oi];
+                    if (w.dn_row[i] >= 0) w.dn_row[i] = SCRATCH_BIT | (base_d + w.dn_row[i]);
+                }
             }
             for (int oi = ib; oi < ie; oi++) {
                 const int i = order_i[oi];
-                if (w.Ui[i] >= 0) w.up_i_row[i] = SCRATCH_BIT | G.n_rows++;
+                const bool leaf = w.adj_off[i + 1] - w.adj_off[i] <= 1;
+                if (w.Ui[i] >= 0 && !leaf) w.up_i_row[i] = SCRATCH_BIT | G.n_rows++;
                 // genotype entry
                 const int slot = v->indiv[i];
                 EmisEnt E{};
@@ -584,6 +638,11 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 w.emis_idx[i] = G.emis_count++;
                 plan.emis.push_back(E);
             }
+            // reference to the up message of member x: its row, or (leaf) LEAF_REF_BIT | member
+            auto push_up_i = [&](int x, int role) {
+                if (w.up_i_row[x] >= 0) push_row(w.up_i_row[x]);
+                else pool.push_back((int)(LEAF_REF_BIT | (unsigned)member(x, role)));
+            };
             auto add_task = [&](int level, int kind) { plan.tasks.push_back(PlanTask{gid, level, kind, (int)pool.size()}); G.task_end++; };
             // levels: >= 0 = up band; -1 = first level of the down band; -(2 + k) = down band level k
             const bool has_m = w.adj_off[r + 1] > w.adj_off[r];
@@ -600,6 +659,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                     const int x = w.mem_i[k];
                     if (x == u) continue;
                     nd++;
+                    if (w.up_i_row[x] < 0) continue;        // leaf: nothing to precompute
                     add_task(2 * lvl_in(x, m), TASK_UP_IN);
                     pool.push_back(member(x, w.mem_role[k])); push_row(w.up_i_row[x]);
                     below_rows(x, m);
@@ -607,7 +667,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 add_task(2 * w.lvlA[m] + 1, TASK_UP_M);
                 pool.push_back(flags); push_row(w.up_m_row[m]); pool.push_back(nd);
                 for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
-                    if (w.mem_i[k] != u) { pool.push_back(w.mem_role[k]); push_row(w.up_i_row[w.mem_i[k]]); }
+                    if (w.mem_i[k] != u) { pool.push_back(w.mem_role[k]); push_up_i(w.mem_i[k], w.mem_role[k]); }
                 add_task(-(2 + 2 * w.depth_m[m]), TASK_DN_IN);
                 pool.push_back(member(u, w.urole[m])); push_row(w.in_u_row[m]);
                 if (w.Ui[u] < 0) pool.push_back(-1); else push_row(w.dn_row[u]);
@@ -616,20 +676,20 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                     const int x = w.mem_i[k];
                     if (x == u) continue;
                     add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_DN_OUT);
-                    pool.push_back(flags | (w.mem_role[k] << 3)); push_row(w.in_u_row[m]); push_row(w.up_i_row[x]);
+                    pool.push_back(flags | (w.mem_role[k] << 3)); push_row(w.in_u_row[m]); push_up_i(x, w.mem_role[k]);
                     pool.push_back(e->stub_row(chain, v->indiv[x]));
                     if (w.dn_row[x] < 0) pool.push_back(-1); else push_row(w.dn_row[x]);
                     pool.push_back(nd - 1);
                     for (int k2 = w.mem_off[m]; k2 < w.mem_off[m + 1]; k2++) {
                         const int y = w.mem_i[k2];
                         if (y == u || k2 == k) continue;
-                        pool.push_back(w.mem_role[k2]); push_row(w.up_i_row[y]);
+                        pool.push_back(w.mem_role[k2]); push_up_i(y, w.mem_role[k2]);
                     }
                 }
                 add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_PRONG);
                 pool.push_back(flags); push_row(w.in_u_row[m]); pool.push_back(e->prong_row(chain, v->marr[m])); pool.push_back(nd);
                 for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
-                    if (w.mem_i[k] != u) { pool.push_back(w.mem_role[k]); push_row(w.up_i_row[w.mem_i[k]]); }
+                    if (w.mem_i[k] != u) { pool.push_back(w.mem_role[k]); push_up_i(w.mem_i[k], w.mem_role[k]); }
             }
             G.pool_len = (int)pool.size() - G.pool_begin;
         }
@@ -763,6 +823,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     P.n_groups = G; P.n_levels = n_levels;
     P.partial = static_cast<double *>(e->partial.p);
     P.n_out = plan.n_out;
+    { const char *dbg = getenv("PF_SWEEP_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
     {
         int rows = 0, rows_smem = 0;
         for (auto &sg : plan.groups) { rows += sg.n_rows; rows_smem += sg.n_rows_smem; }
@@ -819,6 +880,13 @@ extern "C" int pf_sweep_batch(pf_engine *e, int32_t n, const int32_t *chains, co
     int rc = run_sweeps(e, n, chains, views, static_cast<double *>(e->result.p), &n_out);
     if (rc) return rc;
     return fetch_result(e, ll_cc, n_out);
+}
+
+extern "C" int pf_sweep_batch_dev(pf_engine *e, int32_t n, const int32_t *chains, const pf_graph_view *views, double *ll_cc_dev)
+{
+    if (!e || !views || n < 0) return fail(PF_EINVAL, "null argument");
+    int n_out = 0;
+    return run_sweeps(e, n, chains, views, ll_cc_dev, &n_out);
 }
 
 extern "C" int pf_sweep(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc)
@@ -921,6 +989,14 @@ extern "C" int pf_eval_batch(pf_engine *e, int32_t n, const int32_t *chains, con
     int rc = run_evals(e, n, chains, kids, prop_begin, props, static_cast<double *>(e->result.p));
     if (rc) return rc;
     return fetch_result(e, lsum, n_props);
+}
+
+extern "C" int pf_eval_batch_dev(pf_engine *e, int32_t n, const int32_t *chains, const int32_t *kids,
+                                 const int32_t *prop_begin, const pf_proposal *props, double *lsum_dev)
+{
+    if (!e || n < 0 || !kids || !prop_begin) return fail(PF_EINVAL, "null argument");
+    if (prop_begin[n] > 0 && (!props || !lsum_dev)) return fail(PF_EINVAL, "null argument");
+    return run_evals(e, n, chains, kids, prop_begin, props, lsum_dev);
 }
 
 extern "C" int pf_eval(pf_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_proposal *props, double *lsum)

@@ -90,17 +90,10 @@ __device__ __forceinline__ Tri prod_rows(const SweepCtx &C, const int *rows, int
 // A selfing marriage uses the same tensor and reads only its diagonal (gm == gp).
 __device__ __forceinline__ void fold(Mat3 &W, int role, Tri in)
 {
-    const Sym3 K = kid_matrix(in);
-    const bool kid = role == 2, pa = role == 0;
-    W.m[0] *= kid ? K.a00 : in.x;
-    W.m[1] *= kid ? K.a01 : pa ? in.y : in.x;
-    W.m[2] *= kid ? K.a02 : pa ? in.z : in.x;
-    W.m[3] *= kid ? K.a01 : pa ? in.x : in.y;
-    W.m[4] *= kid ? K.a11 : in.y;
-    W.m[5] *= kid ? K.a12 : pa ? in.z : in.y;
-    W.m[6] *= kid ? K.a02 : pa ? in.x : in.z;
-    W.m[7] *= kid ? K.a12 : pa ? in.y : in.z;
-    W.m[8] *= kid ? K.a22 : in.z;
+    // role is warp-uniform (one task per warp), so these branches never diverge
+    if (role == 2) mat_mul_kid(W, in);
+    else if (role == 0) mat_mul_pa(W, in);
+    else mat_mul_ma(W, in);
 }
 __device__ __forceinline__ Tri emit(const Mat3 &W, int role, int selfing)
 {
@@ -115,9 +108,14 @@ __device__ __forceinline__ void ones9(Mat3 &W)
 }
 
 // fold the listed { role, up_i_row } members into W
+// up message of a family member: a stored row, or recomputed for a leaf
+__device__ __forceinline__ Tri up_msg(const SweepCtx &C, int ref)
+{
+    return ref < 0 ? local_of(C, ref & 0x7fffffff) : ld(resolve(C, ref));
+}
 __device__ __forceinline__ void fold_members(const SweepCtx &C, Mat3 &W, const int *mem, int n)
 {
-    for (int y = 0; y < n; y++) fold(W, mem[2 * y], ld(resolve(C, mem[2 * y + 1])));
+    for (int y = 0; y < n; y++) fold(W, mem[2 * y], up_msg(C, mem[2 * y + 1]));
 }
 
 __device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &C, const int *t)
@@ -158,7 +156,7 @@ __device__ __forceinline__ void task_dn_out(const SweepCtx &C, const int *t)
     fold(W, (flags >> 1) & 3, ld(resolve(C, t[1])));
     fold_members(C, W, t + 6, t[5]);
     const Tri dn = emit(W, flags >> 3, flags & 1);
-    st(resolve(C, t[3]), mul(ld(resolve(C, t[2])), dn));
+    st(resolve(C, t[3]), mul(up_msg(C, t[2]), dn));
     if (t[4] >= 0) st(resolve(C, t[4]), dn);
 }
 
@@ -246,6 +244,8 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(const __grid_co
         for (int ti = beg + warp; ti < end; ti += SWEEP_WARPS) {
             const SweepTask tk = tasks[ti];
             const int *t = pool + (tk.off - G.pool_begin);
+            if (P.debug == 1) continue;
+            if (P.debug == 2 && tk.kind != TASK_ROOT) { if (t[0] == 0x7fffffff) break; continue; }
             switch (tk.kind) {
             case TASK_ROOT: task_root(P, C, t); break;
             case TASK_UP_IN: task_up_in(C, t); break;

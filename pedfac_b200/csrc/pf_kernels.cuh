@@ -46,6 +46,9 @@ namespace pf {
 // 1 mother, 2 kid. flags = selfing | (role of u(m) in m) << 1.
 enum TaskKind : int { TASK_ROOT = 0, TASK_UP_IN = 1, TASK_UP_M = 2, TASK_DN_IN = 3, TASK_DN_OUT = 4, TASK_PRONG = 5 };
 constexpr int SMEM_ROW_BIT = 1 << 29;
+// in place of an up_i row reference: the member is a leaf (no marriage below it), its up message
+// is its local factor, recomputed from the staged genotype tile: LEAF_REF_BIT | member
+constexpr unsigned LEAF_REF_BIT = 0x80000000u;
 
 struct SweepTask { int kind; int off; };
 
@@ -82,6 +85,7 @@ struct SweepParams {
     int n_groups, n_levels;
     double *partial;        // [n_tiles][n_out] per-tile log Z sums
     int n_out;
+    int debug;              // measurement aid (PF_SWEEP_DEBUG): 1 = skip task bodies
 };
 
 constexpr int SWEEP_WARPS = 16;

@@ -17,6 +17,9 @@ from .abi import PF_PROP_PRONG, PF_PROP_TRIO, PROPOSAL_DTYPE
 from .pedigree import Pedigree
 
 
+GENO_BLOCK = 50
+
+
 @dataclass
 class SynthData:
     n_total: int               # individuals in the true pedigree (observed + unobserved)
@@ -38,7 +41,7 @@ class SynthData:
 def simulate(n_total: int, n_loci: int, *, soft: bool, seed: int = 46, n_gen: int = 3,
              mean_kids: float = 2.5, geno_err: float = 0.02, observe_frac: float = 0.8,
              missing_frac: float = 0.02, remate_frac: float = 0.1,
-             max_component: int = 150) -> SynthData:
+             max_component: int = 150, locus_range=None) -> SynthData:
     rng = np.random.default_rng(seed)
     # generation sizes: each couple has Poisson(mean_kids) kids, so sizes grow by mean_kids/2
     growth = mean_kids / 2.0
@@ -107,44 +110,49 @@ def simulate(n_total: int, n_loci: int, *, soft: bool, seed: int = 46, n_gen: in
         for kk, c in zip(kids, couple_of_kid):
             union(couples[c][0], int(kk))
 
-    # allele frequencies and gene drop (two haplotypes per individual)
-    af = rng.beta(10.0, 10.0, size=n_loci)
-    maf = np.minimum(af, 1.0 - af)
-    hap = np.zeros((2, n_total, n_loci), dtype=np.uint8)
-    founders = np.flatnonzero(pa < 0)
-    hap[:, founders, :] = (rng.random((2, len(founders), n_loci)) < maf).astype(np.uint8)
-    for k in range(1, n_gen):
-        kids = np.arange(start[k], start[k + 1])
-        pick_p = rng.integers(0, 2, size=(len(kids), n_loci))     # independent loci (unlinked SNPs)
-        pick_m = rng.integers(0, 2, size=(len(kids), n_loci))
-        hp, hm = hap[:, pa[kids], :], hap[:, ma[kids], :]
-        hap[0, kids, :] = np.where(pick_p == 0, hp[0], hp[1])
-        hap[1, kids, :] = np.where(pick_m == 0, hm[0], hm[1])
-    flip = rng.random((2, n_total, n_loci)) < geno_err
-    obs_hap = np.abs(hap.astype(np.int8) - flip.astype(np.int8)).astype(np.uint8)
-    codes = (obs_hap[0] + obs_hap[1]).astype(np.uint8)
-
+    # genotypes are generated in blocks of GENO_BLOCK loci, each from its own seeded stream, so
+    # a rank of a locus-sharded run can generate just its shard and still see the same data
     observed = rng.random(n_total) < observe_frac
     if not observed.any():
         observed[:] = True
-    # front-end recoding: "0" = major allele among observed calls; aFreq = freq of "1", 3 decimals
-    f1 = codes[observed].mean(axis=0) / 2.0
-    swap = f1 > 0.5
-    codes[:, swap] = 2 - codes[:, swap]
-    f1 = np.where(swap, 1.0 - f1, f1)
-    afreq = np.clip(np.round(f1, 3), 0.001, 0.5)
-
-    soft_num = None
-    if soft:
-        base = np.full((n_total, n_loci, 3), geno_err / 2.0)
-        np.put_along_axis(base, codes[..., None].astype(np.int64), 1.0 - geno_err, axis=2)
-        noise = rng.gamma(4.0, 0.25, size=base.shape)
-        lik = base * noise
-        lik /= lik.sum(axis=2, keepdims=True)
-        soft_num = np.clip(np.round(lik * 10000.0), 1, 65535).astype(np.uint16)
-    else:
-        miss = rng.random(codes.shape) < missing_frac
-        codes = np.where(miss, 3, codes).astype(np.uint8)
+    l0, l1 = (0, n_loci) if locus_range is None else locus_range
+    codes = np.zeros((n_total, n_loci), dtype=np.uint8)
+    soft_num = np.zeros((n_total, n_loci, 3), dtype=np.uint16) if soft else None
+    afreq = np.full(n_loci, 0.25)
+    founders = np.flatnonzero(pa < 0)
+    for b0 in range(l0 - l0 % GENO_BLOCK, l1, GENO_BLOCK):
+        b1 = min(b0 + GENO_BLOCK, n_loci)
+        nb = b1 - b0
+        brng = np.random.default_rng([seed, 7919, b0 // GENO_BLOCK])
+        af = brng.beta(10.0, 10.0, size=nb)
+        maf = np.minimum(af, 1.0 - af)
+        hap = np.zeros((2, n_total, nb), dtype=np.uint8)
+        hap[:, founders, :] = (brng.random((2, len(founders), nb)) < maf).astype(np.uint8)
+        for k in range(1, n_gen):                                 # gene drop, unlinked loci
+            kids = np.arange(start[k], start[k + 1])
+            pick_p = brng.integers(0, 2, size=(len(kids), nb), dtype=np.uint8)
+            pick_m = brng.integers(0, 2, size=(len(kids), nb), dtype=np.uint8)
+            hp, hm = hap[:, pa[kids], :], hap[:, ma[kids], :]
+            hap[0, kids, :] = np.where(pick_p == 0, hp[0], hp[1])
+            hap[1, kids, :] = np.where(pick_m == 0, hm[0], hm[1])
+        flip = brng.random((2, n_total, nb)) < geno_err          # per-allele flip errors
+        hap ^= flip.astype(np.uint8)
+        cb = (hap[0] + hap[1]).astype(np.uint8)
+        # front-end recoding: "0" = major allele among observed calls; aFreq = freq of "1", 3 decimals
+        f1 = cb[observed].mean(axis=0) / 2.0
+        swap = f1 > 0.5
+        cb[:, swap] = 2 - cb[:, swap]
+        f1 = np.where(swap, 1.0 - f1, f1)
+        afreq[b0:b1] = np.clip(np.round(f1, 3), 0.001, 0.5)
+        if soft:
+            base = np.full((n_total, nb, 3), geno_err / 2.0)
+            np.put_along_axis(base, cb[..., None].astype(np.int64), 1.0 - geno_err, axis=2)
+            lik = base * brng.gamma(4.0, 0.25, size=base.shape)
+            lik /= lik.sum(axis=2, keepdims=True)
+            soft_num[:, b0:b1, :] = np.clip(np.round(lik * 10000.0), 1, 65535).astype(np.uint16)
+        else:
+            cb = np.where(brng.random(cb.shape) < missing_frac, 3, cb).astype(np.uint8)
+        codes[:, b0:b1] = cb
 
     slot = np.empty(n_total, np.int32)
     slot[observed] = np.arange(observed.sum())
