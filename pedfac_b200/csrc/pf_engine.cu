@@ -103,7 +103,7 @@ struct pf_engine {
     std::vector<SoftChunk> soft_chunks;
     std::vector<double> h_eps;            // local shard, for validation only
 
-    DevBuf scratch, plan, partial, result;
+    DevBuf scratch, plan, partial, result, counters;
     Staging staging;
     double *h_result = nullptr; size_t h_result_cap = 0;
 
@@ -142,7 +142,7 @@ extern "C" int pf_destroy(pf_engine *e)
     cudaFree(e->d_rows); cudaFree(e->d_eps); cudaFree(e->d_hard);
     cudaFree(e->d_kind); cudaFree(e->d_eptr); cudaFree(e->d_denom);
     for (auto &c : e->soft_chunks) cudaFree(c.base);
-    e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release();
+    e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release(); e->counters.release();
     e->staging.release();
     if (e->h_result) cudaFreeHost(e->h_result);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -757,10 +757,16 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     // shared-memory budget per group: stage the plan slice if it is small, then as many transient
     // rows as fit; the launch uses the largest layout
     int smem_bytes = 0, scratch_rows = 0;
+    bool all_staged = true;
+    for (int g = 0; g < G; g++) {
+        const int slice0 = (plan.groups[g].task_end - plan.groups[g].task_begin) * 8 + plan.groups[g].pool_len * 4 + plan.groups[g].emis_count * (int)sizeof(EmisEnt);
+        if (slice0 > SWEEP_PLAN_SMEM_MAX) all_staged = false;
+    }
     for (int g = 0; g < G; g++) {
         SweepGroup &sg = plan.groups[g];
         const int slice = (sg.task_end - sg.task_begin) * 8 + sg.pool_len * 4 + sg.emis_count * (int)sizeof(EmisEnt);
-        sg.staged = slice <= SWEEP_PLAN_SMEM_MAX ? 1 : 0;
+        (void)slice;
+        sg.staged = all_staged ? 1 : 0;
         sg.n_rows_smem = 0;
         const SweepSmem L0 = sweep_smem_layout(sg, n_levels);
         if (L0.total > SWEEP_SMEM_MAX) return fail(PF_EINVAL, "sweep plan too deep for shared memory (%d levels)", n_levels);
@@ -823,7 +829,6 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     P.n_groups = G; P.n_levels = n_levels;
     P.partial = static_cast<double *>(e->partial.p);
     P.n_out = plan.n_out;
-    { const char *dbg = getenv("PF_SWEEP_DEBUG"); P.debug = dbg ? atoi(dbg) : 0; }
     {
         int rows = 0, rows_smem = 0;
         for (auto &sg : plan.groups) { rows += sg.n_rows; rows_smem += sg.n_rows_smem; }
@@ -831,7 +836,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         memcpy(e->last_plan, st, sizeof st);
     }
     e->prof_begin(0);
-    launch_sweep(P, n_tiles, smem_bytes, e->stream);
+    launch_sweep(P, n_tiles, smem_bytes, all_staged, e->stream);
     e->prof_end();
     e->launches++;
     CU(cudaGetLastError());
@@ -945,17 +950,24 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
         for (int b = prop_begin[i]; b < prop_begin[i + 1]; b += EVAL_G)
             hg[gi++] = EvalGroup{e->stub_row(chain, kid), b, std::min(EVAL_G, prop_begin[i + 1] - b), 0};
     }
-    // chunking: enough (chunk x group-block) CTAs to fill the GPU, at most 16 lane-iterations per chunk
+    // chunking: (chunks x group blocks) ~ one full wave of 148 SMs x 8 resident blocks, at least
+    // 4 lane-iterations per chunk, at most 128 (the running mantissa product needs renormalising
+    // only every 512 factors)
     const int group_blocks = (n_groups + EVAL_WARPS - 1) / EVAL_WARPS;
-    int want_chunks = std::max(1, (592 + group_blocks - 1) / group_blocks);
-    int chunk_loci = ((e->Sl + want_chunks - 1) / want_chunks + 31) / 32 * 32;
-    chunk_loci = std::max(32, std::min(chunk_loci, 512));
-    const int n_chunks = (e->Sl + chunk_loci - 1) / chunk_loci;
+    const int max_chunks = std::max(1, (e->Sl + 127) / 128);
+    int n_chunks = std::max(1, std::min(max_chunks, (148 * 8 + group_blocks / 2) / group_blocks));
+    int chunk_loci = ((e->Sl + n_chunks - 1) / n_chunks + 31) / 32 * 32;
+    chunk_loci = std::min(chunk_loci, 4096);
+    n_chunks = (e->Sl + chunk_loci - 1) / chunk_loci;
 
     int rc = sync_tables(e);
     if (rc) return rc;
     CU(e->plan.reserve(blob));
     CU(e->partial.reserve((size_t)n_chunks * n_props * sizeof(double)));
+    if ((size_t)group_blocks * sizeof(unsigned) > e->counters.cap) {
+        CU(e->counters.reserve((size_t)group_blocks * sizeof(unsigned) * 2));
+        CU(cudaMemsetAsync(e->counters.p, 0, e->counters.cap, e->stream));
+    }
     CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
     CU(e->staging.mark(slot, e->stream));
     EvalParams P;
@@ -964,14 +976,10 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     P.props = reinterpret_cast<const EvalProp *>(static_cast<char *>(e->plan.p) + off_props);
     P.n_groups = n_groups; P.n_props = n_props; P.chunk_loci = chunk_loci;
     P.partial = static_cast<double *>(e->partial.p);
+    P.out = out_dev;
+    P.counters = static_cast<unsigned *>(e->counters.p);
     e->prof_begin(1);
     launch_eval(P, n_chunks, e->stream);
-    e->prof_end();
-    e->launches++;
-    CU(cudaGetLastError());
-    ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_chunks, n_props};
-    e->prof_begin(2);
-    launch_reduce(R, e->stream);
     e->prof_end();
     e->launches++;
     CU(cudaGetLastError());

@@ -21,25 +21,60 @@ struct SweepCtx {
     int Sp, Sl, s, lane, tile;
 };
 
-// A row reference resolved for this thread: element of state g is p[g * stride].
-struct RowRef { double *p; int stride; };
-
-__device__ __forceinline__ RowRef resolve(const SweepCtx &C, int ref)
+// Row access. A reference is either a transient row in shared memory, a spilled transient row or
+// a persistent row in global memory; the branch is warp-uniform and keeps each access in a known
+// address space (LDS / LDG instead of generic loads with 64-bit address selects).
+__device__ __forceinline__ Tri ld_row(const SweepCtx &C, int ref)
 {
-    // branch-free: three address spaces (persistent rows, spilled transient rows, shared memory)
-    const bool sm = ref & SMEM_ROW_BIT, tr = ref & SCRATCH_BIT;
-    double *base = sm ? C.smem_lane : tr ? C.scratch_lane : C.rows_lane;
-    const int stride = sm ? TILE_LOCI : C.Sp;
-    return RowRef{base + (size_t)(ref & (SMEM_ROW_BIT - 1)) * (size_t)(3 * stride), stride};
+    const int idx = ref & (SMEM_ROW_BIT - 1);
+    if (ref & SMEM_ROW_BIT) {
+        const double *p = C.smem_lane + idx * (3 * TILE_LOCI);
+        return Tri{p[0], p[TILE_LOCI], p[2 * TILE_LOCI]};
+    }
+    const double *p = ((ref & SCRATCH_BIT) ? C.scratch_lane : C.rows_lane) + (size_t)idx * 3 * C.Sp;
+    return Tri{p[0], p[C.Sp], p[2 * C.Sp]};
 }
-__device__ __forceinline__ Tri ld(RowRef r) { return Tri{r.p[0], r.p[r.stride], r.p[2 * r.stride]}; }
-__device__ __forceinline__ void st(RowRef r, Tri v) { r.p[0] = v.x; r.p[r.stride] = v.y; r.p[2 * r.stride] = v.z; }
+__device__ __forceinline__ void st_row(const SweepCtx &C, int ref, Tri v)
+{
+    const int idx = ref & (SMEM_ROW_BIT - 1);
+    if (ref & SMEM_ROW_BIT) {
+        double *p = C.smem_lane + idx * (3 * TILE_LOCI);
+        p[0] = v.x; p[TILE_LOCI] = v.y; p[2 * TILE_LOCI] = v.z;
+        return;
+    }
+    double *p = ((ref & SCRATCH_BIT) ? C.scratch_lane : C.rows_lane) + (size_t)idx * 3 * C.Sp;
+    p[0] = v.x; p[C.Sp] = v.y; p[2 * C.Sp] = v.z;
+}
 
 // exact num / den for 16-bit numerators: Markstein's correction step on the rounded reciprocal
 __device__ __forceinline__ double div_exact(double num, double den, double rcp)
 {
     const double q = num * rcp;
     return fma(fma(-den, q, num), rcp, q);
+}
+
+// one locus of a genotype row: planes of `ps` loci starting at p, this thread's locus index i
+// (_ReadPedfile@0x10000b1ca-0x10000b6e2 emission model)
+__device__ __forceinline__ Tri decode_emis(const char *p, unsigned kind, int i, int ps, const EmisEnt &E, double ep)
+{
+    if (kind == EMIS_HARD) {
+        const uint32_t w = reinterpret_cast<const uint32_t *>(p)[i >> 4];
+        const int c = (w >> ((i & 15) * 2)) & 3;
+        if (c == 3) return Tri{1.0, 1.0, 1.0};
+        const double lo = ep / 2.0, hi = 1.0 - ep;
+        return Tri{c == 0 ? hi : lo, c == 1 ? hi : lo, c == 2 ? hi : lo};
+    }
+    if (kind == EMIS_DEC16) {
+        const uint16_t *u = reinterpret_cast<const uint16_t *>(p);
+        const double den = (double)E.denom, rcp = E.rcp;
+        return Tri{div_exact((double)u[i], den, rcp), div_exact((double)u[ps + i], den, rcp), div_exact((double)u[2 * ps + i], den, rcp)};
+    }
+    if (kind == EMIS_F32) {
+        const float *f = reinterpret_cast<const float *>(p);
+        return Tri{(double)f[i], (double)f[ps + i], (double)f[2 * ps + i]};
+    }
+    const double *f = reinterpret_cast<const double *>(p);
+    return Tri{f[i], f[ps + i], f[2 * ps + i]};
 }
 
 // local(i) = emission x (founder ? HWE prior : 1) from the staged genotype tile
@@ -51,29 +86,8 @@ __device__ __forceinline__ Tri local_of(const SweepCtx &C, int member)
     Tri e{1.0, 1.0, 1.0};
     const int l = C.lane;
     if (kind != EMIS_NONE) {
-        const bool staged = off != EMIS_NOT_STAGED;
-        // staged tile: planes of 32 loci; global row: planes of Sp loci
-        const char *p = staged ? C.edata + off
-                               : reinterpret_cast<const char *>(((unsigned long long)E.ptr_hi << 32) | E.ptr_lo);
-        const int i = staged ? l : C.s, ps = staged ? TILE_LOCI : C.Sp;
-        if (kind == EMIS_HARD) {
-            const uint32_t w = reinterpret_cast<const uint32_t *>(p)[i >> 4];
-            const int c = (w >> ((i & 15) * 2)) & 3;
-            if (c != 3) {
-                const double ep = C.eps[l], lo = ep / 2.0, hi = 1.0 - ep;
-                e = Tri{c == 0 ? hi : lo, c == 1 ? hi : lo, c == 2 ? hi : lo};
-            }
-        } else if (kind == EMIS_DEC16) {
-            const uint16_t *u = reinterpret_cast<const uint16_t *>(p);
-            const double den = (double)E.denom, rcp = E.rcp;
-            e = Tri{div_exact((double)u[i], den, rcp), div_exact((double)u[ps + i], den, rcp), div_exact((double)u[2 * ps + i], den, rcp)};
-        } else if (kind == EMIS_F32) {
-            const float *f = reinterpret_cast<const float *>(p);
-            e = Tri{(double)f[i], (double)f[ps + i], (double)f[2 * ps + i]};
-        } else {
-            const double *f = reinterpret_cast<const double *>(p);
-            e = Tri{f[i], f[ps + i], f[2 * ps + i]};
-        }
+        if (off != EMIS_NOT_STAGED) e = decode_emis(C.edata + off, kind, l, TILE_LOCI, E, C.eps[l]);
+        else e = decode_emis(reinterpret_cast<const char *>(((unsigned long long)E.ptr_hi << 32) | E.ptr_lo), kind, C.s, C.Sp, E, C.eps[l]);
     }
     if (member & 4) e = mul(e, Tri{C.prior[l], C.prior[TILE_LOCI + l], C.prior[2 * TILE_LOCI + l]});
     return e;
@@ -81,7 +95,7 @@ __device__ __forceinline__ Tri local_of(const SweepCtx &C, int member)
 
 __device__ __forceinline__ Tri prod_rows(const SweepCtx &C, const int *rows, int n, Tri acc)
 {
-    for (int j = 0; j < n; j++) acc = mul(acc, ld(resolve(C, rows[j])));
+    for (int j = 0; j < n; j++) acc = mul(acc, ld_row(C, rows[j]));
     return acc;
 }
 
@@ -111,7 +125,7 @@ __device__ __forceinline__ void ones9(Mat3 &W)
 // up message of a family member: a stored row, or recomputed for a leaf
 __device__ __forceinline__ Tri up_msg(const SweepCtx &C, int ref)
 {
-    return ref < 0 ? local_of(C, ref & 0x7fffffff) : ld(resolve(C, ref));
+    return ref < 0 ? local_of(C, ref & 0x7fffffff) : ld_row(C, ref);
 }
 __device__ __forceinline__ void fold_members(const SweepCtx &C, Mat3 &W, const int *mem, int n)
 {
@@ -121,7 +135,7 @@ __device__ __forceinline__ void fold_members(const SweepCtx &C, Mat3 &W, const i
 __device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &C, const int *t)
 {
     const Tri v = prod_rows(C, t + 4, t[3], local_of(C, t[0]));
-    st(resolve(C, t[1]), v);
+    st_row(C, t[1], v);
     if (t[2] >= 0) {
         LogProd z; lp_init(z);
         if (C.s < C.Sl) lp_mul(z, (v.x + v.y) + v.z);
@@ -132,44 +146,47 @@ __device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &
 
 __device__ __forceinline__ void task_up_in(const SweepCtx &C, const int *t)
 {
-    st(resolve(C, t[1]), prod_rows(C, t + 3, t[2], local_of(C, t[0])));
+    st_row(C, t[1], prod_rows(C, t + 3, t[2], local_of(C, t[0])));
 }
 
 __device__ __forceinline__ void task_up_m(const SweepCtx &C, const int *t)
 {
     Mat3 W; ones9(W);
     fold_members(C, W, t + 3, t[2]);
-    st(resolve(C, t[1]), emit(W, t[0] >> 1, t[0] & 1));
+    st_row(C, t[1], emit(W, t[0] >> 1, t[0] & 1));
 }
 
 __device__ __forceinline__ void task_dn_in(const SweepCtx &C, const int *t)
 {
     Tri in_u = local_of(C, t[0]);
-    if (t[2] >= 0) in_u = mul(in_u, ld(resolve(C, t[2])));
-    st(resolve(C, t[1]), prod_rows(C, t + 4, t[3], in_u));
+    if (t[2] >= 0) in_u = mul(in_u, ld_row(C, t[2]));
+    st_row(C, t[1], prod_rows(C, t + 4, t[3], in_u));
 }
 
 __device__ __forceinline__ void task_dn_out(const SweepCtx &C, const int *t)
 {
     const int flags = t[0];
     Mat3 W; ones9(W);
-    fold(W, (flags >> 1) & 3, ld(resolve(C, t[1])));
+    fold(W, (flags >> 1) & 3, ld_row(C, t[1]));
     fold_members(C, W, t + 6, t[5]);
     const Tri dn = emit(W, flags >> 3, flags & 1);
-    st(resolve(C, t[3]), mul(up_msg(C, t[2]), dn));
-    if (t[4] >= 0) st(resolve(C, t[4]), dn);
+    st_row(C, t[3], mul(up_msg(C, t[2]), dn));
+    if (t[4] >= 0) st_row(C, t[4], dn);
 }
 
 __device__ __forceinline__ void task_prong(const SweepCtx &C, const int *t)
 {
     const int flags = t[0];
     Mat3 W; ones9(W);
-    fold(W, (flags >> 1) & 3, ld(resolve(C, t[1])));
+    fold(W, (flags >> 1) & 3, ld_row(C, t[1]));
     fold_members(C, W, t + 4, t[3]);
-    st(resolve(C, t[2]), (flags & 1) ? self_to_kid(mat_diag(W)) : mat_to_kid(W));
+    st_row(C, t[2], (flags & 1) ? self_to_kid(mat_diag(W)) : mat_to_kid(W));
 }
 
-__global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(const __grid_constant__ SweepParams P)
+// STAGED: every group's plan slice lives in shared memory (the normal case); otherwise plans are
+// read from global memory. Two instantiations keep every pointer in a known address space.
+template <bool STAGED>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, 1) sweep_kernel(const __grid_constant__ SweepParams P)
 {
     extern __shared__ __align__(16) char smem[];
     const DevView &D = P.D;
@@ -189,7 +206,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(const __grid_co
     const SweepTask *tasks = P.tasks + G.task_begin;
     const int *pool = P.pool + G.pool_begin;
     const EmisEnt *emis = P.emis + G.emis_begin;
-    if (G.staged) {
+    if (STAGED) {
         int *d;
         const int *src;
         d = reinterpret_cast<int *>(smem + L.tasks); src = reinterpret_cast<const int *>(tasks);
@@ -198,6 +215,8 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(const __grid_co
         for (int i = tid; i < G.pool_len; i += nthr) d[i] = pool[i];
         d = reinterpret_cast<int *>(smem + L.emis); src = reinterpret_cast<const int *>(emis);
         for (int i = tid; i < G.emis_count * (int)(sizeof(EmisEnt) / 4); i += nthr) d[i] = src[i];
+    }
+    if (STAGED) {
         tasks = reinterpret_cast<const SweepTask *>(smem + L.tasks);
         pool = reinterpret_cast<const int *>(smem + L.pool);
         emis = reinterpret_cast<const EmisEnt *>(smem + L.emis);
@@ -244,8 +263,6 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(const __grid_co
         for (int ti = beg + warp; ti < end; ti += SWEEP_WARPS) {
             const SweepTask tk = tasks[ti];
             const int *t = pool + (tk.off - G.pool_begin);
-            if (P.debug == 1) continue;
-            if (P.debug == 2 && tk.kind != TASK_ROOT) { if (t[0] == 0x7fffffff) break; continue; }
             switch (tk.kind) {
             case TASK_ROOT: task_root(P, C, t); break;
             case TASK_UP_IN: task_up_in(C, t); break;
@@ -259,70 +276,96 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32) sweep_kernel(const __grid_co
     }
 }
 
-void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, cudaStream_t st)
+void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_MAX);
+        cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_MAX);
+        cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_MAX);
         attr_set = true;
     }
     dim3 grid(n_tiles, P.n_groups);
-    sweep_kernel<<<grid, SWEEP_WARPS * 32, smem_bytes, st>>>(P);
+    if (staged) sweep_kernel<true><<<grid, SWEEP_WARPS * 32, smem_bytes, st>>>(P);
+    else sweep_kernel<false><<<grid, SWEEP_WARPS * 32, smem_bytes, st>>>(P);
 }
 
 // ---- proposal evaluation ---------------------------------------------------------------------
 
-__global__ void __launch_bounds__(EVAL_WARPS * 32) eval_kernel(const __grid_constant__ EvalParams P)
+// All row loads of a locus (kid + two rows per proposal of the group) are issued up front and
+// unconditionally — a proposal that has no second row points at the prior row — so one warp keeps
+// 27 independent 256 B segments in flight; the three contraction forms are then all computed and
+// the proposal's kind selects one (a few spare flops on a memory-bound kernel).
+__global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_constant__ EvalParams P)
 {
     const DevView &D = P.D;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gi = blockIdx.y * EVAL_WARPS + warp;
-    if (gi >= P.n_groups) return;
-    const EvalGroup g = P.groups[gi];
     const int chunk = blockIdx.x;
+    EvalGroup g{ROW_PRIOR, 0, 0, 0};
+    if (gi < P.n_groups) g = P.groups[gi];
     const int s_beg = chunk * P.chunk_loci;
     const int s_end = min(s_beg + P.chunk_loci, D.Sl);
+    const size_t row_elems = (size_t)3 * D.Sp;
 
-    EvalProp pr[EVAL_G];
+    int kind[EVAL_G];
     const double *rp[EVAL_G], *rm[EVAL_G];
     LogProd acc[EVAL_G];
 #pragma unroll
     for (int j = 0; j < EVAL_G; j++) {
         lp_init(acc[j]);
-        if (j < g.n) {
-            pr[j] = P.props[g.begin + j];
-            rp[j] = row_ptr(D, pr[j].row_p);
-            rm[j] = row_ptr(D, pr[j].row_m);
-        } else {
-            pr[j].kind = -1; rp[j] = rm[j] = nullptr;
-        }
+        EvalProp pr{0, ROW_PRIOR, ROW_PRIOR, 0};
+        if (j < g.n) pr = P.props[g.begin + j];
+        kind[j] = pr.kind;
+        rp[j] = D.rows + (size_t)pr.row_p * row_elems;
+        rm[j] = D.rows + (size_t)pr.row_m * row_elems;
     }
-    const double *kid_row = row_ptr(D, g.kid_row);
+    const double *kid_row = D.rows + (size_t)g.kid_row * row_elems;
 
     for (int s = s_beg + lane; s < s_end; s += 32) {
         const Tri kid = ld_tri(kid_row, D.Sp, s);
+        Tri xp[EVAL_G], xm[EVAL_G];
+#pragma unroll
+        for (int j = 0; j < EVAL_G; j++) { xp[j] = ld_tri(rp[j], D.Sp, s); xm[j] = ld_tri(rm[j], D.Sp, s); }
         const Sym3 A = kid_matrix(kid);
 #pragma unroll
         for (int j = 0; j < EVAL_G; j++) {
-            if (pr[j].kind < 0) continue;
-            double v;
-            if (pr[j].kind == 0) {
-                const Tri xp = ld_tri(rp[j], D.Sp, s), xm = ld_tri(rm[j], D.Sp, s);
-                v = dot(xm, sym_mv(A, xp));
-            } else if (pr[j].kind == 1) {
-                const Tri xp = ld_tri(rp[j], D.Sp, s);
-                v = dot(kid, self_to_kid(xp));
-            } else {
-                v = dot(ld_tri(rp[j], D.Sp, s), kid);
-            }
-            lp_mul(acc[j], v);
+            const double vt = dot(xm[j], sym_mv(A, xp[j]));         // trio
+            const double vs = dot(kid, self_to_kid(xp[j]));        // selfing
+            const double vp = dot(xp[j], kid);                      // prong
+            const double v = kind[j] == 0 ? vt : kind[j] == 1 ? vs : vp;
+            if (j < g.n) lp_mul(acc[j], v);
         }
     }
 #pragma unroll
     for (int j = 0; j < EVAL_G; j++) {
-        if (pr[j].kind < 0) continue;
+        if (j >= g.n) continue;
         const LogProd r = lp_warp_reduce(acc[j]);
-        if (lane == 0) P.partial[(size_t)chunk * P.n_props + g.begin + j] = lp_log(r);
+        if (lane == 0) { P.partial[(size_t)chunk * P.n_props + g.begin + j] = lp_log(r); __threadfence(); }
+    }
+
+    // fused fixed-order reduction: the last block of this column of the grid to finish adds the
+    // chunks' partial sums in chunk order (deterministic whichever block happens to be last)
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(&P.counters[blockIdx.y], 1u);
+        s_last = done == gridDim.x - 1;
+        if (s_last) P.counters[blockIdx.y] = 0;     // ready for the next launch
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < EVAL_WARPS * EVAL_G) {
+        const int gi2 = blockIdx.y * EVAL_WARPS + threadIdx.x / EVAL_G, j = threadIdx.x % EVAL_G;
+        if (gi2 < P.n_groups) {
+            const EvalGroup g2 = P.groups[gi2];
+            if (j < g2.n) {
+                const double *src = P.partial + g2.begin + j;
+                double sum = 0.0;
+#pragma unroll 8
+                for (int c = 0; c < (int)gridDim.x; c++) sum += __ldcg(src + (size_t)c * P.n_props);
+                P.out[g2.begin + j] = sum;
+            }
+        }
     }
 }
 
@@ -332,20 +375,25 @@ void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st)
     eval_kernel<<<grid, EVAL_WARPS * 32, 0, st>>>(P);
 }
 
-// ---- fixed-order reduction of per-tile / per-chunk partial sums ----------------------------------
+// ---- fixed-order reduction of per-tile partial sums (sweeps) ----------------------------------------
 
+// One warp per output: lanes add parts lane, lane+32, ... (independent L2 loads), then a fixed
+// xor-butterfly adds the 32 lane sums — the order depends only on n_parts, so it is deterministic.
 __global__ void __launch_bounds__(128) reduce_kernel(const __grid_constant__ ReduceParams P)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (i >= P.n) return;
     double acc = 0.0;
-    for (int c = 0; c < P.n_parts; c++) acc += P.partial[(size_t)c * P.n + i];
-    P.out[i] = acc;
+#pragma unroll 4
+    for (int c = lane; c < P.n_parts; c += 32) acc += __ldcg(P.partial + (size_t)c * P.n + i);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) P.out[i] = acc;
 }
 
 void launch_reduce(const ReduceParams &P, cudaStream_t st)
 {
-    reduce_kernel<<<(P.n + 127) / 128, 128, 0, st>>>(P);
+    reduce_kernel<<<(P.n * 32 + 127) / 128, 128, 0, st>>>(P);
 }
 
 } // namespace pf

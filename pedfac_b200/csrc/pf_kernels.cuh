@@ -85,7 +85,6 @@ struct SweepParams {
     int n_groups, n_levels;
     double *partial;        // [n_tiles][n_out] per-tile log Z sums
     int n_out;
-    int debug;              // measurement aid (PF_SWEEP_DEBUG): 1 = skip task bodies
 };
 
 constexpr int SWEEP_WARPS = 16;
@@ -140,6 +139,8 @@ struct EvalParams {
     int n_groups, n_props;
     int chunk_loci;         // multiple of 32
     double *partial;        // [n_chunks][n_props]
+    double *out;            // [n_props] sums over chunks (written by the last block of each column)
+    unsigned *counters;     // [group blocks] arrival counters, zero between launches
 };
 
 struct ReduceParams {
@@ -148,7 +149,7 @@ struct ReduceParams {
     int n_parts, n;
 };
 
-void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, cudaStream_t st);
+void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, cudaStream_t st);
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st);
 void launch_reduce(const ReduceParams &P, cudaStream_t st);
 
