@@ -1,0 +1,1202 @@
+// pedigraph.cpp — Linux `pedigraph` sampler: the host-side chain logic of the reference's
+// exec/pedigraph (a macOS binary shipped without source), restated from its -O0 disassembly,
+// with every likelihood evaluation delegated to the engine behind the C ABI of
+// include/pedfac_cuda.h. Same CLI (-d DIR -n N -r SEEDFILE [-c J] [-s] [-w] [-l]) and the same
+// file contract (prior.txt, geno.txt, optional marriage.txt -> out/ped.txt, out/ll.txt,
+// out/historyNode.csv, out/historyEdge.csv, out/geno.txt), so R/runPedFac.R drives it unmodified
+// (R/runPedFac.R:99-108).
+//
+// Each routine cites the reference routine it follows as pedigraph@<VM address> <symbol>.
+// Differences from the reference, all deliberate and listed in DESIGN.md §7:
+//   * swap moves (_ProposeSwapping@0x100020xxx, enabled by default in the reference) are not
+//     implemented yet: the sampler behaves as the reference does under -w;
+//   * -c 1 (throttle) and -l (loopy BP) are rejected;
+//   * the sweep that ends _PickAndUpdate is merged with the one that follows the next
+//     _PruneIndiv (nothing reads messages in between), so a Gibbs step costs one sweep;
+//   * mnode kid arrays grow (the reference overflows a malloc(8) block).
+//
+// The engine entry points are reached through PFN(name); the default binds libpedfac_cuda
+// (pf_*). The test infrastructure builds the same file against its CPU checker by defining
+// PF_BACKEND_HEADER / PF_BACKEND_PREFIX on the compiler command line.
+#ifndef PF_BACKEND_HEADER
+#define PF_BACKEND_HEADER "../../../include/pedfac_cuda.h"
+#define PF_BACKEND_PREFIX pf_
+#endif
+#include PF_BACKEND_HEADER
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+#define PF_CAT2(a, b) a##b
+#define PF_CAT(a, b) PF_CAT2(a, b)
+#define PFN(name) PF_CAT(PF_BACKEND_PREFIX, name)
+#ifndef PF_ENGINE_T
+#define PF_ENGINE_T PF_CAT(PF_BACKEND_PREFIX, engine)
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// ranlib subset (netlib ranlib.c, Brown & Lovato; L'Ecuyer-Cote combined generator). Only
+// generator 1 is ever current, so setall() reduces to loading the two seeds
+// (_setall@0x10002a2d8, _ignlgi@0x100029fa3, _ranf@0x10002b838, _genunf@0x10002e948, _genbet@0x10002accf).
+namespace rng {
+static long s1 = 1234567890L, s2 = 123456789L;
+static const long m1 = 2147483563L, m2 = 2147483399L, a1 = 40014L, a2 = 40692L;
+
+static void setall(long iseed1, long iseed2) { s1 = iseed1; s2 = iseed2; }
+
+static long ignlgi()
+{
+    long k = s1 / 53668L;
+    s1 = a1 * (s1 - k * 53668L) - k * 12211L;
+    if (s1 < 0) s1 += m1;
+    k = s2 / 52774L;
+    s2 = a2 * (s2 - k * 52774L) - k * 3791L;
+    if (s2 < 0) s2 += m2;
+    long z = s1 - s2;
+    if (z < 1) z += (m1 - 1);
+    return z;
+}
+// _ranf@0x10002b83d-0x10002b8b0: redrawn while the float equals 0.0 or 1.0 (E.C. Anderson's change)
+static float ranf()
+{
+    float r;
+    do { r = (float)((double)ignlgi() * 4.656613057E-10); } while (r == 1.0f || r == 0.0f);
+    return r;
+}
+static float genunf(float low, float high) { return low + (high - low) * ranf(); }
+
+static float genbet(float aa, float bb)
+{
+    const double expmax = 89.0;
+    const float infnty = 1.0E38f;
+    static float olda = -1.0f, oldb = -1.0f;
+    static float result, a, alpha, b, beta, delta, gamma, k1, k2, r, s, t, u1, u2, v, w, y, z;
+    const bool qsame = olda == aa && oldb == bb;
+    if (!qsame) {
+        if (aa <= 0.0 || bb <= 0.0) {
+            fputs(" AA or BB <= 0 in GENBET - Abort!", stderr);
+            fprintf(stderr, " AA: %16.6E BB %16.6E\n", aa, bb);
+            exit(1);
+        }
+        olda = aa; oldb = bb;
+    }
+    if (std::min(aa, bb) > 1.0) {            // algorithm BB
+        if (!qsame) {
+            a = std::min(aa, bb); b = std::max(aa, bb);
+            alpha = a + b;
+            beta = (float)sqrt((alpha - 2.0) / (2.0 * a * b - alpha));
+            gamma = (float)(a + 1.0 / beta);
+        }
+        for (;;) {
+            u1 = ranf(); u2 = ranf();
+            v = (float)(beta * log(u1 / (1.0 - u1)));
+            w = v > expmax ? infnty : (float)(a * exp(v));
+            z = (float)(pow(u1, 2.0) * u2);
+            r = (float)(gamma * v - 1.3862944);
+            s = a + r - w;
+            if (s + 2.609438 >= 5.0 * z) break;
+            t = (float)log(z);
+            if (s > t) break;
+            if (!(r + alpha * log(alpha / (b + w)) < t)) break;
+        }
+        result = aa == a ? w / (b + w) : b / (b + w);
+        return result;
+    }
+    // algorithm BC
+    if (!qsame) {
+        a = std::max(aa, bb); b = std::min(aa, bb);
+        alpha = a + b;
+        beta = (float)(1.0 / b);
+        delta = (float)(1.0 + a - b);
+        k1 = (float)(delta * (1.38889E-2 + 4.16667E-2 * b) / (a * beta - 0.777778));
+        k2 = (float)(0.25 + (0.5 + 0.25 / delta) * b);
+    }
+    for (;;) {
+        u1 = ranf(); u2 = ranf();
+        if (u1 < 0.5) {
+            y = u1 * u2; z = u1 * y;
+            if (0.25 * u2 + z - y >= k1) continue;
+        } else {
+            z = (float)(pow(u1, 2.0) * u2);
+            if (z <= 0.25) {
+                v = (float)(beta * log(u1 / (1.0 - u1)));
+                w = v > expmax ? infnty : (float)(a * exp(v));
+                break;
+            }
+            if (z >= k2) continue;
+        }
+        v = (float)(beta * log(u1 / (1.0 - u1)));
+        w = v > expmax ? infnty : (float)(a * exp(v));
+        if (alpha * (log(alpha / (b + w)) + v) - 1.3862944 < log(z)) continue;
+        break;
+    }
+    result = a == aa ? w / (b + w) : b / (b + w);
+    return result;
+}
+} // namespace rng
+
+// ---------------------------------------------------------------------------------------------
+// Pedigree state (`ped`, `indiv`, `mnode`, `choice`)
+
+struct Indiv {
+    int sex = 0, sexWasUnknown = 0, userID = 0, gen = 0;
+    double genTime = 0;
+    bool observed = false, founder = false, reductive = false, queued = false;
+    int unobsDegree = 0;
+    std::vector<int> M, edge;       // attached marriages and the edge index in each (0 pa, 1 ma, >=2 kid)
+};
+struct Marr {
+    int pa = -1, ma = -1;
+    std::vector<int> kids;
+    bool selfing = false, mark = false;
+    int nEdges() const { return 2 + (int)kids.size(); }
+};
+struct Choice { int mnode, pa, ma, selfing, kind; };
+
+struct Opts {
+    std::string dir, seedfile = "rand.tem";
+    int nIter = 1, cyclic = 0;
+    bool selfing = false, diswap = false, loopy = false;
+};
+
+struct Ped {
+    int S = 0, nGen = 0, nIndivDecl = 0, nObs = 0, nMarDecl = 0, maxID = 0, maxUnobsLayer = 2;
+    double maxAge = 1.0, minAge = 1.0;
+    std::vector<double> afreq, eps, obsFrac;
+    std::vector<int> nObsPerGen, nIndivPerGen;
+    int nIndivUsed = 0, nMarrUsed = 0, capIndiv = 0, capMarr = 0;
+    std::vector<Indiv> indiv;
+    std::vector<Marr> marr;
+    std::vector<char> indivActive, marrActive;
+    std::vector<int> cc, ccDirty;
+    int nCC = 0, nDirty = 0;
+    std::vector<double> LLcc;
+    double LLtot = 0;
+    std::vector<int> freeIndiv, freeMarr;
+    std::vector<std::vector<int>> parentCand;   // ped->ff0 (<= 15 per observed kid)
+    std::vector<int> observedSorted, unobsQueue;
+    int iter = 0;
+    // choice list
+    std::vector<Choice> ch;
+    std::vector<double> chll;
+    int prev[3] = {-1, -1, -1}, neu[4] = {-1, -1, -1, 0}, picked = -1, t = 0;
+    // candidate lists by sex (0 unknown, 1 male, 2 female)
+    std::vector<std::pair<int, double>> cand[3];
+    PF_ENGINE_T *eng = nullptr;
+    FILE *fNode = nullptr, *fEdge = nullptr, *fPed = nullptr, *fGeno = nullptr, *fLL = nullptr;
+    long n_proposals = 0, n_sweeps = 0;
+};
+
+static void die(const char *msg)
+{
+    fprintf(stderr, "%s: %s\n", msg, PFN(last_error)());
+    exit(-1);
+}
+
+// history rows (graph-visualiser event trace)
+static int group_of(const Indiv &x) { return x.sex * 10 + (x.observed ? 1 : 0); }
+static void hist_node(Ped &p, int action, int i)
+{
+    const Indiv &x = p.indiv[i];
+    fprintf(p.fNode, "%i,%i,%i,%i,%i,%i\n", p.t, action, x.userID, x.userID, x.gen << 1, group_of(x));
+}
+static void hist_mnode(Ped &p, int action, int m)
+{
+    const Marr &mm = p.marr[m];
+    const int a = p.indiv[mm.pa].userID, b = p.indiv[mm.ma].userID;
+    fprintf(p.fNode, "%i,%i,%i-%i,%i-%i,%i,m-nodes\n", p.t, action, a, b, a, b, (p.indiv[mm.pa].gen << 1) - 1);
+}
+static void hist_edge(Ped &p, int action, int m, int to)
+{
+    const Marr &mm = p.marr[m];
+    const int a = p.indiv[mm.pa].userID, b = p.indiv[mm.ma].userID;
+    fprintf(p.fEdge, "%i,%i,%i-%i-%i,%i-%i,%i\n", p.t, action, a, b, p.indiv[to].userID, a, b, p.indiv[to].userID);
+}
+
+static void mark_dirty(Ped &p, int label)
+{
+    if (p.ccDirty[label] == 0) p.nDirty++;
+    p.ccDirty[label] = 1;
+}
+
+// _Transverse_fg@0x100006a08 + _DFS@0x100004d58: label everything connected to `start`
+static void label_component(Ped &p, int start, int label)
+{
+    std::vector<int> stack{start};
+    p.cc[start] = label;
+    while (!stack.empty()) {
+        const int i = stack.back(); stack.pop_back();
+        for (int m : p.indiv[i].M) {
+            const Marr &mm = p.marr[m];
+            auto visit = [&](int y) { if (p.cc[y] != label) { p.cc[y] = label; stack.push_back(y); } };
+            visit(mm.pa);
+            if (!mm.selfing) visit(mm.ma);
+            for (int k : mm.kids) visit(k);
+        }
+    }
+}
+
+// _UpdateConComp@0x100013128: the component that contained `id` may have split (or vanished)
+static void UpdateConComp(Ped &p, int id)
+{
+    const int old = p.cc[id];
+    bool any = false;
+    for (int i = 0; i < p.nIndivUsed; i++)
+        if (p.indivActive[i] && p.cc[i] == old) { p.cc[i] = -5; any = true; }
+    if (!any) {
+        if (p.ccDirty[old] == 1) p.nDirty--;
+        p.ccDirty[old] = 0;
+        if (p.nCC - 1 != old) {
+            for (int i = 0; i < p.nIndivUsed; i++)
+                if (p.indivActive[i] && p.cc[i] == p.nCC - 1) p.cc[i] = old;
+            if (p.ccDirty[p.nCC - 1] == 1) { p.ccDirty[old] = 1; p.ccDirty[p.nCC - 1] = 0; }
+            p.LLcc[old] = p.LLcc[p.nCC - 1];
+        }
+        p.nCC--;
+        return;
+    }
+    int found = 0, label = old;
+    for (int i = 0; i < p.nIndivUsed; i++) {
+        if (!p.indivActive[i] || p.cc[i] != -5) continue;
+        label_component(p, i, label);
+        found++;
+        if (found == 1) {
+            mark_dirty(p, label);
+            label = p.nCC;
+        } else {
+            p.ccDirty[p.nCC] = 1; p.nDirty++;
+            p.nCC++;
+            label = p.nCC;
+        }
+    }
+}
+
+// _AssignConComp@0x100013548: merge two labels (smaller wins; last label fills the hole)
+static void AssignConComp(Ped &p, int a, int b)
+{
+    if (a == b) return;
+    const int hi = std::max(a, b), lo = std::min(a, b);
+    if (p.ccDirty[hi] == 1) {
+        if (p.ccDirty[lo] == 1) p.nDirty--;
+        p.ccDirty[lo] = 1; p.ccDirty[hi] = 0;
+    }
+    for (int i = 0; i < p.nIndivUsed; i++)
+        if (p.indivActive[i] && p.cc[i] == hi) p.cc[i] = lo;
+    if (p.nCC - 1 != hi) {
+        for (int i = 0; i < p.nIndivUsed; i++)
+            if (p.indivActive[i] && p.cc[i] == p.nCC - 1) p.cc[i] = hi;
+        if (p.ccDirty[p.nCC - 1] == 1) { p.ccDirty[hi] = 1; p.ccDirty[p.nCC - 1] = 0; }
+        p.LLcc[hi] = p.LLcc[p.nCC - 1];
+    }
+    p.nCC--;
+}
+
+// _DissociateParentMnode@0x100013804: drop marriage m from x's attachment list (swap with last)
+static void DissociateParentMnode(Ped &p, int x, int m)
+{
+    Indiv &ix = p.indiv[x];
+    const int n = (int)ix.M.size();
+    for (int k = 0; k < n - 1; k++)
+        if (ix.M[k] == m) { ix.M[k] = ix.M[n - 1]; ix.edge[k] = ix.edge[n - 1]; break; }
+    ix.M.pop_back(); ix.edge.pop_back();
+}
+// _DissociateSibMnode@0x100013948: drop kid x from marriage m (swap with last, renumber the moved sib)
+static void DissociateSibMnode(Ped &p, int x, int m)
+{
+    Marr &mm = p.marr[m];
+    const int nk = (int)mm.kids.size();
+    for (int k = 0; k < nk - 1; k++) {
+        if (mm.kids[k] != x) continue;
+        mm.kids[k] = mm.kids[nk - 1];
+        Indiv &sib = p.indiv[mm.kids[k]];
+        for (size_t j = 0; j < sib.M.size(); j++)
+            if (sib.edge[j] > 1) sib.edge[j] = k + 2;
+        break;
+    }
+    mm.kids.pop_back();
+}
+
+// _UpdateUnobsDegree@0x100007550
+static void UpdateUnobsDegree(Ped &p, int x)
+{
+    if (x < 0) return;
+    Indiv &ix = p.indiv[x];
+    if (ix.observed) { ix.unobsDegree = 0; return; }
+    int best = p.maxUnobsLayer + 1;
+    for (size_t k = 0; k < ix.M.size(); k++) {
+        const Marr &mm = p.marr[ix.M[k]];
+        const int e = ix.edge[k];
+        auto look = [&](int y) -> bool {
+            if (p.indiv[y].observed) { ix.unobsDegree = 1; return true; }
+            best = std::min(best, p.indiv[y].unobsDegree + 1);
+            return false;
+        };
+        if (e != 0 && look(mm.pa)) return;
+        if (e != 1 && look(mm.ma)) return;
+        for (size_t c = 0; c < mm.kids.size(); c++)
+            if ((int)c + 2 != e && look(mm.kids[c])) return;
+        if (best == 1) { ix.unobsDegree = 1; return; }
+    }
+    ix.unobsDegree = best;
+}
+
+// _DFS_i2m_obs@0x100007070: does individual i contribute information to marriage `via`
+// (observed, a parent elsewhere, or a kid elsewhere while `via` has further kids)?
+static bool informs(Ped &p, int i, int via)
+{
+    const Indiv &x = p.indiv[i];
+    if (x.observed) return true;
+    for (size_t k = 0; k < x.M.size(); k++) {
+        if (x.M[k] == via) continue;
+        if (x.edge[k] <= 1) return true;
+        if (p.marr[via].nEdges() > 3) return true;
+    }
+    return false;
+}
+// _isReductiveParentRecursive@0x100007170: nothing informative anywhere up y's ancestry
+static bool reductive_up(Ped &p, int y)
+{
+    const Indiv &iy = p.indiv[y];
+    for (size_t k = 0; k < iy.M.size(); k++) {
+        if (iy.edge[k] <= 1) continue;
+        const Marr &mm = p.marr[iy.M[k]];
+        if (informs(p, mm.pa, iy.M[k]) || !reductive_up(p, mm.pa)) return false;
+        if (informs(p, mm.ma, iy.M[k]) || !reductive_up(p, mm.ma)) return false;
+    }
+    return true;
+}
+// _isReductiveParent@0x100007340: an unobserved individual that is nobody's parent and whose
+// ancestry holds nothing informative can be dropped without changing any likelihood
+static bool isReductiveParent(Ped &p, int x)
+{
+    if (x < 0) return false;
+    const Indiv &ix = p.indiv[x];
+    if (ix.observed) return false;
+    for (size_t k = 0; k < ix.M.size(); k++) {
+        if (ix.edge[k] <= 1) return false;
+        const Marr &mm = p.marr[ix.M[k]];
+        if (informs(p, mm.pa, ix.M[k]) || !reductive_up(p, mm.pa)) return false;
+        if (informs(p, mm.ma, ix.M[k]) || !reductive_up(p, mm.ma)) return false;
+    }
+    return true;
+}
+
+// _TrimPed@0x100013b30: remove an unobserved individual that no longer links anything
+static void TrimPed(Ped &p, int x)
+{
+    Indiv &ix = p.indiv[x];
+    if (ix.observed) return;
+    if (ix.M.size() > 1) return;
+    if (ix.M.size() == 1 && ix.edge[0] < 2) return;
+    p.indivActive[x] = 0;
+    ix.queued = false;
+    p.freeIndiv.push_back(x);
+    p.nIndivPerGen[ix.gen]--;
+    hist_node(p, 0, x);
+    if (ix.M.empty()) return;
+    const int m = ix.M[0];
+    hist_edge(p, 0, m, x);
+    Marr &mm = p.marr[m];
+    if (mm.nEdges() == 3) {
+        p.marrActive[m] = 0;
+        p.freeMarr.push_back(m);
+        hist_edge(p, 0, m, mm.pa);
+        if (!mm.selfing) hist_edge(p, 0, m, mm.ma);
+        hist_mnode(p, 0, m);
+        const int pa = mm.pa, ma = mm.ma;
+        const bool self = mm.selfing;
+        DissociateParentMnode(p, pa, m);
+        if (!self) DissociateParentMnode(p, ma, m);
+        mm.kids.clear();
+        TrimPed(p, pa);
+        if (!self) TrimPed(p, ma);
+    } else {
+        DissociateSibMnode(p, x, m);
+    }
+    ix.M.clear(); ix.edge.clear();
+}
+
+// _RevertSex@0x100014910
+static void RevertSex(Ped &p, int x)
+{
+    Indiv &ix = p.indiv[x];
+    if (ix.sexWasUnknown != 1) return;
+    for (int e : ix.edge) if (e < 2) return;
+    ix.sex = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// _Propagating_msg@0x10001ba10: build the view of the dirty components and sweep it
+
+static void Propagating_msg(Ped &p)
+{
+    if (p.nDirty == 0) return;     // the reference re-propagates everything; nothing would change
+    const bool all = p.nDirty == p.nCC;
+    std::vector<int> indiv, icc, marr, mpa, mma, kb{0}, kids, labels;
+    std::vector<uint8_t> founder, selfing;
+    std::vector<int> local(p.nCC, -1);
+    for (int c = 0; c < p.nCC; c++)
+        if (all || p.ccDirty[c]) { local[c] = (int)labels.size(); labels.push_back(c); }
+    for (int i = 0; i < p.nIndivUsed; i++) {                 // _TurnOnSpotlight@0x10001bb90
+        if (!p.indivActive[i] || local[p.cc[i]] < 0) continue;
+        indiv.push_back(i); icc.push_back(local[p.cc[i]]); founder.push_back(p.indiv[i].founder ? 1 : 0);
+    }
+    for (int m = 0; m < p.nMarrUsed; m++) {
+        if (!p.marrActive[m] || local[p.cc[p.marr[m].pa]] < 0) continue;
+        const Marr &mm = p.marr[m];
+        marr.push_back(m); mpa.push_back(mm.pa); mma.push_back(mm.ma); selfing.push_back(mm.selfing ? 1 : 0);
+        kids.insert(kids.end(), mm.kids.begin(), mm.kids.end());
+        kb.push_back((int)kids.size());
+    }
+    pf_graph_view v;
+    v.n_indiv = (int)indiv.size(); v.indiv = indiv.data(); v.indiv_cc = icc.data(); v.indiv_founder = founder.data();
+    v.n_marr = (int)marr.size(); v.marr = marr.data(); v.marr_pa = mpa.data(); v.marr_ma = mma.data();
+    v.marr_selfing = selfing.data(); v.marr_kid_begin = kb.data(); v.marr_kids = kids.data();
+    v.n_cc = (int)labels.size();
+    std::vector<double> ll(labels.size() + 1);
+    if (PFN(sweep)(p.eng, 0, &v, ll.data()) != PF_OK) die("sweep failed");
+    p.n_sweeps++;
+    for (size_t j = 0; j < labels.size(); j++) p.LLcc[labels[j]] = ll[j];
+    p.LLtot = 0;                                               // _UpdateProb@0x10001dd0c-0x10001dd65
+    for (int c = 0; c < p.nCC; c++) p.LLtot = p.LLcc[c] + p.LLtot;
+    std::fill(p.ccDirty.begin(), p.ccDirty.begin() + std::max(p.nCC, 0), 0);
+    p.nDirty = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// proposals
+
+struct Batch { std::vector<pf_proposal> props; std::vector<int> slot; };   // slot = index into p.ch
+
+static double compose(Ped &p, int kid, const pf_proposal &q, double lsum)
+{
+    const int ck = p.cc[kid];
+    if (q.kind == PF_PROP_PRONG) {                             // _CalculateLikeByProngs@0x10001fc55-0x10001fce1
+        const int cp = p.cc[p.marr[q.marr].pa];
+        return pf_compose_ll(p.LLtot, lsum, p.LLcc[ck], cp != ck, cp != ck ? p.LLcc[cp] : 0.0, 0, 0.0);
+    }
+    const int cp = q.pa < 0 ? -1 : p.cc[q.pa];
+    if (q.kind == PF_PROP_SELFING)                             // _CalculateLikeByStubsSelfing@0x10001f929-0x10001f9f7
+        return pf_compose_ll(p.LLtot, lsum, p.LLcc[ck], cp != -1 && cp != ck, cp >= 0 ? p.LLcc[cp] : 0.0, 0, 0.0);
+    const int cm = q.ma < 0 ? -1 : p.cc[q.ma];                 // _CalculateLikeByStubs@0x10001f547-0x10001f6ae
+    const int use_pa = cp != -1 && cp != ck, use_ma = cm != -1 && cm != cp && cm != ck;
+    return pf_compose_ll(p.LLtot, lsum, p.LLcc[ck], use_pa, use_pa ? p.LLcc[cp] : 0.0, use_ma, use_ma ? p.LLcc[cm] : 0.0);
+}
+
+static void flush(Ped &p, int kid, Batch &b)
+{
+    if (b.props.empty()) return;
+    std::vector<double> lsum(b.props.size());
+    if (PFN(eval)(p.eng, 0, kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("eval failed");
+    p.n_proposals += (long)b.props.size();
+    for (size_t k = 0; k < b.props.size(); k++) p.chll[b.slot[k]] = compose(p, kid, b.props[k], lsum[k]);
+    b.props.clear(); b.slot.clear();
+}
+
+static int add_choice(Ped &p, Batch &b, int kind, int pa, int ma, int marr)
+{
+    pf_proposal q{kind, pa, ma, marr};
+    Choice c;
+    if (kind == PF_PROP_PRONG) c = Choice{marr, p.marr[marr].pa, p.marr[marr].ma, p.marr[marr].selfing ? 1 : 0, 0};
+    else if (kind == PF_PROP_SELFING) c = Choice{-1, pa, pa, 1, 0};
+    else c = Choice{-1, pa, ma, 0, 0};
+    p.ch.push_back(c); p.chll.push_back(0.0);
+    b.props.push_back(q); b.slot.push_back((int)p.ch.size() - 1);
+    return (int)p.ch.size() - 1;
+}
+
+// _ProposeSingletMove@0x1000149d0 (enumeration part; the likelihood is evaluated in one batch)
+static void ProposeSingletMove(Ped &p, const Opts &o, Batch &b, int c, int kid, std::vector<std::pair<int, int>> cand_slot[3])
+{
+    if (!p.indivActive[c]) return;
+    const double gap = p.indiv[c].genTime - p.indiv[kid].genTime;
+    if (gap > p.maxAge || p.minAge > gap) return;
+    const int sex = p.indiv[c].sex;
+    if (p.cc[c] == p.cc[kid]) return;          // -c 0: would close a loop (throttle modes unsupported)
+    int slot;
+    if (sex == 1) slot = add_choice(p, b, PF_PROP_TRIO, c, -1, -1);
+    else slot = add_choice(p, b, PF_PROP_TRIO, -1, c, -1);
+    cand_slot[sex == 1 ? 1 : sex == 2 ? 2 : 0].push_back({c, slot});
+    if (o.selfing) add_choice(p, b, PF_PROP_SELFING, c, -1, -1);
+}
+
+// _checkMatchingCC@0x1000241b0 under -c 0
+static bool checkMatchingCC(Ped &p, int pa, int ma, int kid)
+{
+    const int ck = p.cc[kid];
+    if (!(p.cc[pa] == p.cc[ma] || ck == p.cc[pa] || ck == p.cc[ma])) return false;
+    if (p.cc[pa] == p.cc[ma]) {
+        const Indiv &ip = p.indiv[pa];
+        for (size_t k = 0; k < ip.M.size(); k++) {
+            if (ip.edge[k] > 1) continue;
+            if (p.marr[ip.M[k]].ma == ma) { p.marr[ip.M[k]].mark = true; break; }
+        }
+    }
+    return true;
+}
+
+static bool by_ll_desc(const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.second > b.second; }
+
+// _EvalMoves@0x100015010 (without the swap block @0x100015989-0x100016651)
+static void EvalMoves(Ped &p, const Opts &o, int kid)
+{
+    p.ch.clear(); p.chll.clear();
+    Batch b;
+    const double kt = p.indiv[kid].genTime;
+    const int ck = p.cc[kid];
+    bool redPa = false, redMa = false;
+    const int ppa = p.prev[0], pma = p.prev[1];
+    if (ppa >= 0) { redPa = p.indiv[ppa].reductive; redMa = p.indiv[pma].reductive; }
+    if (redPa) p.indivActive[ppa] = 0;
+    if (redMa) p.indivActive[pma] = 0;
+    add_choice(p, b, PF_PROP_TRIO, -1, -1, -1);
+    if (o.selfing) add_choice(p, b, PF_PROP_SELFING, -1, -1, -1);
+    std::vector<std::pair<int, int>> cand_slot[3];
+    if (kid >= p.nObs) {
+        for (int c = 0; c < p.nIndivUsed; c++) ProposeSingletMove(p, o, b, c, kid, cand_slot);
+    } else {
+        for (int c : p.parentCand[kid]) ProposeSingletMove(p, o, b, c, kid, cand_slot);
+        for (int c = p.nObs; c < p.nIndivUsed; c++) ProposeSingletMove(p, o, b, c, kid, cand_slot);
+    }
+    if (redPa) p.indivActive[ppa] = 1;
+    if (redMa) p.indivActive[pma] = 1;
+    flush(p, kid, b);                                          // single-parent scores are needed for the top-10 cut
+    for (int s = 0; s < 3; s++) {
+        p.cand[s].clear();
+        for (auto &cs : cand_slot[s]) p.cand[s].push_back({cs.first, p.chll[cs.second]});
+        std::stable_sort(p.cand[s].begin(), p.cand[s].end(), by_ll_desc);      // qsort(_compareLLonGC)
+        if (p.cand[s].size() > 10) p.cand[s].resize(10);
+    }
+    auto pair = [&](int pa, int ma) { if (!checkMatchingCC(p, pa, ma, kid)) add_choice(p, b, PF_PROP_TRIO, pa, ma, -1); };
+    for (auto &m : p.cand[1]) {
+        for (auto &f : p.cand[2]) pair(m.first, f.first);
+        for (auto &u : p.cand[0]) pair(m.first, u.first);
+    }
+    for (auto &f : p.cand[2])
+        for (auto &u : p.cand[0]) pair(u.first, f.first);
+    for (size_t i = 0; i + 1 < p.cand[0].size(); i++)
+        for (size_t j = i + 1; j < p.cand[0].size(); j++) pair(p.cand[0][i].first, p.cand[0][j].first);
+    for (int m = 0; m < p.nMarrUsed; m++) {                    // prong proposals for marked marriages
+        if (!p.marrActive[m]) continue;
+        Marr &mm = p.marr[m];
+        const double g1 = p.indiv[mm.pa].genTime - kt, g2 = p.indiv[mm.ma].genTime - kt;
+        if (g1 > p.maxAge || p.minAge > g1 || g2 > p.maxAge || p.minAge > g2) continue;
+        if (!mm.mark) continue;
+        mm.mark = false;
+        if (p.cc[mm.pa] == ck) continue;
+        add_choice(p, b, PF_PROP_PRONG, -1, -1, m);
+    }
+    flush(p, kid, b);
+}
+
+// _AddObsFracPrior@0x100019800
+static void AddObsFracPrior(Ped &p, int kid)
+{
+    const int g = p.indiv[kid].gen + 1;
+    if (g >= (int)p.obsFrac.size()) return;
+    const double f = p.obsFrac[g];
+    if (f == 0 || p.nObsPerGen[g] == 0) return;
+    double nhat = ceil((double)p.nObsPerGen[g] / f);
+    int u = (int)(nhat - (double)p.nIndivPerGen[g]);
+    if ((double)p.nIndivPerGen[g] > nhat) { nhat = (double)p.nIndivPerGen[g]; u = 0; }
+    const float aa = (float)((1.0 + f) + (double)p.nIndivPerGen[g]);
+    const float bb = (float)((1.0 + (1.0 - f)) + (double)u);
+    const double q = rng::genbet(aa, bb), nq = 1.0 - q;
+    for (size_t c = 0; c < p.ch.size(); c++) {
+        const int pa = p.ch[c].pa, ma = p.ch[c].ma;
+        double add;
+        if (pa == -1 && ma == -1) add = 2.0 * log(nq);
+        else if (pa == -1 || ma == -1) {
+            const int given = pa == -1 ? ma : pa;
+            add = given < p.nObs ? (log(nq) + log(2.0)) + log(q) : (log(nq) + log(2.0)) + log(nq);
+        } else if (pa >= p.nObs && ma >= p.nObs) add = 2.0 * log(nq);
+        else if (pa < p.nObs && ma < p.nObs) add = 2.0 * log(q);
+        else add = (log(nq) + log(2.0)) + log(q);
+        p.chll[c] = add + p.chll[c];
+    }
+}
+
+// _NormalizeAndSelect@0x100016660
+static void NormalizeAndSelect(Ped &p)
+{
+    const int n = (int)p.ch.size();
+    if (n == 0) { p.neu[0] = p.prev[0]; p.neu[1] = p.prev[1]; p.neu[2] = -1; return; }
+    const double thresh = log(pow(10.0, -15.0)) - log((double)n);
+    double mx = p.chll[0];
+    for (int i = 0; i < n; i++) if (p.chll[i] > mx) mx = p.chll[i];
+    std::vector<double> w(n);
+    for (int i = 0; i < n; i++) { const double d = p.chll[i] - mx; w[i] = d < thresh ? 0.0 : exp(d); }
+    double sum = 0, c = 0;
+    for (int i = 0; i < n; i++) {
+        if (w[i] == 0) continue;
+        const double y = w[i] - c, t = sum + y;
+        c = (t - sum) - y; sum = t;
+    }
+    const double u = (double)rng::genunf(0.0f, 1.0f);
+    int pick = -1;
+    double cum = 0; c = 0;
+    for (int i = 0; i < n; i++) {
+        if (w[i] == 0) continue;
+        const double y = w[i] / sum - c, t = cum + y;
+        c = (t - cum) - y; cum = t;
+        if (!(cum < u)) { pick = i; break; }
+    }
+    if (pick == -1) { fprintf(stderr, "Error on calculating a series of cumulative likelihoods \n"); exit(-1); }
+    p.picked = pick;
+    p.neu[0] = p.ch[pick].pa; p.neu[1] = p.ch[pick].ma; p.neu[2] = p.ch[pick].mnode; p.neu[3] = p.ch[pick].selfing;
+}
+
+// _GetEmptyIndivIndx@0x100012ad0 / _GetEmptyMarrIndx@0x100012b80
+static int GetEmptyIndivIndx(Ped &p, int gen)
+{
+    p.nIndivPerGen[gen]++;
+    if (!p.freeIndiv.empty()) { const int s = p.freeIndiv.back(); p.freeIndiv.pop_back(); return s; }
+    if (p.nIndivUsed >= p.capIndiv) { fprintf(stderr, "out of individual slots (%d)\n", p.capIndiv); exit(-1); }
+    return p.nIndivUsed++;
+}
+static int GetEmptyMarrIndx(Ped &p)
+{
+    if (!p.freeMarr.empty()) { const int s = p.freeMarr.back(); p.freeMarr.pop_back(); return s; }
+    if (p.nMarrUsed >= p.capMarr) { fprintf(stderr, "out of marriage slots (%d)\n", p.capMarr); exit(-1); }
+    return p.nMarrUsed++;
+}
+// _AttachUnobsIndiv@0x100012c00
+static void AttachUnobsIndiv(Ped &p, int slot, int kid, int m, int edge)
+{
+    Indiv &x = p.indiv[slot];
+    x = Indiv();
+    x.sex = edge + 1;
+    x.gen = p.indiv[kid].gen + 1;
+    x.genTime = p.indiv[kid].genTime + p.minAge;
+    x.founder = true; x.observed = false;
+    x.userID = p.maxID + slot;
+    p.indivActive[slot] = 1;
+    p.cc[slot] = p.cc[kid];
+    x.M = {m}; x.edge = {edge};
+}
+
+// _PruneIndiv@0x1000141f0
+static void PruneIndiv(Ped &p, int id)
+{
+    hist_node(p, 2, id);
+    Indiv &x = p.indiv[id];
+    int m = -1;
+    for (size_t k = 0; k < x.M.size(); k++) if (x.edge[k] > 1) { m = x.M[k]; break; }
+    x.founder = false;
+    if (m == -1) {
+        p.prev[0] = p.prev[1] = -1; p.prev[2] = -1;
+        mark_dirty(p, p.cc[id]);
+        return;
+    }
+    Marr &mm = p.marr[m];
+    const int pa = mm.pa, ma = mm.ma;
+    p.prev[0] = pa; p.prev[1] = ma;
+    hist_edge(p, 0, m, id);
+    if (mm.nEdges() == 3) {
+        p.marrActive[m] = 0; mm.mark = false;
+        p.freeMarr.push_back(m);
+        hist_edge(p, 0, m, pa);
+        if (!mm.selfing) hist_edge(p, 0, m, ma);
+        hist_mnode(p, 0, m);
+        DissociateParentMnode(p, pa, m);
+        if (!mm.selfing) DissociateParentMnode(p, ma, m);
+        DissociateParentMnode(p, id, m);
+        mm.kids.clear();
+        p.prev[2] = -1;
+    } else {
+        p.prev[2] = m;
+        DissociateSibMnode(p, id, m);
+        DissociateParentMnode(p, id, m);
+    }
+    UpdateConComp(p, id);
+    UpdateUnobsDegree(p, pa);
+    UpdateUnobsDegree(p, ma);
+    p.indiv[pa].reductive = isReductiveParent(p, pa);
+    p.indiv[ma].reductive = isReductiveParent(p, ma);
+}
+
+// _PickAndUpdate@0x100016a60 (attach moves; swap choices do not exist here)
+static void PickAndUpdate(Ped &p, int kid)
+{
+    NormalizeAndSelect(p);
+    bool draw = true;
+    if (p.neu[0] != -1 && p.indiv[p.neu[0]].sex != 0) draw = false;
+    if (p.neu[1] != -1 && p.indiv[p.neu[1]].sex != 0) draw = false;
+    if (draw) {
+        const double u = (double)rng::genunf(0.0f, 1.0f);
+        if (!(u < 0.5)) std::swap(p.neu[0], p.neu[1]);
+    }
+    fprintf(p.fLL, "%d %d %f\n", p.iter, kid, p.picked >= 0 ? p.chll[p.picked] : 0.0);
+    if (p.neu[0] != p.prev[0] && p.prev[0] > -1) {
+        TrimPed(p, p.prev[0]); UpdateConComp(p, p.prev[0]); RevertSex(p, p.prev[0]);
+    }
+    if (p.prev[0] != p.prev[1] && p.neu[1] != p.prev[1] && p.prev[1] > -1) {
+        TrimPed(p, p.prev[1]); UpdateConComp(p, p.prev[1]); RevertSex(p, p.prev[0]);   // sic: prev.pa
+    }
+    int m = p.neu[2], pa = p.neu[0], ma = p.neu[1];
+    Indiv &k = p.indiv[kid];
+    if (m != -1) {
+        Marr &mm = p.marr[m];
+        mm.kids.push_back(kid);
+        k.M.push_back(m); k.edge.push_back(mm.nEdges() - 1);
+        pa = mm.pa; ma = mm.ma;
+        AssignConComp(p, p.cc[pa], p.cc[kid]);
+        hist_edge(p, 1, m, kid);
+    } else {
+        m = GetEmptyMarrIndx(p);
+        Marr &mm = p.marr[m];
+        mm = Marr();
+        const bool self = p.neu[3] == 1;
+        auto attach_parent = [&](int &par, int edge) {
+            if (par == -1) {
+                par = GetEmptyIndivIndx(p, k.gen + 1);
+                AttachUnobsIndiv(p, par, kid, m, edge);
+                hist_node(p, 1, par);
+            } else {
+                Indiv &ip = p.indiv[par];
+                ip.M.push_back(m); ip.edge.push_back(edge);
+                if (!self && ip.sex == 0) ip.sex = edge + 1;
+                AssignConComp(p, p.cc[par], p.cc[kid]);
+            }
+        };
+        attach_parent(pa, 0);
+        if (self) ma = pa; else attach_parent(ma, 1);
+        k.M.push_back(m); k.edge.push_back(2);
+        mm.pa = pa; mm.ma = ma; mm.kids = {kid}; mm.selfing = self; mm.mark = false;
+        p.marrActive[m] = 1;
+        hist_mnode(p, 1, m);
+        hist_edge(p, 1, m, pa);
+        if (!self) hist_edge(p, 1, m, ma);
+        hist_edge(p, 1, m, kid);
+    }
+    hist_node(p, 3, kid);
+    mark_dirty(p, p.cc[kid]);
+    p.neu[0] = pa; p.neu[1] = ma; p.neu[2] = m;
+    p.indiv[pa].sex = 1; p.indiv[ma].sex = 2;
+    UpdateUnobsDegree(p, pa); UpdateUnobsDegree(p, ma); UpdateUnobsDegree(p, kid);
+    fprintf(p.fPed, "%d %d %d %d\n", p.iter, k.userID, p.indiv[pa].userID, p.indiv[ma].userID);
+    // the reference calls Propagating_msg here; the dirty flags carry over to the sweep at the
+    // start of the next Gibbs step instead (see the header of this file)
+}
+
+// _MCMC_sampling@0x100019ec0
+static void MCMC_sampling(Ped &p, const Opts &o, int id)
+{
+    if (!(p.indiv[id].gen < p.nGen - 1)) return;
+    if (!(p.indiv[id].unobsDegree <= p.maxUnobsLayer)) return;
+    p.t++;
+    PruneIndiv(p, id);
+    Propagating_msg(p);
+    EvalMoves(p, o, id);
+    p.t++;
+    AddObsFracPrior(p, id);
+    PickAndUpdate(p, id);
+    const int pa = p.neu[0], ma = p.neu[1], self = p.neu[3];
+    auto enqueue = [&](int x) { p.unobsQueue.push_back(x); p.indiv[x].queued = true; };
+    const bool qa = pa >= p.nObs && !p.indiv[pa].queued, qm = ma >= p.nObs && !p.indiv[ma].queued;
+    if (qa && qm) {
+        if (self == 1) enqueue(pa);
+        else {
+            const double u = (double)rng::genunf(0.0f, 1.0f);
+            if (u > 0.5) { enqueue(pa); enqueue(ma); } else { enqueue(ma); enqueue(pa); }
+        }
+    } else if (qa) enqueue(pa);
+    else if (qm) enqueue(ma);
+}
+
+// ---------------------------------------------------------------------------------------------
+// input (_ReadPedfile@0x1000094f0, _CalculateMaxSize@0x1000079c0)
+
+static std::vector<std::string> split(const std::string &s, char sep)
+{
+    std::vector<std::string> out;
+    size_t i = 0;
+    while (i <= s.size()) {
+        size_t j = s.find(sep, i);
+        if (j == std::string::npos) j = s.size();
+        if (j > i) out.push_back(s.substr(i, j - i));
+        i = j + 1;
+    }
+    return out;
+}
+
+static bool read_line(FILE *f, std::string &line)
+{
+    line.clear();
+    int c;
+    bool any = false;
+    while ((c = fgetc(f)) != EOF) { any = true; if (c == '\n') break; if (c != '\r') line.push_back((char)c); }
+    return any;
+}
+
+static void ReadPrior(Ped &p, const std::string &path)
+{
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) { fprintf(stderr, "Failed to open prior.txt for reading\n"); exit(-1); }
+    std::string line;
+    while (read_line(f, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        auto tok = split(line, ' ');
+        if (tok.empty()) continue;
+        const std::string &k = tok[0];
+        auto ival = [&]() { return tok.size() > 1 ? atoi(tok[1].c_str()) : 0; };
+        auto dvec = [&](size_t n) { std::vector<double> v(n, 0.0); for (size_t i = 0; i < n && i + 1 < tok.size(); i++) v[i] = atof(tok[i + 1].c_str()); return v; };
+        if (k == "nIndiv") p.nIndivDecl = ival();
+        else if (k == "nObsIndiv") p.nObs = ival();
+        else if (k == "nGen") p.nGen = ival();
+        else if (k == "nSNP") p.S = ival();
+        else if (k == "nMar") p.nMarDecl = ival();
+        else if (k == "maxID") p.maxID = ival();
+        else if (k == "aFreq") p.afreq = dvec(p.S);
+        else if (k == "epsilon") p.eps = dvec(p.S);
+        else if (k == "obsFrac") p.obsFrac = dvec(p.nGen);
+        else if (k == "maxAge") p.maxAge = tok.size() > 1 ? atof(tok[1].c_str()) : 1.0;
+        else if (k == "minAge") p.minAge = tok.size() > 1 ? atof(tok[1].c_str()) : 1.0;
+        else if (k == "maxUnobsLayer") p.maxUnobsLayer = ival();
+        else if (k == "maxMarrGap") { /* parsed and ignored by the reference (@0x100009d47) */ }
+        else { fprintf(stderr, "In prior.txt, I cannot recognize this keyword: %s. \n", k.c_str()); exit(-1); }
+    }
+    fclose(f);
+    if (p.S <= 0 || p.nGen <= 0 || (int)p.afreq.size() != p.S || (int)p.eps.size() != p.S) {
+        fprintf(stderr, "prior.txt: nSNP, nGen, aFreq and epsilon are required\n"); exit(-1);
+    }
+    if ((int)p.obsFrac.size() != p.nGen) p.obsFrac.assign(p.nGen, 0.0);
+}
+
+// exact decimal numerators: "0.9800" -> 9800 over 10000 when the token has <= 4 fractional digits
+static bool parse_dec4(const char *s, unsigned &num)
+{
+    unsigned long ip = 0; int nd = 0, nf = 0; unsigned long fp = 0;
+    const char *c = s;
+    while (*c >= '0' && *c <= '9') { ip = ip * 10 + (*c - '0'); c++; nd++; if (ip > 6) return false; }
+    if (*c == '.') { c++; while (*c >= '0' && *c <= '9') { if (nf == 4) { if (*c != '0') return false; } else { fp = fp * 10 + (*c - '0'); nf++; } c++; } }
+    if (*c != 0 || (nd == 0 && nf == 0)) return false;
+    while (nf < 4) { fp *= 10; nf++; }
+    const unsigned long v = ip * 10000 + fp;
+    if (v > 65535) return false;
+    num = (unsigned)v;
+    return true;
+}
+
+static void ReadGeno(Ped &p, const std::string &path)
+{
+    // pass 1 (_CalculateMaxSize): observed individuals per generation -> capacities
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) { fprintf(stderr, "Failed to open geno.txt for reading\n"); exit(-1); }
+    std::string line;
+    std::vector<int> nPerGen(p.nGen, 0);
+    while (read_line(f, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        auto tok = split(line, ' ');
+        if (tok.size() < 4 || atoi(tok[1].c_str()) == 0) continue;
+        const int g = atoi(tok[3].c_str());
+        if (g >= 0 && g < p.nGen) nPerGen[g]++;
+    }
+    p.capIndiv = 0; p.capMarr = 0;
+    for (int g = 0; g < p.nGen; g++) {
+        p.capIndiv += nPerGen[g] * (int)(pow(2.0, (double)(p.nGen - g)) - 1.0);
+        p.capMarr += nPerGen[g] * (int)(pow(2.0, (double)(p.nGen - g - 1)) - 1.0);
+    }
+    p.capMarr += 1;
+    p.capIndiv = std::max(p.capIndiv, p.nIndivDecl) + 1;
+    printf("# of marriage allowed/allocated for: %d\n", p.capMarr);
+    printf("# of individuals allocated for : %d\n", p.capIndiv);
+    p.indiv.assign(p.capIndiv, Indiv());
+    p.marr.assign(p.capMarr, Marr());
+    p.indivActive.assign(p.capIndiv, 0); p.marrActive.assign(p.capMarr, 0);
+    p.cc.assign(p.capIndiv, -1); p.ccDirty.assign(p.capIndiv + 1, 0); p.LLcc.assign(p.capIndiv + 1, 0.0);
+    p.nObsPerGen.assign(p.nGen + 1, 0); p.nIndivPerGen.assign(p.nGen + 1, 0);
+    p.parentCand.assign(p.capIndiv, {});
+
+    pf_config cfg{};
+    cfg.n_loci = p.S; cfg.locus_begin = 0; cfg.locus_end = p.S; cfg.cap_indiv = p.capIndiv; cfg.cap_marr = p.capMarr;
+    cfg.n_chains = 1; cfg.device = getenv("PEDFAC_DEVICE") ? atoi(getenv("PEDFAC_DEVICE")) : 0;
+    if (PFN(create)(&p.eng, &cfg) != PF_OK) die("cannot create the likelihood engine");
+    if (PFN(set_locus_params)(p.eng, p.eps.data(), p.afreq.data()) != PF_OK) die("set_locus_params");
+
+    // pass 2: rows. Observed rows fill slots 0..nObs-1 in file order, unobserved rows follow
+    rewind(f);
+    int nextObs = 0, nextUnobs = p.nObs, row = 0;
+    std::vector<uint8_t> codes(p.S);
+    std::vector<double> lik((size_t)p.S * 3);
+    std::vector<uint16_t> num((size_t)p.S * 3);
+    while (read_line(f, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        auto tok = split(line, ' ');
+        if (tok.size() < 5) continue;
+        const bool obs = atoi(tok[1].c_str()) != 0;
+        int slot;
+        if (obs) {
+            if (nextObs >= p.nObs) { fprintf(stderr, "There are more observed individuals in your genoInfo.txt than what you have declared\n"); exit(-1); }
+            slot = nextObs++;
+        } else {
+            if (nextUnobs >= p.capIndiv) { fprintf(stderr, "There are more individuals in your genoInfo.txt than what we can allocate\n"); exit(-1); }
+            slot = nextUnobs++;
+        }
+        Indiv &x = p.indiv[slot];
+        x.userID = atoi(tok[0].c_str());
+        x.observed = obs;
+        x.sex = atoi(tok[2].c_str()); x.sexWasUnknown = x.sex == 0;
+        x.genTime = atof(tok[3].c_str());
+        x.gen = (int)(x.genTime / p.minAge);
+        if (x.gen >= p.nGen || x.gen < 0) {
+            fprintf(stderr, "In genoInfo.txt, the assigned generation level of %d-th individual is %d, beyond nGen\n", row, x.gen); exit(0);
+        }
+        p.nIndivPerGen[x.gen]++;
+        if (obs) p.nObsPerGen[x.gen]++;
+        x.founder = atoi(tok[4].c_str()) != 0;
+        p.indivActive[slot] = 1;
+        if (obs) {
+            if ((int)tok.size() - 5 < p.S) {
+                fprintf(stderr, "error on geno.txt: Individual %d has fewer SNPs than reported. \nnum of SNP - obs: %d , exp: %d", row, (int)tok.size() - 5, p.S); exit(-1);
+            }
+            bool soft = false, dec_ok = true;
+            for (int s = 0; s < p.S; s++) {
+                const std::string &t = tok[5 + s];
+                if (t.find(',') != std::string::npos) {
+                    soft = true;
+                    auto parts = split(t, ',');
+                    if (parts.size() != 3) { fprintf(stderr, "Expect three genotype posterior prob on the geno.txt\n"); exit(1); }
+                    for (int g = 0; g < 3; g++) {
+                        lik[(size_t)s * 3 + g] = strtod(parts[g].c_str(), nullptr);
+                        unsigned nn = 0;
+                        if (dec_ok && parse_dec4(parts[g].c_str(), nn)) num[(size_t)s * 3 + g] = (uint16_t)nn; else dec_ok = false;
+                    }
+                    codes[s] = 3;
+                } else {
+                    const int c = (int)strtod(t.c_str(), nullptr);
+                    if (c < 0 || c > 3) {
+                        fprintf(stderr, "Acceptable genotype values are 0, 1, 2, or 3.\nIf you are uncertain about the genotype value, you can replace that value with 3.\n"); exit(-1);
+                    }
+                    codes[s] = (uint8_t)c;
+                    const double e = p.eps[s];
+                    for (int g = 0; g < 3; g++) lik[(size_t)s * 3 + g] = c == 3 ? 1.0 : (g == c ? 1.0 - e : e / 2.0);
+                    dec_ok = false;
+                }
+            }
+            int rc;
+            if (!soft) rc = PFN(set_genotypes_hard)(p.eng, slot, codes.data());
+            else if (dec_ok) rc = PFN(set_genotypes_soft_dec16)(p.eng, slot, num.data(), 10000);
+            else rc = PFN(set_genotypes_soft_f64)(p.eng, slot, lik.data());   // mixed rows: exact doubles
+            if (rc != PF_OK) die("genotype upload failed");
+        }
+        row++;
+    }
+    fclose(f);
+    if (nextObs < p.nObs) { fprintf(stderr, "There are fewer observed individuals in your genoInfo.txt than what you have declared\n"); exit(-1); }
+    p.nIndivUsed = nextUnobs;
+}
+
+static void ReadMarriages(Ped &p, const std::string &path)
+{
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) { printf("optional marriage.txt is not found; will build marriage from ground-up\n"); return; }
+    std::vector<int> byUser;
+    auto find_slot = [&](int uid) { for (int i = 0; i < p.nIndivUsed; i++) if (p.indivActive[i] && p.indiv[i].userID == uid) return i; return -1; };
+    std::string line;
+    std::vector<std::pair<std::pair<int, int>, int>> couples;   // (pa, ma) -> marriage slot
+    while (read_line(f, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        auto tok = split(line, ' ');
+        if (tok.size() < 3) continue;
+        const int kid = find_slot(atoi(tok[0].c_str())), pa = find_slot(atoi(tok[1].c_str())), ma = find_slot(atoi(tok[2].c_str()));
+        if (kid < 0) { fprintf(stderr, "The genotype information for this kid's ID %s from marriage.txt cannot be found\n", tok[0].c_str()); exit(-1); }
+        if (pa < 0) { fprintf(stderr, "The genotype information for the parent 0's ID %s from marriage.txt cannot be found\n", tok[1].c_str()); exit(-1); }
+        if (ma < 0) { fprintf(stderr, "The genotype information for the parent 1's ID %s from marriage.txt cannot be found\n", tok[2].c_str()); exit(-1); }
+        int m = -1;
+        for (auto &c : couples) if (c.first.first == pa && c.first.second == ma) m = c.second;
+        if (m < 0) {
+            m = GetEmptyMarrIndx(p);
+            Marr &mm = p.marr[m];
+            mm = Marr(); mm.pa = pa; mm.ma = ma; mm.selfing = pa == ma;
+            p.marrActive[m] = 1;
+            p.indiv[pa].M.push_back(m); p.indiv[pa].edge.push_back(0);
+            if (pa != ma) { p.indiv[ma].M.push_back(m); p.indiv[ma].edge.push_back(1); }
+            couples.push_back({{pa, ma}, m});
+        }
+        Marr &mm = p.marr[m];
+        mm.kids.push_back(kid);
+        p.indiv[kid].M.push_back(m); p.indiv[kid].edge.push_back(mm.nEdges() - 1);
+    }
+    fclose(f);
+    if (p.nMarDecl != 0 && (int)couples.size() != p.nMarDecl) {
+        fprintf(stderr, "The number of marriage observed in marriage.txt doesn't match up with nMar in prior.txt\n"); exit(-1);
+    }
+}
+
+// _CheckPed@0x100012e10: label components; all start dirty. Loops abort (acyclic model).
+static void CheckPed(Ped &p)
+{
+    p.nCC = 0; p.nDirty = 0;
+    for (int i = 0; i < p.nIndivUsed; i++) {
+        if (!p.indivActive[i] || p.cc[i] != -1) continue;
+        label_component(p, i, p.nCC);
+        p.ccDirty[p.nCC] = 1; p.nDirty++;
+        p.nCC++;
+    }
+    // forest test: edges = nodes - components
+    long edges = 0, nodes = 0;
+    for (int i = 0; i < p.nIndivUsed; i++) nodes += p.indivActive[i] ? 1 : 0;
+    for (int m = 0; m < p.nMarrUsed; m++) if (p.marrActive[m]) { nodes++; edges += p.marr[m].nEdges() - (p.marr[m].selfing ? 1 : 0); }
+    if (edges != nodes - p.nCC) { fprintf(stderr, "Initial pedigree configuration contains loops."); exit(-1); }
+}
+
+// _RefineParentOffPair@0x100014d20: top-15 single-parent candidates per observed kid, scored on
+// the engine in one dense scan per group of kids sharing a generation time
+static void RefineParentOffPair(Ped &p)
+{
+    std::vector<int> order(p.nObs);
+    for (int i = 0; i < p.nObs; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return p.indiv[a].genTime < p.indiv[b].genTime; });
+    size_t i0 = 0;
+    while (i0 < order.size()) {
+        size_t i1 = i0;
+        while (i1 < order.size() && p.indiv[order[i1]].genTime == p.indiv[order[i0]].genTime) i1++;
+        const double kt = p.indiv[order[i0]].genTime;
+        std::vector<int> kids(order.begin() + i0, order.begin() + i1), cands;
+        std::sort(kids.begin(), kids.end());
+        std::vector<double> bias;
+        for (int j = 0; j < p.nObs; j++) {
+            const double gap = p.indiv[j].genTime - kt;
+            if (gap > p.maxAge || p.minAge > gap) continue;
+            cands.push_back(j); bias.push_back(-p.LLcc[p.cc[j]]);
+        }
+        if (!cands.empty()) {
+            std::vector<uint8_t> role(kids.size());
+            for (size_t k = 0; k < kids.size(); k++) role[k] = p.indiv[kids[k]].sex == 1 ? 1 : 0;
+            const int K = 15;
+            std::vector<int> slot(kids.size() * K);
+            std::vector<double> score(kids.size() * K);
+            if (PFN(prefilter)(p.eng, 0, (int)kids.size(), kids.data(), role.data(), (int)cands.size(), cands.data(),
+                               bias.data(), K, slot.data(), score.data()) != PF_OK) die("prefilter failed");
+            for (size_t k = 0; k < kids.size(); k++) {
+                auto &pc = p.parentCand[kids[k]];
+                pc.clear();
+                for (int t = 0; t < K; t++) if (slot[k * K + t] >= 0) pc.push_back(slot[k * K + t]);
+            }
+        }
+        i0 = i1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CLI (_GetCommLineOpts@0x10000f450: the seven functional flags of the ECA_Opt3 parser)
+
+static void usage()
+{
+    fprintf(stderr, "pedigraph -d/--directory-info DIR [-r/--random-file FILE] [-n/--num-iter N] [-c/--cyclic-choice J] [-s/--selfing] [-w/--diswap] [-l/--LBP]\n");
+}
+
+static Opts GetCommLineOpts(int argc, char **argv)
+{
+    Opts o;
+    for (int i = 1; i < argc; i++) {
+        const std::string a = argv[i];
+        auto need = [&]() -> const char * { if (i + 1 >= argc) { usage(); exit(1); } return argv[++i]; };
+        if (a == "-d" || a == "--directory-info") o.dir = need();
+        else if (a == "-r" || a == "--random-file") o.seedfile = need();
+        else if (a == "-n" || a == "--num-iter") o.nIter = atoi(need());
+        else if (a == "-c" || a == "--cyclic-choice") o.cyclic = atoi(need());
+        else if (a == "-s" || a == "--selfing") o.selfing = true;
+        else if (a == "-w" || a == "--diswap") o.diswap = true;
+        else if (a == "-l" || a == "--LBP") o.loopy = true;
+        else if (a == "--help" || a == "--help-full") { usage(); exit(0); }
+        else if (a == "--version") { printf("pedigraph (pedfac-b200)\n"); exit(0); }
+        else { fprintf(stderr, "unknown option %s\n", a.c_str()); usage(); exit(1); }
+    }
+    if (o.dir.empty()) { usage(); exit(1); }
+    if (o.cyclic != 0 || o.loopy) { fprintf(stderr, "pedigraph: -c %d / -l are not supported by this build (acyclic sampler only)\n", o.cyclic); exit(1); }
+    return o;
+}
+
+int main(int argc, char **argv)
+{
+    Opts o = GetCommLineOpts(argc, argv);
+    Ped p;
+    {   // _SeedFromFile@0x100027070
+        long a = 0, b = 0;
+        FILE *f = fopen(o.seedfile.c_str(), "r");
+        if (!f) {
+            a = (long)time(nullptr); b = a / 3;
+            printf("SEEDFILE: No file \"%s\".  Using clock to set RNG: %ld %ld\n", o.seedfile.c_str(), a, b);
+        } else {
+            if (fscanf(f, "%ld %ld", &a, &b) != 2) { a = 1234567890L; b = 123456789L; }
+            printf("SEEDFILE: Using contents of %s to set RNG: %ld %ld\n", o.seedfile.c_str(), a, b);
+            fclose(f);
+        }
+        rng::setall(a, b);
+    }
+    {   // _PrepOutFiles@0x10001a3a0
+        const std::string out = o.dir + "/out";
+        mkdir(out.c_str(), 0777);
+        p.fEdge = fopen((out + "/historyEdge.csv").c_str(), "w");
+        p.fNode = fopen((out + "/historyNode.csv").c_str(), "w");
+        p.fPed = fopen((out + "/ped.txt").c_str(), "w");
+        p.fGeno = fopen((out + "/geno.txt").c_str(), "w");
+        p.fLL = fopen((out + "/ll.txt").c_str(), "w");
+        if (!p.fEdge || !p.fNode || !p.fPed || !p.fGeno || !p.fLL) { fprintf(stderr, "cannot open output files under %s\n", out.c_str()); return -1; }
+    }
+    ReadPrior(p, o.dir + "/prior.txt");
+    ReadGeno(p, o.dir + "/geno.txt");
+    ReadMarriages(p, o.dir + "/marriage.txt");
+    printf("\t\tcompleted allocation!\n");
+    CheckPed(p);
+    printf("Allow selfing: %d\n", o.selfing ? 1 : 0);
+    printf("Allow loopy: %d\n", o.loopy ? 1 : 0);
+    printf("propagating message\n");
+    Propagating_msg(p);
+    printf("prior: %f \n", p.LLtot);
+    printf("finish propagating message\n");
+    {   // _PrintInitalHistory@0x100012600
+        fprintf(p.fNode, "t,action,id,label,level,group\n");
+        fprintf(p.fEdge, "t,action,id,from,to\n");
+        for (int i = 0; i < p.nIndivUsed; i++) if (p.indivActive[i]) hist_node(p, 1, i);
+        for (int m = 0; m < p.nMarrUsed; m++) {
+            if (!p.marrActive[m]) continue;
+            hist_mnode(p, 1, m);
+            hist_edge(p, 1, m, p.marr[m].pa);
+            if (!p.marr[m].selfing) hist_edge(p, 1, m, p.marr[m].ma);
+            for (int k : p.marr[m].kids) hist_edge(p, 1, m, k);
+        }
+    }
+    for (int i = 0; i < p.nIndivUsed; i++) UpdateUnobsDegree(p, i);
+    RefineParentOffPair(p);
+    p.observedSorted.resize(p.nObs);
+    for (int i = 0; i < p.nObs; i++) p.observedSorted[i] = i;
+    std::stable_sort(p.observedSorted.begin(), p.observedSorted.end(), [&](int a, int b) { return p.indiv[a].gen < p.indiv[b].gen; });   // qsort(_CompareGen)
+    printf("sample for %d iterations: -- \n", o.nIter);
+    for (p.iter = 0; p.iter < o.nIter; p.iter++) {             // _main@0x10001a812-0x10001aaea
+        p.unobsQueue.clear();
+        int qBeg = 0, qEnd = -1;
+        for (int k = 0; k < p.nObs; k++) {
+            const int id = p.observedSorted[k];
+            MCMC_sampling(p, o, id);
+            const bool last = k == p.nObs - 1;
+            if (!last && !(p.indiv[id].gen < p.indiv[p.observedSorted[k + 1]].gen)) continue;
+            const int gap = last ? p.nGen - p.indiv[id].gen : p.indiv[p.observedSorted[k + 1]].gen - p.indiv[id].gen;
+            for (int g = 1; g <= gap; g++) {
+                for (int q = qBeg; q < qEnd + 1; q++) {
+                    const int u = p.unobsQueue[q];
+                    if (!p.indiv[u].queued) continue;
+                    MCMC_sampling(p, o, u);
+                    p.indiv[u].queued = false;
+                }
+                if ((int)p.unobsQueue.size() - qEnd > 1) { qBeg = qEnd + 1; qEnd = (int)p.unobsQueue.size() - 1; }
+            }
+        }
+        printf("..%i\n", p.iter);
+        fflush(stdout);
+    }
+    printf(".. DONE \n");
+    if (getenv("PEDFAC_STATS")) fprintf(stderr, "pedigraph: %ld proposals, %ld sweeps\n", p.n_proposals, p.n_sweeps);
+    fclose(p.fEdge); fclose(p.fNode); fclose(p.fPed); fclose(p.fGeno); fclose(p.fLL);
+    PFN(destroy)(p.eng);
+    return 0;
+}

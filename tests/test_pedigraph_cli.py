@@ -1,0 +1,107 @@
+"""The `pedigraph` sampler executable: CLI + file contract and chain behaviour.
+CPU tests drive oracle/pedigraph_ref (the product's host chain logic linked against the CPU
+oracle); the -m gpu test drives pedfac_b200/bin/pedigraph (linked against libpedfac_cuda) and
+requires the two to sample the identical pedigree trace from the same inputs and seed."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from pedfac_b200 import frontend, synth
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = ROOT / "oracle" / "pedigraph_ref"
+GPU = ROOT / "pedfac_b200" / "bin" / "pedigraph"
+
+
+def run(binary, run_dir, n_iter=2, extra=()):
+    return subprocess.run([str(binary), "-d", str(run_dir), "-n", str(n_iter), "-r", str(Path(run_dir) / "rand"), *extra],
+                          capture_output=True, text=True, timeout=600)
+
+
+def make_run(tmp_path, name, n=80, S=60, soft=False, seed=46, seeds=(2590, 7579545)):
+    d = synth.simulate(n, S, soft=soft, seed=seed)
+    order = frontend.write_run_dir(d, tmp_path / name, seeds=seeds)
+    return d, order, tmp_path / name
+
+
+def test_outputs_follow_the_file_contract(tmp_path):
+    d, order, rd = make_run(tmp_path, "r")
+    r = run(REF, rd, n_iter=3)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    for needle in ["SEEDFILE: Using contents of", "Allow selfing: 0", "Allow loopy: 0", "propagating message",
+                   "prior: ", "finish propagating message", "sample for 3 iterations: --", "..0", "..2", ".. DONE"]:
+        assert needle in out
+    ped = (rd / "out" / "ped.txt").read_text().splitlines()
+    ll = (rd / "out" / "ll.txt").read_text().splitlines()
+    assert len(ped) == len(ll) > 0
+    assert all(re.fullmatch(r"\d+ \d+ \d+ \d+", x) for x in ped)          # "%d %d %d %d\n"
+    assert all(re.fullmatch(r"\d+ \d+ -?\d+\.\d{6}", x) for x in ll)       # "%d %d %f\n"
+    assert (rd / "out" / "geno.txt").read_text() == ""                     # opened, never written
+    assert (rd / "out" / "historyNode.csv").read_text().startswith("t,action,id,label,level,group\n")
+    assert (rd / "out" / "historyEdge.csv").read_text().startswith("t,action,id,from,to\n")
+    rows = np.array([list(map(int, x.split())) for x in ped])
+    assert set(rows[:, 0]) == {0, 1, 2}
+    n_obs = len(order)
+    # observed ids are 1..n; unobserved parents are numbered maxID + slot = (n + 1) + slot, slot >= n
+    assert rows[:, 1].min() >= 1 and (rows[:, 2:] >= 1).all()
+    assert ((rows[:, 2:] <= n_obs) | (rows[:, 2:] >= 2 * n_obs + 1)).all()
+    # the oldest generation is never sampled (gen >= nGen - 1)
+    top_ids = {k + 1 for k, i in enumerate(order) if d.gen[i] == d.gen[order].max()}
+    assert not (set(rows[:, 1]) & top_ids)
+
+
+def test_same_seed_same_trace_and_recovers_true_parents(tmp_path):
+    d, order, rd = make_run(tmp_path, "a", n=200, S=150)
+    _, _, rd2 = make_run(tmp_path, "b", n=200, S=150)
+    _, _, rd3 = make_run(tmp_path, "c", n=200, S=150, seeds=(11, 22))
+    for x in (rd, rd2, rd3):
+        assert run(REF, x, n_iter=3).returncode == 0
+    assert (rd / "out" / "ped.txt").read_text() == (rd2 / "out" / "ped.txt").read_text()
+    assert (rd / "out" / "ll.txt").read_text() == (rd2 / "out" / "ll.txt").read_text()
+    assert (rd / "out" / "ped.txt").read_text() != (rd3 / "out" / "ped.txt").read_text()
+    rows = np.loadtxt(rd / "out" / "ped.txt", dtype=int)
+    last = rows[rows[:, 0] == rows[:, 0].max()]
+    uid = {int(i): k + 1 for k, i in enumerate(order)}
+    inv = {v: k for k, v in uid.items()}
+    ok = tot = 0
+    for _, kid, pa, ma in last:
+        k = inv.get(int(kid))
+        if k is None or d.pa[k] < 0 or not (d.observed[d.pa[k]] and d.observed[d.ma[k]]):
+            continue
+        tot += 1
+        ok += {int(pa), int(ma)} == {uid[int(d.pa[k])], uid[int(d.ma[k])]}
+    assert tot > 20 and ok / tot > 0.9
+
+
+def test_soft_calls_and_error_paths(tmp_path):
+    d, order, rd = make_run(tmp_path, "s", n=60, S=40, soft=True)
+    assert run(REF, rd, n_iter=1).returncode == 0
+    bad = tmp_path / "bad"
+    frontend.write_run_dir(d, bad)
+    (bad / "prior.txt").write_text((bad / "prior.txt").read_text() + "\nnonsense 3")
+    r = run(REF, bad)
+    assert r.returncode != 0 and "cannot recognize this keyword: nonsense" in r.stderr
+    r = subprocess.run([str(REF), "-d", str(rd), "-c", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not supported" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("soft", [False, True])
+def test_gpu_sampler_reproduces_the_cpu_trace(tmp_path, soft):
+    """north_star: sampled pedigree traces identical for the same inputs and seed; log-likelihoods
+    of the picked choices agree to 1e-9 relative (ll.txt prints 6 decimals)."""
+    d, order, rd = make_run(tmp_path, "g", n=260, S=180, soft=soft)
+    _, _, rd2 = make_run(tmp_path, "h", n=260, S=180, soft=soft)
+    rg, rc = run(GPU, rd, n_iter=3), run(REF, rd2, n_iter=3)
+    assert rg.returncode == 0, rg.stderr
+    assert rc.returncode == 0, rc.stderr
+    assert (rd / "out" / "ped.txt").read_text() == (rd2 / "out" / "ped.txt").read_text()
+    a = np.loadtxt(rd / "out" / "ll.txt"); b = np.loadtxt(rd2 / "out" / "ll.txt")
+    np.testing.assert_array_equal(a[:, :2], b[:, :2])
+    np.testing.assert_allclose(a[:, 2], b[:, 2], rtol=1e-9, atol=2e-6)
+    pg = float(re.search(r"prior: (-?[\d.]+)", rg.stdout).group(1)); pc = float(re.search(r"prior: (-?[\d.]+)", rc.stdout).group(1))
+    assert abs(pg - pc) <= 1e-9 * abs(pc) + 2e-6
