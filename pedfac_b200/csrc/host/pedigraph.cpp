@@ -191,7 +191,7 @@ struct Ped {
     std::vector<std::pair<int, double>> cand[3];
     PF_ENGINE_T *eng = nullptr;
     FILE *fNode = nullptr, *fEdge = nullptr, *fPed = nullptr, *fGeno = nullptr, *fLL = nullptr;
-    long n_proposals = 0, n_sweeps = 0;
+    long n_proposals = 0, n_sweeps = 0, n_steps = 0;
 };
 
 static void die(const char *msg)
@@ -792,6 +792,7 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
     if (!(p.indiv[id].gen < p.nGen - 1)) return;
     if (!(p.indiv[id].unobsDegree <= p.maxUnobsLayer)) return;
     p.t++;
+    p.n_steps++;
     PruneIndiv(p, id);
     Propagating_msg(p);
     EvalMoves(p, o, id);
@@ -1172,11 +1173,19 @@ int main(int argc, char **argv)
     for (int i = 0; i < p.nObs; i++) p.observedSorted[i] = i;
     std::stable_sort(p.observedSorted.begin(), p.observedSorted.end(), [&](int a, int b) { return p.indiv[a].gen < p.indiv[b].gen; });   // qsort(_CompareGen)
     printf("sample for %d iterations: -- \n", o.nIter);
+    // measurement aids (not part of the reference contract): PEDFAC_STATS=1 prints per-iteration
+    // counters and wall time to stderr; PEDFAC_MAX_STEPS=K stops after K Gibbs steps in total
+    const bool stats = getenv("PEDFAC_STATS") != nullptr;
+    const long max_steps = getenv("PEDFAC_MAX_STEPS") ? atol(getenv("PEDFAC_MAX_STEPS")) : -1;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     for (p.iter = 0; p.iter < o.nIter; p.iter++) {             // _main@0x10001a812-0x10001aaea
+        const double t_iter = now();
+        const long props0 = p.n_proposals, sweeps0 = p.n_sweeps, steps0 = p.n_steps;
         p.unobsQueue.clear();
         int qBeg = 0, qEnd = -1;
         for (int k = 0; k < p.nObs; k++) {
             const int id = p.observedSorted[k];
+            if (max_steps >= 0 && p.n_steps >= max_steps) break;
             MCMC_sampling(p, o, id);
             const bool last = k == p.nObs - 1;
             if (!last && !(p.indiv[id].gen < p.indiv[p.observedSorted[k + 1]].gen)) continue;
@@ -1193,9 +1202,11 @@ int main(int argc, char **argv)
         }
         printf("..%i\n", p.iter);
         fflush(stdout);
+        if (stats)
+            fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld seconds %.6f\n", p.iter,
+                    p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, now() - t_iter);
     }
     printf(".. DONE \n");
-    if (getenv("PEDFAC_STATS")) fprintf(stderr, "pedigraph: %ld proposals, %ld sweeps\n", p.n_proposals, p.n_sweeps);
     fclose(p.fEdge); fclose(p.fNode); fclose(p.fPed); fclose(p.fGeno); fclose(p.fLL);
     PFN(destroy)(p.eng);
     return 0;

@@ -23,15 +23,20 @@ def write_run_dir(data: SynthData, run_dir, *, max_unobs: int = 1, min_age: floa
     order = obs[np.argsort(data.slot[obs])]
     top = int(data.gen[obs].max())
     n_gen = top + max_gen + 1
+    if data.soft_num is not None:      # every possible 4-decimal token, looked up instead of formatted
+        tbl = np.array([f"{k / 10000.0:.4f}" for k in range(65536)])
+        tblc = np.char.add(tbl, ",")
+    else:
+        tbl = np.array(["0", "1", "2", "3"])
     with open(run / "geno.txt", "w") as f:
         for rank, i in enumerate(order):
             founder = 1 if (max_gen == 0 and data.gen[i] == top) else 0
             if data.soft_num is not None:
-                toks = [",".join(f"{x / 10000.0:.4f}".rstrip("0").rstrip(".") if x % 10000 else str(x // 10000) for x in trip)
-                        for trip in data.soft_num[i, sl]]
+                n = data.soft_num[i, sl]
+                toks = np.char.add(np.char.add(tblc[n[:, 0]], tblc[n[:, 1]]), tbl[n[:, 2]])
             else:
-                toks = [str(int(c)) for c in data.codes[i, sl]]
-            f.write(f"{rank + 1} 1 {int(data.sex[i])} {int(data.gen[i])} {founder} " + " ".join(toks) + "\n")
+                toks = tbl[data.codes[i, sl]]
+            f.write(f"{rank + 1} 1 {int(data.sex[i])} {int(data.gen[i])} {founder} " + " ".join(toks.tolist()) + "\n")
     obs_frac = np.zeros(n_gen)
     obs_frac[np.unique(data.gen[obs])] = observe_frac
     with open(run / "prior.txt", "w") as f:
