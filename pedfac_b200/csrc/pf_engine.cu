@@ -103,7 +103,7 @@ struct pf_engine {
     std::vector<SoftChunk> soft_chunks;
     std::vector<double> h_eps;            // local shard, for validation only
 
-    DevBuf scratch, plan, partial, result, counters;
+    DevBuf scratch, plan, partial, result, counters, clockbuf;
     Staging staging;
     double *h_result = nullptr; size_t h_result_cap = 0;
 
@@ -406,7 +406,7 @@ struct ViewWork {           // scratch vectors reused across calls
     std::vector<int> mem_off, mem_i, mem_role;      // marriage -> members (pa, ma, kids)
     std::vector<int> Ui, um, urole, depth_m, lvlA;
     std::vector<int> up_i_row, up_m_row, dn_row, in_u_row, emis_idx;
-    std::vector<int> bfs_m, queue, cnt_a, cnt_b;
+    std::vector<int> bfs_m, queue, cnt_a, cnt_b, cnt_c, tmp_row;
     std::vector<char> vis_i, vis_m, label_seen;
 };
 
@@ -470,7 +470,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
 
         w.Ui.assign(nI, -1); w.um.assign(nM, -1); w.urole.assign(nM, 0); w.depth_m.assign(nM, 0);
         w.lvlA.assign(nM, 0); w.vis_i.assign(nI, 0); w.vis_m.assign(nM, 0); w.label_seen.assign(v->n_cc, 0);
-        w.up_i_row.assign(nI, -1); w.up_m_row.assign(nM, -1); w.in_u_row.assign(nM, -1); w.dn_row.assign(nI, -1); w.emis_idx.assign(nI, -1);
+        w.up_i_row.assign(nI, -1); w.up_m_row.assign(nM, -1); w.in_u_row.assign(nM, -1); w.tmp_row.assign(nM, -1); w.dn_row.assign(nI, -1); w.emis_idx.assign(nI, -1);
         w.bfs_m.clear();
         std::vector<int> roots, comp_members_end;   // BFS order of individuals per component
         std::vector<int> order_i;
@@ -602,30 +602,49 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 for (size_t b = mb; b < me; b++) max_depth = std::max(max_depth, w.depth_m[w.bfs_m[b]]);
                 std::vector<int> &cnt_m = w.cnt_a, &cnt_d = w.cnt_b;
                 cnt_m.assign(max_depth + 1, 0); cnt_d.assign(max_depth + 1, 0);
-                int bank_m = 0, bank_d = 0;
+                std::vector<int> &cnt_t = w.cnt_c;
+                cnt_t.assign(max_depth + 1, 0);
+                int bank_m = 0, bank_d = 0, bank_t = 0;
                 for (size_t b = mb; b < me; b++) {
                     const int m = w.bfs_m[b], d = w.depth_m[m];
-                    w.in_u_row[m] = cnt_m[d]++;                         // index inside the bank
-                    bank_m = std::max(bank_m, cnt_m[d]);
+                    {   // large sibships park their prefix products in 2 scratch rows per down kid
+                        int nk = 0;
+                        for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) if (w.mem_i[k] != w.um[m] && w.mem_role[k] == 2) nk++;
+                        w.tmp_row[m] = -1;
+                        if (nk > FAM_SMALL_MAX) { w.tmp_row[m] = cnt_t[d]; cnt_t[d] += 2 + 2 * ((nk + FAM_CHUNK - 1) / FAM_CHUNK); bank_t = std::max(bank_t, cnt_t[d]); }
+                    }
                     for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
                         const int x = w.mem_i[k];
                         if (x == w.um[m] || w.adj_off[x + 1] - w.adj_off[x] <= 1) continue;
-                        w.dn_row[x] = cnt_d[d]++;
-                        bank_d = std::max(bank_d, cnt_d[d]);
+                        w.dn_row[x] = (cnt_d[d]++) * 2 + (d & 1);      // two banks: consecutive depths overlap in time
+                        bank_d = std::max(bank_d, 2 * cnt_d[d]);
                     }
                 }
-                const int base_m = G.n_rows, base_d = G.n_rows + bank_m;
-                G.n_rows += bank_m + bank_d;
-                for (size_t b = mb; b < me; b++) w.in_u_row[w.bfs_m[b]] = SCRATCH_BIT | (base_m + w.in_u_row[w.bfs_m[b]]);
+                const int base_m = G.n_rows, base_d = G.n_rows + bank_m, base_t = base_d + bank_d;
+                G.n_rows += bank_m + bank_d + bank_t;
+                (void)base_m;
+                for (size_t b = mb; b < me; b++) if (w.tmp_row[w.bfs_m[b]] >= 0) w.tmp_row[w.bfs_m[b]] = SCRATCH_BIT | (base_t + w.tmp_row[w.bfs_m[b]]);
                 for (int oi = ib; oi < ie; oi++) {
                     const int i = order_i[oi];
                     if (w.dn_row[i] >= 0) w.dn_row[i] = SCRATCH_BIT | (base_d + w.dn_row[i]);
                 }
             }
+            // up_i rows: every non-leaf; then leaves with genotype data while shared memory has
+            // room — a cached leaf is decoded once (UP_IN at level 0, straight from global memory,
+            // so its genotype tile is not staged) instead of once per family task that folds it
             for (int oi = ib; oi < ie; oi++) {
                 const int i = order_i[oi];
                 const bool leaf = w.adj_off[i + 1] - w.adj_off[i] <= 1;
                 if (w.Ui[i] >= 0 && !leaf) w.up_i_row[i] = SCRATCH_BIT | G.n_rows++;
+            }
+            for (int oi = ib; oi < ie; oi++) {
+                const int i = order_i[oi];
+                const bool leaf = w.adj_off[i + 1] - w.adj_off[i] <= 1;
+                bool cached_leaf = false;
+                if (w.Ui[i] >= 0 && leaf && e->h_kind[v->indiv[i]] != EMIS_NONE && G.n_rows < SWEEP_LEAF_ROW_BUDGET) {
+                    w.up_i_row[i] = SCRATCH_BIT | G.n_rows++;
+                    cached_leaf = true;
+                }
                 // genotype entry
                 const int slot = v->indiv[i];
                 EmisEnt E{};
@@ -633,7 +652,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 const unsigned long long pp = (unsigned long long)(uintptr_t)e->h_eptr[slot];
                 E.ptr_lo = (unsigned)(pp & 0xffffffffu); E.ptr_hi = (unsigned)(pp >> 32);
                 const int bytes = emis_tile_bytes(E.kind);
-                if (bytes > 0 && G.emis_bytes + bytes <= SWEEP_EMIS_SMEM_MAX) { E.smem_off = (unsigned)G.emis_bytes; G.emis_bytes += (bytes + 7) & ~7; }
+                if (!cached_leaf && bytes > 0 && G.emis_bytes + bytes <= SWEEP_EMIS_SMEM_MAX) { E.smem_off = (unsigned)G.emis_bytes; G.emis_bytes += (bytes + 7) & ~7; }
                 else E.smem_off = EMIS_NOT_STAGED;
                 w.emis_idx[i] = G.emis_count++;
                 plan.emis.push_back(E);
@@ -650,46 +669,82 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             pool.push_back(member(r, 0));
             pool.push_back(e->stub_row(chain, v->indiv[r])); pool.push_back(out_base + v->indiv_cc[r]);
             below_rows(r, -1);
+            // cached leaves are decoded once, at level 0
+            for (int oi = ib; oi < ie; oi++) {
+                const int i = order_i[oi];
+                const bool leaf = w.adj_off[i + 1] - w.adj_off[i] <= 1;
+                if (!leaf || w.up_i_row[i] < 0) continue;
+                add_task(0, TASK_LEAF_IN);
+                pool.push_back(member(i, 0)); push_row(w.up_i_row[i]);
+            }
             for (size_t b = mb; b < me; b++) {
                 const int m = w.bfs_m[b];
                 const int flags = (v->marr_selfing[m] ? 1 : 0) | (w.urole[m] << 1);
                 const int u = w.um[m];
                 int nd = 0;
-                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
-                    const int x = w.mem_i[k];
-                    if (x == u) continue;
-                    nd++;
-                    if (w.up_i_row[x] < 0) continue;        // leaf: nothing to precompute
-                    add_task(2 * lvl_in(x, m), TASK_UP_IN);
-                    pool.push_back(member(x, w.mem_role[k])); push_row(w.up_i_row[x]);
-                    below_rows(x, m);
+                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) if (w.mem_i[k] != u) nd++;
+                add_task(1 + w.lvlA[m], TASK_FAM_UP);
+                pool.push_back(flags); push_row(w.up_m_row[m]);
+                {
+                    const size_t nc_at = pool.size(); pool.push_back(0);
+                    int ncomp = 0;
+                    for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                        const int x = w.mem_i[k];
+                        if (x == u || w.adj_off[x + 1] - w.adj_off[x] <= 1) continue;
+                        pool.push_back(member(x, w.mem_role[k])); push_row(w.up_i_row[x]);
+                        below_rows(x, m);
+                        ncomp++;
+                    }
+                    pool[nc_at] = ncomp;
                 }
-                add_task(2 * w.lvlA[m] + 1, TASK_UP_M);
-                pool.push_back(flags); push_row(w.up_m_row[m]); pool.push_back(nd);
+                int pa_k = -1, ma_k = -1, nkid = 0;
+                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                    if (w.mem_i[k] == u) continue;
+                    if (w.mem_role[k] == 0) pa_k = k; else if (w.mem_role[k] == 1) ma_k = k; else nkid++;
+                }
+                if (pa_k >= 0) push_up_i(w.mem_i[pa_k], 0); else pool.push_back(NO_REF);
+                if (ma_k >= 0) push_up_i(w.mem_i[ma_k], 1); else pool.push_back(NO_REF);
+                pool.push_back(nkid);
                 for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
-                    if (w.mem_i[k] != u) { pool.push_back(w.mem_role[k]); push_up_i(w.mem_i[k], w.mem_role[k]); }
-                add_task(-(2 + 2 * w.depth_m[m]), TASK_DN_IN);
-                pool.push_back(member(u, w.urole[m])); push_row(w.in_u_row[m]);
+                    if (w.mem_i[k] != u && w.mem_role[k] == 2) push_up_i(w.mem_i[k], 2);
+                add_task(-(2 + 2 * w.depth_m[m]), TASK_FAM_DOWN);
+                pool.push_back(flags); pool.push_back(e->prong_row(chain, v->marr[m]));
+                pool.push_back(member(u, w.urole[m]));
                 if (w.Ui[u] < 0) pool.push_back(-1); else push_row(w.dn_row[u]);
                 below_rows(u, m);
-                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                auto down_entry = [&](int k) {
+                    if (k < 0) { pool.push_back(NO_REF); pool.push_back(-1); pool.push_back(-1); return; }
                     const int x = w.mem_i[k];
-                    if (x == u) continue;
-                    add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_DN_OUT);
-                    pool.push_back(flags | (w.mem_role[k] << 3)); push_row(w.in_u_row[m]); push_up_i(x, w.mem_role[k]);
+                    push_up_i(x, w.mem_role[k]);
                     pool.push_back(e->stub_row(chain, v->indiv[x]));
                     if (w.dn_row[x] < 0) pool.push_back(-1); else push_row(w.dn_row[x]);
-                    pool.push_back(nd - 1);
-                    for (int k2 = w.mem_off[m]; k2 < w.mem_off[m + 1]; k2++) {
-                        const int y = w.mem_i[k2];
-                        if (y == u || k2 == k) continue;
-                        pool.push_back(w.mem_role[k2]); push_up_i(y, w.mem_role[k2]);
+                };
+                down_entry(pa_k); down_entry(ma_k);
+                pool.push_back(nkid);
+                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
+                    if (w.mem_i[k] != u && w.mem_role[k] == 2) down_entry(k);
+                if (w.tmp_row[m] < 0) pool.push_back(-1); else push_row(w.tmp_row[m]);
+                if (w.tmp_row[m] >= 0) {
+                    // KID_CHUNK tasks, one per FAM_CHUNK down kids (member order), on the next level
+                    std::vector<int> kk;
+                    for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
+                        if (w.mem_i[k] != u && w.mem_role[k] == 2) kk.push_back(k);
+                    const int tbase = w.tmp_row[m] & ~SCRATCH_BIT;
+                    for (size_t c0 = 0; c0 < kk.size(); c0 += FAM_CHUNK) {
+                        const int cn = (int)std::min<size_t>(FAM_CHUNK, kk.size() - c0);
+                        add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_KID_CHUNK);
+                        pool.push_back(flags);
+                        push_row(SCRATCH_BIT | tbase);
+                        push_row(SCRATCH_BIT | (tbase + 2 + 2 * (int)(c0 / FAM_CHUNK)));
+                        pool.push_back(cn);
+                        for (int j = 0; j < cn; j++) {
+                            const int x = w.mem_i[kk[c0 + j]];
+                            push_up_i(x, 2);
+                            pool.push_back(e->stub_row(chain, v->indiv[x]));
+                            if (w.dn_row[x] < 0) pool.push_back(-1); else push_row(w.dn_row[x]);
+                        }
                     }
                 }
-                add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_PRONG);
-                pool.push_back(flags); push_row(w.in_u_row[m]); pool.push_back(e->prong_row(chain, v->marr[m])); pool.push_back(nd);
-                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
-                    if (w.mem_i[k] != u) { pool.push_back(w.mem_role[k]); push_up_i(w.mem_i[k], w.mem_role[k]); }
             }
             G.pool_len = (int)pool.size() - G.pool_begin;
         }
@@ -727,11 +782,11 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     *n_out_total = out_base;
     if (plan.tasks.empty()) return PF_OK;
 
-    // levels: up band [0, 2 * max_up), down band starts at 2 * max_up
+    // levels: 0 = leaf caching, up band [1, 1 + max_up), down band starts at 1 + max_up
     int n_levels = 1;
     for (auto &t : plan.tasks) {
-        if (t.level == -1) t.level = 2 * max_up;
-        else if (t.level <= -2) t.level = 2 * max_up + (-t.level - 2);
+        if (t.level == -1) t.level = 1 + max_up;
+        else if (t.level <= -2) t.level = 1 + max_up + (-t.level - 2);
         n_levels = std::max(n_levels, t.level + 1);
     }
     plan.n_levels = n_levels;
@@ -829,6 +884,15 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     P.n_groups = G; P.n_levels = n_levels;
     P.partial = static_cast<double *>(e->partial.p);
     P.n_out = plan.n_out;
+    P.clocks = nullptr; P.clock_group = 0;
+    if (getenv("PF_SWEEP_CLOCKS")) {
+        // measurement aid: per-level clocks of the largest group, printed after the launch
+        CU(e->clockbuf.reserve((size_t)(n_levels + 2) * sizeof(long long)));
+        P.clocks = static_cast<long long *>(e->clockbuf.p);
+        int best = 0;
+        for (int g = 0; g < G; g++) if (plan.groups[g].task_end - plan.groups[g].task_begin > plan.groups[best].task_end - plan.groups[best].task_begin) best = g;
+        P.clock_group = best;
+    }
     {
         int rows = 0, rows_smem = 0;
         for (auto &sg : plan.groups) { rows += sg.n_rows; rows_smem += sg.n_rows_smem; }
@@ -840,6 +904,15 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     e->prof_end();
     e->launches++;
     CU(cudaGetLastError());
+    if (P.clocks) {
+        std::vector<long long> hc(n_levels + 1);
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpy(hc.data(), P.clocks, hc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const int *lo = &level_off[(size_t)P.clock_group * (n_levels + 1)];
+        fprintf(stderr, "sweep-clocks levels %d group-tasks %d:", n_levels, lo[n_levels] - lo[0]);
+        for (int l = 0; l < n_levels; l++) fprintf(stderr, " %d:%lld", lo[l + 1] - lo[l], hc[l + 1] - hc[l]);
+        fprintf(stderr, "\n");
+    }
     if (plan.n_out > 0) {
         ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_tiles, plan.n_out};
         e->prof_begin(2);

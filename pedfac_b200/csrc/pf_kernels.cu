@@ -18,8 +18,9 @@ struct SweepCtx {
     double *smem_lane;        // transient rows in shared memory, + lane
     double *scratch_lane;     // spilled transient rows of this group, + locus
     double *rows_lane;        // persistent rows, + locus
-    int Sp, Sl, s, lane, tile;
+    int Sp, Sl, s, lane, tile, n_rows_smem;
 };
+
 
 // Row access. A reference is either a transient row in shared memory, a spilled transient row or
 // a persistent row in global memory; the branch is warp-uniform and keeps each access in a known
@@ -44,6 +45,12 @@ __device__ __forceinline__ void st_row(const SweepCtx &C, int ref, Tri v)
     }
     double *p = ((ref & SCRATCH_BIT) ? C.scratch_lane : C.rows_lane) + (size_t)idx * 3 * C.Sp;
     p[0] = v.x; p[C.Sp] = v.y; p[2 * C.Sp] = v.z;
+}
+
+// reference to transient row idx of this group (used when a task walks consecutive scratch rows)
+__device__ __forceinline__ int scratch_ref(const SweepCtx &C, int idx)
+{
+    return SCRATCH_BIT | idx | (idx < C.n_rows_smem ? SMEM_ROW_BIT : 0);
 }
 
 // exact num / den for 16-bit numerators: Markstein's correction step on the rounded reciprocal
@@ -99,37 +106,40 @@ __device__ __forceinline__ Tri prod_rows(const SweepCtx &C, const int *rows, int
     return acc;
 }
 
-// fold one member's incoming message into the family tensor W[gm][gp]; one code path for all
-// roles: the member's factor matrix is in[gp] (father), in[gm] (mother) or K(gm,gp) (kid).
-// A selfing marriage uses the same tensor and reads only its diagonal (gm == gp).
-__device__ __forceinline__ void fold(Mat3 &W, int role, Tri in)
+// ---- family contractions -----------------------------------------------------------------------
+// A marriage with father message a[gp], mother message b[gm] and kid messages k_j contracts
+//     W[gm][gp] = a[gp] * b[gm] * prod_j K_j(gm,gp),   K_j(gm,gp) = sum_gk T[gk][gm][gp] k_j[gk].
+// Every K_j is symmetric in (gm,gp) and so is their elementwise product P (6 values); only the
+// parents' own factors break the symmetry. Messages out of the marriage:
+//     to the father  out[gp] = sum_gm b[gm] P[gm][gp]        (a left out)
+//     to the mother  out[gm] = sum_gp a[gp] P[gm][gp]        (b left out)
+//     to kid j       out[gk] = sum T[gk][gm][gp] a[gp] b[gm] P_{-j}[gm][gp]
+//     prong          the same with all kids in P                (_FillInProngs@0x10001dd70)
+// A selfing marriage has one parent state g = gm = gp: only the diagonal of P and a are used.
+__device__ __forceinline__ Sym3 sym_ones() { return Sym3{1.0, 1.0, 1.0, 1.0, 1.0, 1.0}; }
+__device__ __forceinline__ void sym_mul(Sym3 &P, const Sym3 &K)
 {
-    // role is warp-uniform (one task per warp), so these branches never diverge
-    if (role == 2) mat_mul_kid(W, in);
-    else if (role == 0) mat_mul_pa(W, in);
-    else mat_mul_ma(W, in);
+    P.a00 *= K.a00; P.a01 *= K.a01; P.a02 *= K.a02; P.a11 *= K.a11; P.a12 *= K.a12; P.a22 *= K.a22;
 }
-__device__ __forceinline__ Tri emit(const Mat3 &W, int role, int selfing)
+__device__ __forceinline__ Tri fam_to_pa(const Sym3 &P, Tri b, int selfing)
 {
-    if (selfing) return role == 0 ? mat_diag(W) : self_to_kid(mat_diag(W));
-    return role == 0 ? mat_to_pa(W) : role == 1 ? mat_to_ma(W) : mat_to_kid(W);
+    if (selfing) return Tri{P.a00, P.a11, P.a22};
+    return Tri{b.x * P.a00 + b.y * P.a01 + b.z * P.a02, b.x * P.a01 + b.y * P.a11 + b.z * P.a12, b.x * P.a02 + b.y * P.a12 + b.z * P.a22};
+}
+__device__ __forceinline__ Tri fam_to_kid(const Sym3 &P, Tri a, Tri b, int selfing)
+{
+    if (selfing) return self_to_kid(Tri{a.x * P.a00, a.y * P.a11, a.z * P.a22});
+    Mat3 W;     // W[gm][gp] = b[gm] * a[gp] * P[gm][gp]
+    W.m[0] = b.x * a.x * P.a00; W.m[1] = b.x * a.y * P.a01; W.m[2] = b.x * a.z * P.a02;
+    W.m[3] = b.y * a.x * P.a01; W.m[4] = b.y * a.y * P.a11; W.m[5] = b.y * a.z * P.a12;
+    W.m[6] = b.z * a.x * P.a02; W.m[7] = b.z * a.y * P.a12; W.m[8] = b.z * a.z * P.a22;
+    return mat_to_kid(W);
 }
 
-__device__ __forceinline__ void ones9(Mat3 &W)
-{
-#pragma unroll
-    for (int i = 0; i < 9; i++) W.m[i] = 1.0;
-}
-
-// fold the listed { role, up_i_row } members into W
-// up message of a family member: a stored row, or recomputed for a leaf
+// up message of a family member: a stored row, or recomputed for a leaf without a cached row
 __device__ __forceinline__ Tri up_msg(const SweepCtx &C, int ref)
 {
     return ref < 0 ? local_of(C, ref & 0x7fffffff) : ld_row(C, ref);
-}
-__device__ __forceinline__ void fold_members(const SweepCtx &C, Mat3 &W, const int *mem, int n)
-{
-    for (int y = 0; y < n; y++) fold(W, mem[2 * y], up_msg(C, mem[2 * y + 1]));
 }
 
 __device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &C, const int *t)
@@ -144,43 +154,156 @@ __device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &
     }
 }
 
-__device__ __forceinline__ void task_up_in(const SweepCtx &C, const int *t)
+// LEAF_IN: member, up_i_row — decode a leaf's local factor once into its cached row (level 0)
+__device__ __forceinline__ void task_leaf_in(const SweepCtx &C, const int *t)
 {
-    st_row(C, t[1], prod_rows(C, t + 3, t[2], local_of(C, t[0])));
+    st_row(C, t[1], local_of(C, t[0]));
 }
 
-__device__ __forceinline__ void task_up_m(const SweepCtx &C, const int *t)
+// product of the kid factors K(up_msg(ref)) of refs[0..n), four at a time so that the twelve
+// shared-memory loads of a chunk are in flight together (a long sibship is otherwise one
+// dependent load -> fma chain per kid)
+__device__ __forceinline__ void fold_kids(const SweepCtx &C, Sym3 &P, const int *refs, int stride, int n)
 {
-    Mat3 W; ones9(W);
-    fold_members(C, W, t + 3, t[2]);
-    st_row(C, t[1], emit(W, t[0] >> 1, t[0] & 1));
+    int j = 0;
+    for (; j + FAM_CHUNK <= n; j += FAM_CHUNK) {
+        Tri in[FAM_CHUNK];
+#pragma unroll
+        for (int c = 0; c < FAM_CHUNK; c++) in[c] = up_msg(C, refs[(j + c) * stride]);
+#pragma unroll
+        for (int c = 0; c < FAM_CHUNK; c++) sym_mul(P, kid_matrix(in[c]));
+    }
+    for (; j < n; j++) sym_mul(P, kid_matrix(up_msg(C, refs[j * stride])));
 }
 
-__device__ __forceinline__ void task_dn_in(const SweepCtx &C, const int *t)
+// FAM_UP: flags, up_m_row, nC, { member, up_i_row, nD, below[nD] } * nC, pa_ref, ma_ref, nk, kid_ref[nk]
+//   the nC non-leaf down members get their up message computed and stored first; pa_ref / ma_ref
+//   are NO_REF when that parent is the up individual (or the marriage is selfing)
+__device__ __forceinline__ void task_fam_up(const SweepCtx &C, const int *t)
 {
-    Tri in_u = local_of(C, t[0]);
-    if (t[2] >= 0) in_u = mul(in_u, ld_row(C, t[2]));
-    st_row(C, t[1], prod_rows(C, t + 4, t[3], in_u));
+    const int flags = t[0], selfing = flags & 1, urole = flags >> 1, nC = t[2];
+    const int *q = t + 3;
+    for (int x = 0; x < nC; x++) {
+        st_row(C, q[1], prod_rows(C, q + 3, q[2], local_of(C, q[0])));
+        q += 3 + q[2];
+    }
+    const Tri one{1.0, 1.0, 1.0};
+    const Tri a = q[0] == NO_REF ? one : up_msg(C, q[0]);
+    const Tri b = q[1] == NO_REF ? one : up_msg(C, q[1]);
+    Sym3 P = sym_ones();
+    fold_kids(C, P, q + 3, 1, q[2]);
+    const Tri out = urole == 0 ? fam_to_pa(P, b, selfing) : urole == 1 ? fam_to_pa(P, a, 0) : fam_to_kid(P, a, b, selfing);
+    st_row(C, t[1], out);
 }
 
-__device__ __forceinline__ void task_dn_out(const SweepCtx &C, const int *t)
+// message + stub of one down member
+__device__ __forceinline__ void put_down(const SweepCtx &C, const int *ent, Tri up, Tri dn)
 {
-    const int flags = t[0];
-    Mat3 W; ones9(W);
-    fold(W, (flags >> 1) & 3, ld_row(C, t[1]));
-    fold_members(C, W, t + 6, t[5]);
-    const Tri dn = emit(W, flags >> 3, flags & 1);
-    st_row(C, t[3], mul(up_msg(C, t[2]), dn));
-    if (t[4] >= 0) st_row(C, t[4], dn);
+    st_row(C, ent[1], mul(up, dn));
+    if (ent[2] >= 0) st_row(C, ent[2], dn);
 }
 
-__device__ __forceinline__ void task_prong(const SweepCtx &C, const int *t)
+// FAM_DOWN: flags, prong_row, u_member, u_dn_row (-1 = root), nSib, sib[nSib],
+//           pa{ref, stub_row, dn_row}, ma{ref, stub_row, dn_row}, nk, kid{ref, stub_row, dn_row} * nk, tmp_row
+//   pa.ref / ma.ref = NO_REF when that parent is the up individual (or selfing mother);
+//   tmp_row = scratch rows of a large sibship (2 for a, b + 2 per chunk of FAM_CHUNK kids) or -1
+__device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
 {
-    const int flags = t[0];
-    Mat3 W; ones9(W);
-    fold(W, (flags >> 1) & 3, ld_row(C, t[1]));
-    fold_members(C, W, t + 4, t[3]);
-    st_row(C, t[2], (flags & 1) ? self_to_kid(mat_diag(W)) : mat_to_kid(W));
+    const int flags = t[0], selfing = flags & 1, urole = flags >> 1, nSib = t[4];
+    Tri in_u = local_of(C, t[2]);
+    if (t[3] >= 0) in_u = mul(in_u, ld_row(C, t[3]));
+    in_u = prod_rows(C, t + 5, nSib, in_u);
+    const int *pa = t + 5 + nSib, *ma = pa + 3;
+    const int nk = ma[3];
+    const int *kid = ma + 4;
+    const Tri one{1.0, 1.0, 1.0};
+    const Tri a = urole == 0 ? in_u : pa[0] == NO_REF ? one : up_msg(C, pa[0]);
+    const Tri b = urole == 1 ? in_u : ma[0] == NO_REF ? one : up_msg(C, ma[0]);
+    Sym3 Pu = sym_ones();
+    if (urole == 2) sym_mul(Pu, kid_matrix(in_u));
+    const int tmp = kid[3 * nk];
+
+    if (tmp < 0) {
+        // small sibship (nk <= FAM_SMALL_MAX): everything from registers
+        Sym3 K[FAM_SMALL_MAX];
+#pragma unroll
+        for (int j = 0; j < FAM_SMALL_MAX; j++)
+            if (j < nk) K[j] = kid_matrix(up_msg(C, kid[3 * j]));
+        Sym3 Pall = Pu;
+#pragma unroll
+        for (int j = 0; j < FAM_SMALL_MAX; j++) if (j < nk) sym_mul(Pall, K[j]);
+        st_row(C, t[1], fam_to_kid(Pall, a, b, selfing));                 // prong
+        if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(Pall, b, selfing));
+        if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(Pall, a, 0));
+#pragma unroll
+        for (int j = 0; j < FAM_SMALL_MAX; j++) {
+            if (j >= nk) break;
+            Sym3 Pm = Pu;
+#pragma unroll
+            for (int i = 0; i < FAM_SMALL_MAX; i++) if (i != j && i < nk) sym_mul(Pm, K[i]);
+            put_down(C, kid + 3 * j, up_msg(C, kid[3 * j]), fam_to_kid(Pm, a, b, selfing));
+        }
+        return;
+    }
+    // large sibship: park a, b and, per chunk, the product of all factors OUTSIDE the chunk
+    // (exclusive prefix x exclusive suffix over chunks); KID_CHUNK tasks on the next level turn
+    // them into the kids' messages in parallel on the block's other warps
+    const int base = tmp & (SMEM_ROW_BIT - 1);
+    st_row(C, scratch_ref(C, base), a);
+    st_row(C, scratch_ref(C, base + 1), b);
+    const int nc = (nk + FAM_CHUNK - 1) / FAM_CHUNK;
+    Sym3 run = Pu;
+    for (int c = 0; c < nc; c++) {
+        const int r = base + 2 + 2 * c;
+        st_row(C, scratch_ref(C, r), Tri{run.a00, run.a01, run.a02});
+        st_row(C, scratch_ref(C, r + 1), Tri{run.a11, run.a12, run.a22});
+        fold_kids(C, run, kid + 3 * c * FAM_CHUNK, 3, min(FAM_CHUNK, nk - c * FAM_CHUNK));
+    }
+    st_row(C, t[1], fam_to_kid(run, a, b, selfing));                      // prong: run = all kids now
+    if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(run, b, selfing));
+    if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(run, a, 0));
+    Sym3 suf = sym_ones();
+    for (int c = nc - 1; c >= 0; c--) {
+        const int r = base + 2 + 2 * c;
+        const Tri p0 = ld_row(C, scratch_ref(C, r)), p1 = ld_row(C, scratch_ref(C, r + 1));
+        st_row(C, scratch_ref(C, r), Tri{p0.x * suf.a00, p0.y * suf.a01, p0.z * suf.a02});
+        st_row(C, scratch_ref(C, r + 1), Tri{p1.x * suf.a11, p1.y * suf.a12, p1.z * suf.a22});
+        if (c > 0) fold_kids(C, suf, kid + 3 * c * FAM_CHUNK, 3, min(FAM_CHUNK, nk - c * FAM_CHUNK));
+    }
+}
+
+// KID_CHUNK: flags, ab_row (a at ab_row, b at ab_row + 1), out_row (outside product, 2 rows), n,
+//            { up_ref, stub_row, dn_row (-1 = not needed) } * n            (n <= FAM_CHUNK kids)
+__device__ __forceinline__ void task_kid_chunk(const SweepCtx &C, const int *t)
+{
+    const int selfing = t[0] & 1, n = t[3];
+    const int ab = t[1] & (SMEM_ROW_BIT - 1), orow = t[2] & (SMEM_ROW_BIT - 1);
+    const Tri a = ld_row(C, scratch_ref(C, ab)), b = ld_row(C, scratch_ref(C, ab + 1));
+    const Tri p0 = ld_row(C, scratch_ref(C, orow)), p1 = ld_row(C, scratch_ref(C, orow + 1));
+    const Sym3 Pout{p0.x, p0.y, p0.z, p1.x, p1.y, p1.z};
+    const int *mem = t + 4;
+    Sym3 K[FAM_CHUNK];
+#pragma unroll
+    for (int j = 0; j < FAM_CHUNK; j++)
+        if (j < n) K[j] = kid_matrix(up_msg(C, mem[3 * j]));
+#pragma unroll
+    for (int j = 0; j < FAM_CHUNK; j++) {
+        if (j >= n) break;
+        Sym3 Pm = Pout;
+#pragma unroll
+        for (int i = 0; i < FAM_CHUNK; i++)
+            if (i != j && i < n) sym_mul(Pm, K[i]);
+        put_down(C, mem + 3 * j, up_msg(C, mem[3 * j]), fam_to_kid(Pm, a, b, selfing));
+    }
+}
+
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(unsigned smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
 // STAGED: every group's plan slice lives in shared memory (the normal case); otherwise plans are
@@ -221,43 +344,47 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, 1) sweep_kernel(const __grid
         pool = reinterpret_cast<const int *>(smem + L.pool);
         emis = reinterpret_cast<const EmisEnt *>(smem + L.emis);
     }
-    // genotype tiles: one warp per individual, lanes along the loci (global entries: the copy in
-    // shared memory may not be visible yet, so read the entry from global memory here)
+    __syncthreads();
+    // genotype tiles: fire-and-forget asynchronous copies (cp.async, 4 or 8 bytes per lane), one
+    // warp per individual, all of a warp's individuals in flight at once; one wait at the end.
+    // (A blocking load per individual made this phase a chain of global-memory latencies.)
     {
-        const EmisEnt *gemis = P.emis + G.emis_begin;
         char *edata = smem + L.edata;
-        const int s = tile * TILE_LOCI + lane;
+        const size_t Sp = D.Sp;
         for (int i = warp; i < G.emis_count; i += SWEEP_WARPS) {
-            const EmisEnt E = gemis[i];
+            const EmisEnt E = emis[i];
             if (E.smem_off == EMIS_NOT_STAGED || E.kind == EMIS_NONE) continue;
-            const void *gp = reinterpret_cast<const void *>(((unsigned long long)E.ptr_hi << 32) | E.ptr_lo);
-            char *dst = edata + E.smem_off;
-            if (E.kind == EMIS_HARD) {
-                if (lane < 2) reinterpret_cast<uint32_t *>(dst)[lane] = static_cast<const uint32_t *>(gp)[tile * 2 + lane];
-            } else if (E.kind == EMIS_DEC16) {
-                const uint16_t *u = static_cast<const uint16_t *>(gp);
-                uint16_t *o = reinterpret_cast<uint16_t *>(dst);
-                o[lane] = u[s]; o[TILE_LOCI + lane] = u[D.Sp + s]; o[2 * TILE_LOCI + lane] = u[2 * D.Sp + s];
-            } else if (E.kind == EMIS_F32) {
-                const float *f = static_cast<const float *>(gp);
-                float *o = reinterpret_cast<float *>(dst);
-                o[lane] = f[s]; o[TILE_LOCI + lane] = f[D.Sp + s]; o[2 * TILE_LOCI + lane] = f[2 * D.Sp + s];
-            } else {
-                const double *f = static_cast<const double *>(gp);
-                double *o = reinterpret_cast<double *>(dst);
-                o[lane] = f[s]; o[TILE_LOCI + lane] = f[D.Sp + s]; o[2 * TILE_LOCI + lane] = f[2 * D.Sp + s];
+            const char *gp = reinterpret_cast<const char *>(((unsigned long long)E.ptr_hi << 32) | E.ptr_lo);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(edata + E.smem_off);
+            if (E.kind == EMIS_HARD) {                      // 8 bytes: 2 words of 16 calls
+                if (lane < 2) cp_async4(dst + 4 * lane, gp + ((size_t)tile * 2 + lane) * 4);
+            } else if (E.kind == EMIS_DEC16) {              // 3 planes x 64 bytes
+                const int pl = lane >> 4, w4 = lane & 15;   // lanes 0-15 plane 0, 16-31 plane 1
+                cp_async4(dst + pl * 64 + 4 * w4, gp + ((size_t)pl * Sp + (size_t)tile * TILE_LOCI) * 2 + 4 * w4);
+                if (lane < 16) cp_async4(dst + 128 + 4 * w4, gp + ((size_t)2 * Sp + (size_t)tile * TILE_LOCI) * 2 + 4 * w4);
+            } else if (E.kind == EMIS_F32) {                // 3 planes x 128 bytes
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++)
+                    cp_async4(dst + pl * 128 + 4 * lane, gp + ((size_t)pl * Sp + (size_t)tile * TILE_LOCI + lane) * 4);
+            } else {                                        // 3 planes x 256 bytes
+#pragma unroll
+                for (int pl = 0; pl < 3; pl++)
+                    cp_async8(dst + pl * 256 + 8 * lane, gp + ((size_t)pl * Sp + (size_t)tile * TILE_LOCI + lane) * 8);
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
 
     SweepCtx C;
     C.emis = emis; C.edata = smem + L.edata; C.prior = s_prior; C.eps = s_eps;
-    C.lane = lane; C.tile = tile; C.s = tile * TILE_LOCI + lane; C.Sp = D.Sp; C.Sl = D.Sl;
+    C.lane = lane; C.tile = tile; C.s = tile * TILE_LOCI + lane; C.Sp = D.Sp; C.Sl = D.Sl; C.n_rows_smem = G.n_rows_smem;
     C.smem_lane = reinterpret_cast<double *>(smem + L.rows) + lane;
     C.scratch_lane = D.scratch + (size_t)G.scratch_base * 3 * D.Sp + C.s;
     C.rows_lane = D.rows + C.s;
 
+    const bool clk = P.clocks != nullptr && blockIdx.x == 0 && (int)blockIdx.y == P.clock_group && tid == 0;
+    if (clk) P.clocks[0] = clock64();
     for (int lev = 0; lev < P.n_levels; lev++) {
         const int beg = s_loff[lev] - G.task_begin, end = s_loff[lev + 1] - G.task_begin;
         for (int ti = beg + warp; ti < end; ti += SWEEP_WARPS) {
@@ -265,14 +392,14 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, 1) sweep_kernel(const __grid
             const int *t = pool + (tk.off - G.pool_begin);
             switch (tk.kind) {
             case TASK_ROOT: task_root(P, C, t); break;
-            case TASK_UP_IN: task_up_in(C, t); break;
-            case TASK_UP_M: task_up_m(C, t); break;
-            case TASK_DN_IN: task_dn_in(C, t); break;
-            case TASK_DN_OUT: task_dn_out(C, t); break;
-            default: task_prong(C, t); break;
+            case TASK_LEAF_IN: task_leaf_in(C, t); break;
+            case TASK_FAM_UP: task_fam_up(C, t); break;
+            case TASK_FAM_DOWN: task_fam_down(C, t); break;
+            default: task_kid_chunk(C, t); break;
             }
         }
         if (lev + 1 < P.n_levels) __syncthreads();
+        if (clk) P.clocks[lev + 1] = clock64();
     }
 }
 

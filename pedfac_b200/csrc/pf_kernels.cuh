@@ -25,26 +25,37 @@ namespace pf {
 // scratch array). The level loop therefore runs on shared-memory latency; the only global
 // traffic inside it is the streaming store of stubs and prongs.
 //
-// Fine-grained tasks keep every dependency step short (a step is executed by ONE warp per
-// 32-locus tile, so its length is the critical path) and let the idle warps of a block run the
-// independent pieces of a family in parallel:
-//   UP_IN(x)     up_i(x) = local(x) * prod up_m(below x)                 level 2h
-//   UP_M(m)      up_m(m) from the up_i of its down members                level 2h+1
-//   ROOT(r)      stub(r), log Z                                           first level of the down band
-//   DN_IN(m)     in_u(m) = local(u) * dn_m(u) * prod up_m(other below u)  level base+2d
-//   DN_OUT(m,x)  dn_m(x), stub(x) = up_i(x) * dn_m(x)                     level base+2d+1
-//   PRONG(m)     prong(m)                                                 level base+2d+1
+// One task per family and direction keeps the level count at (tree radius) x 2 and lets a warp
+// load every member's message once; a task is executed by ONE warp per 32-locus tile, the other
+// warps of the block take the other families of the level:
+//   LEAF_IN(x)   cache a leaf's local factor in a shared-memory row             level 0
+//   FAM_UP(m)    up_i of the non-leaf members (stored), then up_m(m)             level 1 + height
+//   ROOT(r)      stub(r), log Z                                                  first level of the down band
+//   FAM_DOWN(m)  in_u(m); dn_m(x) and stub(x) = up_i(x) * dn_m(x) for every down
+//                member x; prong(m)                                              level base + depth
 // Task records live in an int32 pool. Row references: plain = persistent row index; bit 30 =
-// transient row (group-local index), and bit 29 as well when that row lives in shared memory.
-//   ROOT:    member, stub_row, out_idx, nD, up_m_row[nD]
-//   UP_IN:   member, up_i_row, nD, up_m_row[nD]
-//   UP_M:    flags, up_m_row, n, { role, up_i_row } * n
-//   DN_IN:   member(u), in_u_row, u_dn_row (-1 = root), nSib, sib_up_m_row[nSib]
-//   DN_OUT:  flags | x_role << 3, in_u_row, x_up_i_row, stub_row, dn_row (-1 = not needed), n, { role, up_i_row } * n
-//   PRONG:   flags, in_u_row, prong_row, n, { role, up_i_row } * n
+// transient row (group-local index), and bit 29 as well when that row lives in shared memory;
+// bit 31 (LEAF_REF_BIT) = no row: recompute the leaf's local factor from its genotype tile.
+//   ROOT:     member, stub_row, out_idx, nD, up_m_row[nD]
+//   LEAF_IN:  member, up_i_row
+//   FAM_UP:   flags, up_m_row, nC, { member, up_i_row, nD, below_up_m_row[nD] } * nC, pa_ref, ma_ref, nk, kid_ref[nk]
+//   FAM_DOWN: flags, prong_row, u_member, u_dn_row (-1 = root), nSib, sib_up_m_row[nSib],
+//             pa{ref, stub_row, dn_row}, ma{ref, stub_row, dn_row}, nk, kid{ref, stub_row, dn_row} * nk, tmp_row
+//             (ref = NO_REF: that parent is the up individual / absent; dn_row = -1: not needed;
+//              tmp_row: scratch rows of a large sibship — 2 for the parents' messages + 2 per chunk — or -1)
 // member = role | founder << 2 | (group-local genotype entry index) << 3; roles: 0 father,
 // 1 mother, 2 kid. flags = selfing | (role of u(m) in m) << 1.
-enum TaskKind : int { TASK_ROOT = 0, TASK_UP_IN = 1, TASK_UP_M = 2, TASK_DN_IN = 3, TASK_DN_OUT = 4, TASK_PRONG = 5 };
+//   KID_CHUNK (large sibships; next level): flags, ab_row, outside_row, n, { up_ref, stub_row, dn_row } * n
+enum TaskKind : int { TASK_ROOT = 0, TASK_LEAF_IN = 1, TASK_FAM_UP = 2, TASK_FAM_DOWN = 3, TASK_KID_CHUNK = 4 };
+constexpr int NO_REF = 0x1fffffff;
+#ifndef PF_FAM_CHUNK
+#define PF_FAM_CHUNK 1
+#endif
+#ifndef PF_FAM_SMALL_MAX
+#define PF_FAM_SMALL_MAX 1
+#endif
+constexpr int FAM_CHUNK = PF_FAM_CHUNK;           // kids per KID_CHUNK task
+constexpr int FAM_SMALL_MAX = PF_FAM_SMALL_MAX;   // sibships up to this size are finished inside FAM_DOWN
 constexpr int SMEM_ROW_BIT = 1 << 29;
 // in place of an up_i row reference: the member is a leaf (no marriage below it), its up message
 // is its local factor, recomputed from the staged genotype tile: LEAF_REF_BIT | member
@@ -85,14 +96,18 @@ struct SweepParams {
     int n_groups, n_levels;
     double *partial;        // [n_tiles][n_out] per-tile log Z sums
     int n_out;
+    long long *clocks;      // measurement aid: per-level clock64() of block (0, largest group), or null
+    int clock_group;
 };
 
 constexpr int SWEEP_WARPS = 16;
 constexpr int TILE_LOCI = 32;
 constexpr int SMEM_ROW_BYTES = 3 * TILE_LOCI * 8;
-constexpr int SWEEP_SMEM_MAX = 220 * 1024;       // dynamic shared memory budget of one block
+constexpr int SWEEP_SMEM_MAX = 195 * 1024;       // dynamic shared memory budget of one block: stays under the
+                                                 // 196 KB carve-out so that 32 KB of L1 remain
 constexpr int SWEEP_PLAN_SMEM_MAX = 56 * 1024;   // larger plan slices are read from global memory
 constexpr int SWEEP_EMIS_SMEM_MAX = 72 * 1024;
+constexpr int SWEEP_LEAF_ROW_BUDGET = 160;       // transient rows per group below which leaves get a cached row
 
 // staged bytes of one individual's 32-locus genotype tile
 __host__ __device__ inline int emis_tile_bytes(unsigned kind)
