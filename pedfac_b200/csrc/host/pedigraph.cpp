@@ -192,7 +192,10 @@ struct Ped {
     PF_ENGINE_T *eng = nullptr;
     FILE *fNode = nullptr, *fEdge = nullptr, *fPed = nullptr, *fGeno = nullptr, *fLL = nullptr;
     long n_proposals = 0, n_sweeps = 0, n_steps = 0;
+    double t_sweep = 0, t_eval = 0, t_view = 0;      // seconds inside the engine calls / building views (PEDFAC_STATS)
 };
+
+static double now_s() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 static void die(const char *msg)
 {
@@ -438,6 +441,7 @@ static void RevertSex(Ped &p, int x)
 static void Propagating_msg(Ped &p)
 {
     if (p.nDirty == 0) return;     // the reference re-propagates everything; nothing would change
+    const double t0 = now_s();
     const bool all = p.nDirty == p.nCC;
     std::vector<int> indiv, icc, marr, mpa, mma, kb{0}, kids, labels;
     std::vector<uint8_t> founder, selfing;
@@ -461,7 +465,9 @@ static void Propagating_msg(Ped &p)
     v.marr_selfing = selfing.data(); v.marr_kid_begin = kb.data(); v.marr_kids = kids.data();
     v.n_cc = (int)labels.size();
     std::vector<double> ll(labels.size() + 1);
+    const double t1 = now_s();
     if (PFN(sweep)(p.eng, 0, &v, ll.data()) != PF_OK) die("sweep failed");
+    p.t_view += t1 - t0; p.t_sweep += now_s() - t1;
     p.n_sweeps++;
     for (size_t j = 0; j < labels.size(); j++) p.LLcc[labels[j]] = ll[j];
     p.LLtot = 0;                                               // _UpdateProb@0x10001dd0c-0x10001dd65
@@ -494,7 +500,9 @@ static void flush(Ped &p, int kid, Batch &b)
 {
     if (b.props.empty()) return;
     std::vector<double> lsum(b.props.size());
+    const double t0 = now_s();
     if (PFN(eval)(p.eng, 0, kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("eval failed");
+    p.t_eval += now_s() - t0;
     p.n_proposals += (long)b.props.size();
     for (size_t k = 0; k < b.props.size(); k++) p.chll[b.slot[k]] = compose(p, kid, b.props[k], lsum[k]);
     b.props.clear(); b.slot.clear();
@@ -1203,8 +1211,12 @@ int main(int argc, char **argv)
         printf("..%i\n", p.iter);
         fflush(stdout);
         if (stats)
+        {
             fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld seconds %.6f\n", p.iter,
                     p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, now() - t_iter);
+            fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view);
+            p.t_sweep = p.t_eval = p.t_view = 0;
+        }
     }
     printf(".. DONE \n");
     fclose(p.fEdge); fclose(p.fNode); fclose(p.fPed); fclose(p.fGeno); fclose(p.fLL);

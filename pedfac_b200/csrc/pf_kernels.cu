@@ -165,13 +165,17 @@ __device__ __forceinline__ void task_leaf_in(const SweepCtx &C, const int *t)
 // dependent load -> fma chain per kid)
 __device__ __forceinline__ void fold_kids(const SweepCtx &C, Sym3 &P, const int *refs, int stride, int n)
 {
+    constexpr int B = 4;
     int j = 0;
-    for (; j + FAM_CHUNK <= n; j += FAM_CHUNK) {
-        Tri in[FAM_CHUNK];
+    for (; j + B <= n; j += B) {
+        int ref[B];
+        Tri in[B];
 #pragma unroll
-        for (int c = 0; c < FAM_CHUNK; c++) in[c] = up_msg(C, refs[(j + c) * stride]);
+        for (int c = 0; c < B; c++) ref[c] = refs[(j + c) * stride];
 #pragma unroll
-        for (int c = 0; c < FAM_CHUNK; c++) sym_mul(P, kid_matrix(in[c]));
+        for (int c = 0; c < B; c++) in[c] = up_msg(C, ref[c]);
+#pragma unroll
+        for (int c = 0; c < B; c++) sym_mul(P, kid_matrix(in[c]));
     }
     for (; j < n; j++) sym_mul(P, kid_matrix(up_msg(C, refs[j * stride])));
 }
