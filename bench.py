@@ -142,6 +142,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture of this command
+    (profiles/r01_traffic.json; config B), or None."""
+    p = ROOT / "profiles" / "r01_traffic.json"
+    try:
+        return float(json.loads(p.read_text())[kernel]["dram_bytes_per_launch"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def cpu_count():
     try:
         return len(os.sched_getaffinity(0))
@@ -458,7 +468,7 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = alg / (k_ms[dom] * 1e-3) / 1e9 if k_ms[dom] > 0 else 0.0
     roofline = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(f"{dom}_kernel") if wl == "B" else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg / max(k_n[dom], 1),
                 "avg_launch_us": k_ms[dom] * 1e3 / max(k_n[dom], 1),
                 "kernel_ms_per_step": {k: v / 2 for k, v in k_ms.items()},
