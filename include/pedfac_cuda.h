@@ -145,6 +145,45 @@ int pf_sweep_batch_dev(pf_engine *e, int32_t n, const int32_t *chains, const pf_
 int pf_eval_batch_dev(pf_engine *e, int32_t n, const int32_t *chains, const int32_t *kids,
                       const int32_t *prop_begin, const pf_proposal *props, double *lsum_dev);
 
+/*
+ * Swap proposals ≙ _ProposeSwapping@0x1000223d0 with its helpers _initSwapMsg@0x100021cd0,
+ * _directpassIV2IF@0x100020810, _directpassIF2IV@0x100020a70 and the data term of
+ * _calculateBundlell@0x1000220e0 (enumerated by _EvalMoves@0x100015989-0x100016651).
+ *
+ * x is the focal individual (already pruned from its previous parents prev_pa / prev_ma; prev_marr is
+ * their marriage if it still exists, i.e. x had siblings, else -1), z a spouse of x in marriage
+ * marr_x, and marr_z the marriage in which z is a kid, with parents (pa_z, ma_z). With K0 = the kids
+ * left in prev_marr and Kz = the siblings of z, the proposal scores the pedigree in which
+ *     kind 1: the fathers are exchanged   marr_z = (prev_pa, ma_z, .)   x's family = (pa_z, prev_ma, .)
+ *     kind 2: the mothers are exchanged   marr_z = (pa_z, prev_ma, .)   x's family = (prev_pa, ma_z, .)
+ *     kind 3: both                        marr_z = (prev_pa, prev_ma, .) x's family = (pa_z, ma_z, .)
+ * and the sibships stay (move_kids = 0: marr_z keeps Kz + z, x joins K0; only kinds 1 and 2) or are
+ * exchanged too (move_kids = 1: marr_z gets K0 + z, x's family gets Kz + x; always for kind 3).
+ * The reference's kind 4 (two spouses) cannot be reached: its enumeration looks up the parents of x
+ * itself, which has none at that point (_EvalMoves@0x100016136-0x100016292).
+ *
+ * `view` must hold the current components of x, prev_pa and prev_ma (the messages of the last
+ * sweep of those components are the inputs, as in the reference). lsum[p] = sum over this engine's
+ * loci of log sum_g h0[g]*h1[g] = log Z of the merged, rewired component. The engine evaluates it as
+ * an upward-only sweep of that hypothetical component; nothing persisted is modified. The caller
+ * adds the bookkeeping with pf_compose_swap_ll().
+ */
+typedef struct pf_swap {
+    int32_t kind;       /* 1, 2 or 3 */
+    int32_t move_kids;  /* 0 / 1 (the reference's choice aux[1]: -1 / z) */
+    int32_t x, z;       /* individual slots */
+    int32_t marr_z;     /* marriage where z is a kid */
+    int32_t marr_x;     /* marriage of x and z */
+    int32_t prev_pa, prev_ma;
+    int32_t prev_marr;  /* or -1 */
+    int32_t reserved;
+} pf_swap;
+
+int pf_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t n,
+                  const pf_swap *swaps, double *lsum);
+int pf_eval_swaps_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t n,
+                      const pf_swap *swaps, double *lsum_dev);
+
 /* ≙ _RefineParentOffPair@0x100014d20 (its N_obs^2 x S _CalculateLLByStubs calls), dense form:
  * for every kid k and every candidate c (c != kid) the score
  *     lsum(kid k; c as the single given parent, the other parent a new founder) + cand_bias[c]
@@ -188,6 +227,16 @@ static inline double pf_compose_ll(double ll_tot, double lsum, double ll_cc_kid,
     a = a + (use_pa ? -ll_cc_pa : 0.0);
     a = a + (use_ma ? -ll_cc_ma : 0.0);
     return a + (ll_tot + lsum);
+}
+
+/* Bookkeeping of a swap proposal, in the order of _calculateBundlell@0x100022291-0x1000223a8:
+ *   ll = ((-LLcc[cc(x)] + -LLcc[cc(prev_pa)]) + (double)(-use_ma) * LLcc[cc(prev_ma)]) + (LLtot + lsum)
+ * use_ma = cc(prev_pa) != cc(prev_ma) && cc(prev_pa) != cc(x). */
+static inline double pf_compose_swap_ll(double ll_tot, double lsum, double ll_cc_x, double ll_cc_pa,
+                                        int use_ma, double ll_cc_ma)
+{
+    const double a = (-ll_cc_x) + (-ll_cc_pa);
+    return (a + (double)(-(use_ma ? 1 : 0)) * ll_cc_ma) + (ll_tot + lsum);
 }
 
 #ifdef __cplusplus

@@ -10,8 +10,7 @@
  * recomputed for every out-edge), full re-contraction per proposal.
  *
  * Differences that do not change any value: flat arrays instead of pointer-of-pointer rows;
- * per-edge messages live in a per-sweep arena instead of persisting on the mnode (the reference
- * recomputes all of them for a dirty component anyway); the swap-with-last worklist
+ * the swap-with-last worklist
  * bookkeeping is replaced by repeated scans (a tree message depends only on its inputs, so the
  * schedule cannot change a bit of the result).
  */
@@ -44,6 +43,8 @@ struct pfo_engine {
     double **emis;          /* [capI] -> [Sl][3] or NULL (= all ones)  indiv->lik */
     double **stub;          /* [capI] -> [Sl][3]  indiv->stub */
     double **prong;         /* [capM] -> [Sl][3]  mnode->prong */
+    double **m_in, **m_out; /* [capM] -> [ne][Sl][3]  mnode->in / mnode->out of the last sweep of that marriage */
+    int *m_ne;              /* [capM] edge capacity of the stored message arrays */
     int *loc;               /* [capI] slot -> index in the current view, else -1 */
     char *arena; size_t arena_cap, arena_used;
 };
@@ -72,8 +73,11 @@ int pfo_create(pfo_engine **out, const pf_config *cfg)
     e->emis = calloc(e->capI, sizeof(double *));
     e->stub = calloc(e->capI, sizeof(double *));
     e->prong = calloc(e->capM > 0 ? e->capM : 1, sizeof(double *));
+    e->m_in = calloc(e->capM > 0 ? e->capM : 1, sizeof(double *));
+    e->m_out = calloc(e->capM > 0 ? e->capM : 1, sizeof(double *));
+    e->m_ne = calloc(e->capM > 0 ? e->capM : 1, sizeof(int));
     e->loc = malloc(sizeof(int) * e->capI);
-    if (!e->eps || !e->prior || !e->emis || !e->stub || !e->prong || !e->loc) FAIL(PF_ENOMEM, "oom");
+    if (!e->eps || !e->prior || !e->emis || !e->stub || !e->prong || !e->loc || !e->m_in || !e->m_out || !e->m_ne) FAIL(PF_ENOMEM, "oom");
     for (int i = 0; i < e->capI; i++) e->loc[i] = -1;
     *out = e;
     return PF_OK;
@@ -83,7 +87,8 @@ int pfo_destroy(pfo_engine *e)
 {
     if (!e) return PF_OK;
     for (int i = 0; i < e->capI; i++) { free(e->emis[i]); free(e->stub[i]); }
-    for (int m = 0; m < e->capM; m++) free(e->prong[m]);
+    for (int m = 0; m < e->capM; m++) { free(e->prong[m]); free(e->m_in[m]); free(e->m_out[m]); }
+    free(e->m_in); free(e->m_out); free(e->m_ne);
     free(e->eps); free(e->prior); free(e->emis); free(e->stub); free(e->prong); free(e->loc);
     free(e->arena); free(e);
     return PF_OK;
@@ -188,7 +193,7 @@ int pfo_sweep(pfo_engine *e, int32_t chain, const pf_graph_view *v, double *ll_c
     /* size the arena */
     size_t nedges = 0;
     for (int j = 0; j < nM; j++) nedges += 2 + (v->marr_kid_begin[j + 1] - v->marr_kid_begin[j]);
-    size_t need = sizeof(double) * T3 * (6 * (size_t)nI + 2 * nedges) + sizeof(double) * nI
+    size_t need = sizeof(double) * T3 * (6 * (size_t)nI) + sizeof(double) * nI
                 + (sizeof(iadj) + 64) * (size_t)(nI + 1) + (sizeof(madj) + 192) * (size_t)(nM + 1)
                 + (sizeof(int) * 2 + 2) * (nedges + 16) + 4096;
     if (need > e->arena_cap) {
@@ -234,8 +239,17 @@ int pfo_sweep(pfo_engine *e, int32_t chain, const pf_graph_view *v, double *ll_c
         int ne = 2 + (v->marr_kid_begin[j + 1] - v->marr_kid_begin[j]);
         if (v->marr[j] < 0 || v->marr[j] >= e->capM) { rc = PF_EINVAL; snprintf(g_err, sizeof g_err, "bad marriage slot"); goto done_reset; }
         ma[j].ne = ne; ma[j].selfing = v->marr_selfing[j];
-        ma[j].in = arena_get(e, sizeof(double) * T3 * ne);
-        ma[j].out = arena_get(e, sizeof(double) * T3 * ne);
+        {   /* mnode->in / mnode->out persist between sweeps (the swap proposals read them) */
+            const int slot = v->marr[j];
+            if (e->m_ne[slot] < ne || !e->m_in[slot]) {
+                free(e->m_in[slot]); free(e->m_out[slot]);
+                e->m_in[slot] = malloc(sizeof(double) * T3 * (ne + 2));
+                e->m_out[slot] = malloc(sizeof(double) * T3 * (ne + 2));
+                if (!e->m_in[slot] || !e->m_out[slot]) { rc = PF_ENOMEM; snprintf(g_err, sizeof g_err, "oom"); goto done_reset; }
+                e->m_ne[slot] = ne + 2;
+            }
+            ma[j].in = e->m_in[slot]; ma[j].out = e->m_out[slot];
+        }
         ma[j].passIn = arena_get(e, ne); ma[j].passOut = arena_get(e, ne);   /* _ResetMsg@0x10001c210 */
         memset(ma[j].passIn, 0, ne); memset(ma[j].passOut, 0, ne);
     }
@@ -529,6 +543,236 @@ int pfo_eval(pfo_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_prop
  * sort descending (_compareLLonGC), keep top_k. The age-window test is the caller's (it chooses
  * the candidate set); the -LLcc terms of @0x10001f183-0x10001f241 arrive as cand_bias.
  * Ties: earlier candidate first. */
+/* ---------------------------------------------------------------------------------------- */
+/* Swap proposals: _ProposeSwapping@0x1000223d0 and its helpers, on the per-edge messages the
+ * last sweep left on the marriages (mnode->in / mnode->out).                                 */
+
+typedef struct {
+    pfo_engine *e;
+    const pf_graph_view *v;
+    int *mloc;      /* marriage slot -> index in the view, else -1 */
+    iadj *ia;       /* per view individual: attached marriages (view index) and edge */
+    size_t T3;
+} swap_ctx;
+
+static int view_edge_slot(const pf_graph_view *v, int j, int ed)
+{
+    return ed == 0 ? v->marr_pa[j] : ed == 1 ? v->marr_ma[j] : v->marr_kids[v->marr_kid_begin[j] + ed - 2];
+}
+
+/* _initSwapMsg@0x100021cd0: the message a kid receives from a family whose father message comes
+ * from marriage mPa's edge 0 (or the stub of iPa when mPa == -1), mother message from mMa's edge 1
+ * (or the stub of iMa), siblings = the kids of mKids except exclKid (none when mKids == -1). */
+static void init_swap_msg(const swap_ctx *c, double *holder, int mPa, int mMa, int mKids, int iPa, int iMa, int exclKid)
+{
+    const pfo_engine *e = c->e;
+    const size_t T3 = c->T3;
+    const double *paMsg = e->stub[iPa], *maMsg = e->stub[iMa];
+    if (mPa != -1) paMsg = e->m_in[mPa];                    /* @0x100021d47-0x100021d64 */
+    if (mMa != -1) maMsg = e->m_in[mMa] + T3;               /* @0x100021d68-0x100021d8a */
+    const int jk = mKids == -1 ? -1 : c->mloc[mKids];
+    const int ne = jk < 0 ? 2 : 2 + (c->v->marr_kid_begin[jk + 1] - c->v->marr_kid_begin[jk]);
+    for (int s = 0; s < e->Sl; s++)
+        for (int gk = 0; gk < 3; gk++) {
+            double acc = 0.0;
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < 3; b++) {
+                    double t = (TPROB[gk * 9 + b * 3 + a] * paMsg[s * 3 + a]) * maMsg[s * 3 + b];
+                    for (int k = 2; k < ne; k++) {          /* @0x100021f51-0x100022059 */
+                        if (view_edge_slot(c->v, jk, k) == exclKid) continue;
+                        double K = 0.0;
+                        for (int g = 0; g < 3; g++) K = K + TPROB[g * 9 + b * 3 + a] * e->m_in[mKids][k * T3 + s * 3 + g];
+                        t = t * K;
+                    }
+                    acc = acc + t;
+                }
+            holder[s * 3 + gk] = acc;
+        }
+}
+
+/* _directpassIV2IF@0x100020810: push the holder through individual `slot`: multiply by what its
+ * other marriages (all but mA, mB) send it, by its prior message and by its emission. */
+static void directpass_iv2if(const swap_ctx *c, double *holder, int slot, int mA, int mB)
+{
+    const pfo_engine *e = c->e;
+    const size_t T3 = c->T3;
+    const int i = e->loc[slot];
+    const double *em = e->emis[slot];
+    const int founder = c->v->indiv_founder[i];
+    for (int s = 0; s < e->Sl; s++)
+        for (int g = 0; g < 3; g++) {
+            double t = holder[s * 3 + g];
+            for (int k = 0; k < c->ia[i].nM; k++) {
+                const int m = c->v->marr[c->ia[i].mar[k]];
+                if (m == mA || m == mB) continue;
+                t = t * e->m_out[m][c->ia[i].edge[k] * T3 + s * 3 + g];
+            }
+            holder[s * 3 + g] = (t * (founder ? e->prior[s * 3 + g] : 1.0)) * (em ? em[s * 3 + g] : 1.0);
+        }
+}
+
+/* _directpassIF2IV@0x100020a70: push the holder through marriage M from member src to member dst:
+ * the holder replaces M's incoming message on src's edge (the reference saves and restores that
+ * row through ped->f160), then the ordinary marriage -> individual formula for dst's edge. */
+static int directpass_if2iv(const swap_ctx *c, double *holder, double *tmp, int M, int src, int dst)
+{
+    const pfo_engine *e = c->e;
+    const size_t T3 = c->T3;
+    const int j = c->mloc[M];
+    const pf_graph_view *v = c->v;
+    const int ne = 2 + (v->marr_kid_begin[j + 1] - v->marr_kid_begin[j]);
+    const int self = v->marr_selfing[j];
+    int dst_ed = 0;                                             /* @0x100020afb-0x100020bab */
+    if (v->marr_ma[j] == dst) dst_ed = 1;
+    else for (int k = 2; k < ne; k++) if (view_edge_slot(v, j, k) == dst) { dst_ed = k; break; }
+    int src_ed = -1;                                            /* @0x100020bb0-0x100020f13 */
+    if (v->marr_pa[j] == src) src_ed = 0;
+    else if (v->marr_ma[j] == src) src_ed = 1;
+    else for (int k = 2; k < ne; k++) if (view_edge_slot(v, j, k) == src) { src_ed = k; break; }
+    if (src_ed < 0 || ne > 64) return -1;
+    memcpy(tmp, holder, sizeof(double) * T3);
+    const double *in[64];
+    for (int k = 0; k < ne; k++) in[k] = k == src_ed ? tmp : e->m_in[M] + k * T3;
+    for (int s = 0; s < e->Sl; s++)
+        for (int go = 0; go < 3; go++) {
+            double acc;
+            if (dst_ed == 0 && !self) {                         /* @0x100020f44-0x1000210db */
+                acc = 0.0;
+                for (int gm = 0; gm < 3; gm++) {
+                    double t = in[1][s * 3 + gm];
+                    for (int k = 2; k < ne; k++) {
+                        double K = 0.0;
+                        for (int gk = 0; gk < 3; gk++) K = K + TPROB[gk * 9 + gm * 3 + go] * in[k][s * 3 + gk];
+                        t = t * K;
+                    }
+                    acc = acc + t;
+                }
+            } else if (dst_ed == 0) {                           /* @0x1000210e0-0x10002126e */
+                acc = 1.0;
+                for (int k = 2; k < ne; k++) {
+                    double K = 0.0;
+                    for (int gk = 0; gk < 3; gk++) K = K + TPROB[gk * 9 + go * 3 + go] * in[k][s * 3 + gk];
+                    acc = acc * K;
+                }
+            } else if (dst_ed == 1) {                           /* @0x100021282-0x100021496 */
+                acc = 0.0;
+                for (int gp = 0; gp < 3; gp++) {
+                    double t = in[0][s * 3 + gp];
+                    for (int k = 2; k < ne; k++) {
+                        double K = 0.0;
+                        for (int gk = 0; gk < 3; gk++) K = K + TPROB[gk * 9 + go * 3 + gp] * in[k][s * 3 + gk];
+                        t = t * K;
+                    }
+                    acc = acc + t;
+                }
+            } else if (!self) {                                 /* @0x1000214b8-0x100021764 */
+                acc = 0.0;
+                for (int gp = 0; gp < 3; gp++)
+                    for (int gm = 0; gm < 3; gm++) {
+                        double t = (TPROB[go * 9 + gm * 3 + gp] * in[0][s * 3 + gp]) * in[1][s * 3 + gm];
+                        for (int k = 2; k < ne; k++) {
+                            if (k == dst_ed) continue;
+                            double K = 0.0;
+                            for (int gk = 0; gk < 3; gk++) K = K + TPROB[gk * 9 + gm * 3 + gp] * in[k][s * 3 + gk];
+                            t = t * K;
+                        }
+                        acc = acc + t;
+                    }
+            } else {                                            /* @0x100021769-0x1000219b6 */
+                acc = 0.0;
+                for (int g = 0; g < 3; g++) {
+                    double t = TPROB[go * 9 + g * 3 + g] * in[0][s * 3 + g];
+                    for (int k = 2; k < ne; k++) {
+                        if (k == dst_ed) continue;
+                        double K = 0.0;
+                        for (int gk = 0; gk < 3; gk++) K = K + TPROB[gk * 9 + g * 3 + g] * in[k][s * 3 + gk];
+                        t = t * K;
+                    }
+                    acc = acc + t;
+                }
+            }
+            holder[s * 3 + go] = acc;
+        }
+    return 0;
+}
+
+int pfo_eval_swaps(pfo_engine *e, int32_t chain, const pf_graph_view *v, int32_t n, const pf_swap *swaps, double *lsum)
+{
+    (void)chain;
+    if (!e || !v || n < 0 || (n > 0 && (!swaps || !lsum))) FAIL(PF_EINVAL, "null argument");
+    const int nI = v->n_indiv, nM = v->n_marr;
+    const size_t T3 = (size_t)e->Sl * 3;
+    int rc = PF_OK;
+    swap_ctx c = {e, v, NULL, NULL, T3};
+    c.mloc = malloc(sizeof(int) * (e->capM + 1));
+    c.ia = calloc(nI + 1, sizeof(iadj));
+    size_t nedges = 0;
+    for (int j = 0; j < nM; j++) nedges += 2 + (v->marr_kid_begin[j + 1] - v->marr_kid_begin[j]);
+    int *adj = malloc(sizeof(int) * 2 * (nedges + 1));
+    double *h0 = malloc(sizeof(double) * T3), *h1 = malloc(sizeof(double) * T3), *tmp = malloc(sizeof(double) * T3);
+    int registered = 0;
+    if (!c.mloc || !c.ia || !adj || !h0 || !h1 || !tmp) { rc = PF_ENOMEM; snprintf(g_err, sizeof g_err, "oom"); goto done; }
+    for (int m = 0; m < e->capM; m++) c.mloc[m] = -1;
+    for (int i = 0; i < nI; i++) {
+        const int slot = v->indiv[i];
+        if (slot < 0 || slot >= e->capI || e->loc[slot] != -1) { rc = PF_EINVAL; snprintf(g_err, sizeof g_err, "bad or duplicate individual slot %d in view", slot); goto done; }
+        e->loc[slot] = i; registered = i + 1;
+    }
+    for (int pass = 0; pass < 2; pass++) {
+        if (pass == 1) {
+            int *p = adj;
+            for (int i = 0; i < nI; i++) { c.ia[i].mar = p; p += c.ia[i].nM; c.ia[i].edge = p; p += c.ia[i].nM; c.ia[i].nM = 0; }
+        }
+        for (int j = 0; j < nM; j++) {
+            const int ne = 2 + (v->marr_kid_begin[j + 1] - v->marr_kid_begin[j]);
+            if (v->marr[j] < 0 || v->marr[j] >= e->capM) { rc = PF_EINVAL; snprintf(g_err, sizeof g_err, "bad marriage slot"); goto done; }
+            c.mloc[v->marr[j]] = j;
+            for (int ed = 0; ed < ne; ed++) {
+                if (ed == 1 && v->marr_selfing[j]) continue;
+                const int slot = view_edge_slot(v, j, ed);
+                if (slot < 0 || slot >= e->capI || e->loc[slot] < 0) { rc = PF_EINVAL; snprintf(g_err, sizeof g_err, "view not closed"); goto done; }
+                const int i = e->loc[slot];
+                if (pass == 1) { c.ia[i].mar[c.ia[i].nM] = j; c.ia[i].edge[c.ia[i].nM] = ed; }
+                c.ia[i].nM++;
+            }
+        }
+    }
+    for (int q = 0; q < n; q++) {
+        const pf_swap *w = &swaps[q];
+        const int Mz = w->marr_z, Mx = w->marr_x, M0 = w->prev_marr, P = w->prev_pa, Q = w->prev_ma, x = w->x, z = w->z;
+        if (Mz < 0 || Mz >= e->capM || c.mloc[Mz] < 0 || Mx < 0 || Mx >= e->capM || c.mloc[Mx] < 0 || (M0 != -1 && (M0 < 0 || M0 >= e->capM || c.mloc[M0] < 0)) ||
+            x < 0 || x >= e->capI || e->loc[x] < 0 || z < 0 || z >= e->capI || e->loc[z] < 0 || P < 0 || P >= e->capI || e->loc[P] < 0 || Q < 0 || Q >= e->capI || e->loc[Q] < 0 ||
+            w->kind < 1 || w->kind > 3 || (w->kind == 3 && !w->move_kids)) { rc = PF_EINVAL; snprintf(g_err, sizeof g_err, "swap %d references something outside the view", q); goto done; }
+        if (v->marr_selfing[c.mloc[Mz]] || v->marr_selfing[c.mloc[Mx]] || (M0 != -1 && v->marr_selfing[c.mloc[M0]])) { rc = PF_EINVAL; snprintf(g_err, sizeof g_err, "swap %d touches a selfing marriage", q); goto done; }
+        const int paz = v->marr_pa[c.mloc[Mz]], maz = v->marr_ma[c.mloc[Mz]];
+        {
+            int z_in = 0;
+            for (int k = v->marr_kid_begin[c.mloc[Mz]]; k < v->marr_kid_begin[c.mloc[Mz] + 1]; k++) z_in = z_in || v->marr_kids[k] == z;
+            if (!z_in) { rc = PF_EINVAL; snprintf(g_err, sizeof g_err, "swap %d: z is not a kid of marr_z", q); goto done; }
+        }
+        /* _ProposeSwapping@0x100022422-0x100022a9e: which messages feed the two holders */
+        if (w->kind == 1 && !w->move_kids)      { init_swap_msg(&c, h0, M0, Mz, Mz, P, maz, z);   init_swap_msg(&c, h1, Mz, M0, M0, paz, Q, x); }
+        else if (w->kind == 1)                  { init_swap_msg(&c, h0, M0, Mz, M0, P, maz, x);   init_swap_msg(&c, h1, Mz, M0, Mz, paz, Q, z); }
+        else if (w->kind == 2 && !w->move_kids) { init_swap_msg(&c, h0, Mz, M0, Mz, paz, Q, z);   init_swap_msg(&c, h1, M0, Mz, M0, P, maz, x); }
+        else if (w->kind == 2)                  { init_swap_msg(&c, h0, Mz, M0, M0, paz, Q, x);   init_swap_msg(&c, h1, M0, Mz, Mz, P, maz, z); }
+        else                                    { init_swap_msg(&c, h0, M0, M0, M0, P, Q, x);     init_swap_msg(&c, h1, Mz, Mz, Mz, paz, maz, z); }
+        directpass_iv2if(&c, h0, z, Mz, Mx);                    /* path index 1: through z           */
+        if (directpass_if2iv(&c, h0, tmp, Mx, z, x)) { rc = PF_EINVAL; snprintf(g_err, sizeof g_err, "swap %d: z is not a member of marr_x", q); goto done; }
+        directpass_iv2if(&c, h0, x, Mx, Mx);                    /* path index 2: through x           */
+        double acc = 0.0;                                       /* _calculateBundlell@0x1000221b5-0x100022291 */
+        for (int s = 0; s < e->Sl; s++) {
+            double d = 0.0;
+            for (int g = 0; g < 3; g++) d = d + h1[s * 3 + g] * h0[s * 3 + g];
+            acc = acc + log(d);
+        }
+        lsum[q] = acc;
+    }
+done:
+    for (int i = 0; i < registered; i++) e->loc[v->indiv[i]] = -1;
+    free(c.mloc); free(c.ia); free(adj); free(h0); free(h1); free(tmp);
+    return rc;
+}
+
 int pfo_prefilter(pfo_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
                   const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
                   const double *cand_bias, int32_t top_k, int32_t *out_slot, double *out_score)

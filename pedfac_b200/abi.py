@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
+    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "eval_swaps", "eval_swaps_dev", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -88,6 +88,8 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("eval_batch", C.c_int, vp, C.c_int32, _i32p, _i32p, _i32p, vp, _f64p)
     sig("sweep_batch_dev", C.c_int, vp, C.c_int32, _i32p, C.POINTER(PfGraphView), vp)
     sig("eval_batch_dev", C.c_int, vp, C.c_int32, _i32p, _i32p, _i32p, vp, vp)
+    sig("eval_swaps", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), C.c_int32, vp, _f64p)
+    sig("eval_swaps_dev", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), C.c_int32, vp, vp)
     sig("prefilter", C.c_int, vp, C.c_int32, C.c_int32, _i32p, _u8p, C.c_int32, _i32p, _f64p,
         C.c_int32, _i32p, _f64p)
     sig("get_stub", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
@@ -152,6 +154,19 @@ def make_proposals(rows) -> np.ndarray:
     """rows: iterable of (kind, pa, ma, marr) -> contiguous `pf_proposal` array."""
     arr = np.array([tuple(r) for r in rows], dtype=PROPOSAL_DTYPE) if not isinstance(rows, np.ndarray) else rows
     return np.ascontiguousarray(arr, dtype=PROPOSAL_DTYPE)
+
+
+#: `pf_swap` of the header
+SWAP_DTYPE = np.dtype([("kind", "<i4"), ("move_kids", "<i4"), ("x", "<i4"), ("z", "<i4"), ("marr_z", "<i4"),
+                       ("marr_x", "<i4"), ("prev_pa", "<i4"), ("prev_ma", "<i4"), ("prev_marr", "<i4"),
+                       ("reserved", "<i4")])
+
+
+def make_swaps(rows) -> np.ndarray:
+    """rows: iterable of (kind, move_kids, x, z, marr_z, marr_x, prev_pa, prev_ma, prev_marr)."""
+    if isinstance(rows, np.ndarray) and rows.dtype == SWAP_DTYPE:
+        return np.ascontiguousarray(rows)
+    return np.array([tuple(r) + (0,) for r in rows], dtype=SWAP_DTYPE)
 
 
 class CEngine:
@@ -237,6 +252,17 @@ class CEngine:
         self._check(self._fn("eval")(self._h, chain, kid, len(props), C.c_void_p(props.ctypes.data), ptr(out, _f64p)))
         return out[:len(props)]
 
+    def eval_swaps(self, view: GraphView, swaps, chain: int = 0) -> np.ndarray:
+        swaps = make_swaps(swaps)
+        out = np.empty(max(len(swaps), 1), dtype=np.float64)
+        self._check(self._fn("eval_swaps")(self._h, chain, C.byref(view.struct), len(swaps),
+                                           C.c_void_p(swaps.ctypes.data), ptr(out, _f64p)))
+        return out[:len(swaps)]
+
+    def eval_swaps_dev(self, view: GraphView, swaps: np.ndarray, out_dev_ptr: int, chain: int = 0):
+        self._check(self._fn("eval_swaps_dev")(self._h, chain, C.byref(view.struct), len(swaps),
+                                               C.c_void_p(swaps.ctypes.data), C.c_void_p(out_dev_ptr)))
+
     def sweep_dev(self, view: GraphView, out_dev_ptr: int, chain: int = 0):
         self._check(self._fn("sweep_dev")(self._h, chain, C.byref(view.struct), C.c_void_p(out_dev_ptr)))
 
@@ -311,6 +337,12 @@ class CEngine:
     def launch_count(self) -> int:
         fn = getattr(self._lib, self._prefix + "launch_count", None)
         return int(fn(self._h)) if fn is not None else 0
+
+
+def compose_swap_ll(ll_tot, lsum, ll_cc_x, ll_cc_pa, use_ma, ll_cc_ma):
+    """`pf_compose_swap_ll` of the header (_calculateBundlell's scalar order)."""
+    a = (-ll_cc_x) + (-ll_cc_pa)
+    return (a + float(-(1 if use_ma else 0)) * ll_cc_ma) + (ll_tot + lsum)
 
 
 def compose_ll(ll_tot, lsum, ll_cc_kid, use_pa, ll_cc_pa, use_ma, ll_cc_ma):

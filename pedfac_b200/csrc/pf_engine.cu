@@ -419,7 +419,7 @@ static thread_local ViewWork g_work;
 // The band offset is fixed up by the caller once every view has been added. While a group is
 // being filled, SweepGroup::task_end counts its tasks and n_rows / emis_count its transient rows
 // and genotype entries.
-static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels)
+static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only)
 {
     if (!v) return fail(PF_EINVAL, "null view");
     const int nI = v->n_indiv, nM = v->n_marr;
@@ -597,7 +597,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             // and consumed within two consecutive levels of the down band, so every depth reuses
             // the same small bank of rows.
             for (size_t b = mb; b < me; b++) w.up_m_row[w.bfs_m[b]] = SCRATCH_BIT | G.n_rows++;
-            {
+            if (!up_only) {
                 int max_depth = 0;
                 for (size_t b = mb; b < me; b++) max_depth = std::max(max_depth, w.depth_m[w.bfs_m[b]]);
                 std::vector<int> &cnt_m = w.cnt_a, &cnt_d = w.cnt_b;
@@ -667,7 +667,9 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             const bool has_m = w.adj_off[r + 1] > w.adj_off[r];
             add_task(has_m ? -1 : 0, TASK_ROOT);
             pool.push_back(member(r, 0));
-            pool.push_back(e->stub_row(chain, v->indiv[r])); pool.push_back(out_base + v->indiv_cc[r]);
+            if (up_only) push_row(SCRATCH_BIT | G.n_rows++);        // nothing persisted: the root's belief goes to a transient row
+            else pool.push_back(e->stub_row(chain, v->indiv[r]));
+            pool.push_back(out_base + v->indiv_cc[r]);
             below_rows(r, -1);
             // cached leaves are decoded once, at level 0
             for (int oi = ib; oi < ie; oi++) {
@@ -707,6 +709,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 pool.push_back(nkid);
                 for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
                     if (w.mem_i[k] != u && w.mem_role[k] == 2) push_up_i(w.mem_i[k], 2);
+                if (up_only) continue;                              // log Z only: no down band
                 add_task(-(2 + 2 * w.depth_m[m]), TASK_FAM_DOWN);
                 pool.push_back(flags); pool.push_back(e->prong_row(chain, v->marr[m]));
                 pool.push_back(member(u, w.urole[m]));
@@ -755,7 +758,7 @@ cleanup:
 }
 
 // Upload the plan and launch sweep + reduce. out_dev receives n_out doubles.
-static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph_view *views, double *out_dev, int *n_out_total)
+static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph_view *views, double *out_dev, int *n_out_total, bool up_only = false)
 {
     CU(cudaSetDevice(e->cfg.device));
     int rc = sync_tables(e);
@@ -774,7 +777,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     int max_up = 0;
     int out_base = 0;
     for (int i = 0; i < n; i++) {
-        rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up);
+        rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up, up_only);
         if (rc) return rc;
         out_base += views[i].n_cc;
     }
@@ -977,6 +980,134 @@ extern "C" int pf_sweep_dev(pf_engine *e, int32_t chain, const pf_graph_view *vi
     if (!e || !view) return fail(PF_EINVAL, "null argument");
     int n_out = 0;
     return run_sweeps(e, 1, &chain, view, ll_cc_dev, &n_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Swap proposals (_ProposeSwapping@0x1000223d0). The reference pushes two "holder" messages along
+// the path parents(z) -> z -> marr_x -> x using the per-edge messages it keeps on every marriage;
+// the value, sum_s log sum_g h0*h1, is the log partition value of the component that results from
+// the rewiring _PickAndUpdate@0x100017f5a-0x100019281 would perform. This engine persists no
+// per-edge messages: it builds that hypothetical component and runs the upward half of a sweep
+// over it (log Z only, nothing persisted is written), one task group per proposal, one launch.
+
+namespace {
+struct HypoView {
+    std::vector<int> indiv, icc, marr, mpa, mma, kb, kids;
+    std::vector<uint8_t> founder, selfing;
+    pf_graph_view v;
+    void finish()
+    {
+        v.n_indiv = (int)indiv.size(); v.indiv = indiv.data(); v.indiv_cc = icc.data(); v.indiv_founder = founder.data();
+        v.n_marr = (int)marr.size(); v.marr = marr.data(); v.marr_pa = mpa.data(); v.marr_ma = mma.data();
+        v.marr_selfing = selfing.data(); v.marr_kid_begin = kb.data(); v.marr_kids = kids.data(); v.n_cc = 1;
+    }
+};
+} // namespace
+
+static int build_swap_view(pf_engine *e, const pf_graph_view *b, const pf_swap &w, int q, HypoView &H)
+{
+    auto label_of = [&](int slot) { return slot >= 0 && slot < e->cfg.cap_indiv && e->loc[slot] >= 0 ? b->indiv_cc[e->loc[slot]] : -1; };
+    const int lx = label_of(w.x), lp = label_of(w.prev_pa), lq = label_of(w.prev_ma);
+    if (lx < 0 || lp < 0 || lq < 0 || label_of(w.z) != lx) return fail(PF_EINVAL, "swap %d: x, z, prev_pa or prev_ma not in the view (or x and z in different components)", q);
+    if (lp == lx || lq == lx) return fail(PF_EINVAL, "swap %d: a previous parent is in the component of x", q);
+    if (w.kind < 1 || w.kind > 3 || (w.kind == 3 && !w.move_kids)) return fail(PF_EINVAL, "swap %d: bad kind", q);
+    auto in_set = [&](int l) { return l == lx || l == lp || l == lq; };
+    H.indiv.clear(); H.icc.clear(); H.founder.clear(); H.marr.clear(); H.mpa.clear(); H.mma.clear(); H.selfing.clear(); H.kids.clear(); H.kb.assign(1, 0);
+    for (int i = 0; i < b->n_indiv; i++)
+        if (in_set(b->indiv_cc[i])) { H.indiv.push_back(b->indiv[i]); H.icc.push_back(0); H.founder.push_back(b->indiv_founder[i]); }
+    int paz = -1, maz = -1;
+    bool have_z = false, have_x = false, have_0 = w.prev_marr == -1;
+    std::vector<int> Kz, K0;
+    for (int j = 0; j < b->n_marr; j++) {
+        const int lj = label_of(b->marr_pa[j]);
+        if (lj < 0) return fail(PF_EINVAL, "view not closed: marriage %d", b->marr[j]);
+        if (!in_set(lj)) continue;
+        const int kb = b->marr_kid_begin[j], ke = b->marr_kid_begin[j + 1];
+        const int slot = b->marr[j];
+        if (slot == w.marr_z || (slot == w.prev_marr && w.prev_marr != -1)) {
+            if (b->marr_selfing[j]) return fail(PF_EINVAL, "swap %d touches a selfing marriage", q);
+            if (slot == w.marr_z) {
+                paz = b->marr_pa[j]; maz = b->marr_ma[j];
+                bool found = false;
+                for (int k = kb; k < ke; k++) { if (b->marr_kids[k] == w.z) found = true; else Kz.push_back(b->marr_kids[k]); }
+                if (!found) return fail(PF_EINVAL, "swap %d: z is not a kid of marr_z", q);
+                have_z = true;
+            } else {
+                if (b->marr_pa[j] != w.prev_pa || b->marr_ma[j] != w.prev_ma) return fail(PF_EINVAL, "swap %d: prev_marr does not join prev_pa and prev_ma", q);
+                for (int k = kb; k < ke; k++) { if (b->marr_kids[k] == w.x) return fail(PF_EINVAL, "swap %d: x is still a kid of prev_marr", q); K0.push_back(b->marr_kids[k]); }
+                have_0 = true;
+            }
+            continue;
+        }
+        if (slot == w.marr_x) {
+            if (b->marr_selfing[j]) return fail(PF_EINVAL, "swap %d touches a selfing marriage", q);
+            const bool ok = (b->marr_pa[j] == w.x && b->marr_ma[j] == w.z) || (b->marr_pa[j] == w.z && b->marr_ma[j] == w.x);
+            if (!ok) return fail(PF_EINVAL, "swap %d: marr_x does not join x and z", q);
+            have_x = true;
+        }
+        H.marr.push_back(slot); H.mpa.push_back(b->marr_pa[j]); H.mma.push_back(b->marr_ma[j]); H.selfing.push_back(b->marr_selfing[j]);
+        H.kids.insert(H.kids.end(), b->marr_kids + kb, b->marr_kids + ke);
+        H.kb.push_back((int)H.kids.size());
+    }
+    if (!have_z || !have_x || !have_0) return fail(PF_EINVAL, "swap %d: marr_z, marr_x or prev_marr not in the view", q);
+    // the two rewired families (see pf_swap in the header)
+    const int P = w.prev_pa, Q = w.prev_ma;
+    int za, zb, xa, xb;
+    if (w.kind == 1) { za = P; zb = maz; xa = paz; xb = Q; }
+    else if (w.kind == 2) { za = paz; zb = Q; xa = P; xb = maz; }
+    else { za = P; zb = Q; xa = paz; xb = maz; }
+    const std::vector<int> &kids_z = w.move_kids ? K0 : Kz, &kids_x = w.move_kids ? Kz : K0;
+    auto emit = [&](int slot, int pa, int ma, const std::vector<int> &sibs, int extra) {
+        H.marr.push_back(slot); H.mpa.push_back(pa); H.mma.push_back(ma); H.selfing.push_back(0);
+        H.kids.insert(H.kids.end(), sibs.begin(), sibs.end()); H.kids.push_back(extra);
+        H.kb.push_back((int)H.kids.size());
+    };
+    emit(w.marr_z, za, zb, kids_z, w.z);
+    emit(w.prev_marr == -1 ? w.marr_z : w.prev_marr, xa, xb, kids_x, w.x);   // the slot only names a prong row, which an upward sweep never writes
+    H.finish();
+    return PF_OK;
+}
+
+static int run_swaps(pf_engine *e, int chain, const pf_graph_view *view, int n, const pf_swap *swaps, double *out_dev)
+{
+    if (!e || !view || n < 0 || (n > 0 && !swaps)) return fail(PF_EINVAL, "null argument");
+    if (n == 0) return PF_OK;
+    if (view->n_indiv < 0 || view->n_marr < 0 || (view->n_indiv > 0 && (!view->indiv || !view->indiv_cc || !view->indiv_founder)) ||
+        (view->n_marr > 0 && (!view->marr || !view->marr_pa || !view->marr_ma || !view->marr_selfing || !view->marr_kid_begin)))
+        return fail(PF_EINVAL, "malformed view");
+    int rc = PF_OK, registered = 0;
+    std::vector<HypoView> H(n);
+    std::vector<pf_graph_view> hv(n);
+    std::vector<int32_t> chains(n, chain);
+    for (int i = 0; i < view->n_indiv; i++) {
+        const int slot = view->indiv[i];
+        if (slot < 0 || slot >= e->cfg.cap_indiv || e->loc[slot] != -1) { rc = fail(PF_EINVAL, "bad or duplicate individual slot %d in view", slot); break; }
+        e->loc[slot] = i; registered = i + 1;
+    }
+    for (int q = 0; q < n && rc == PF_OK; q++) rc = build_swap_view(e, view, swaps[q], q, H[q]);
+    for (int i = 0; i < registered; i++) e->loc[view->indiv[i]] = -1;
+    if (rc) return rc;
+    for (int q = 0; q < n; q++) hv[q] = H[q].v;
+    int n_out = 0;
+    return run_sweeps(e, n, chains.data(), hv.data(), out_dev, &n_out, true);
+}
+
+extern "C" int pf_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t n, const pf_swap *swaps, double *lsum)
+{
+    if (!e) return fail(PF_EINVAL, "null argument");
+    if (n > 0 && !lsum) return fail(PF_EINVAL, "null output");
+    CU(cudaSetDevice(e->cfg.device));
+    CU(e->result.reserve((size_t)std::max(n, 1) * sizeof(double)));
+    int rc = run_swaps(e, chain, view, n, swaps, static_cast<double *>(e->result.p));
+    if (rc) return rc;
+    return fetch_result(e, lsum, n);
+}
+
+extern "C" int pf_eval_swaps_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t n, const pf_swap *swaps, double *lsum_dev)
+{
+    if (!e) return fail(PF_EINVAL, "null argument");
+    if (n > 0 && !lsum_dev) return fail(PF_EINVAL, "null output");
+    return run_swaps(e, chain, view, n, swaps, lsum_dev);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -62,6 +62,51 @@ class Pedigree:
             return mm.pa, mm.ma, None
         return mm.pa, mm.ma, m
 
+    def apply_swap(self, kind: int, move_kids: bool, x: int, z: int, marr_z: int, prev_pa: int,
+                   prev_ma: int, prev_marr, new_marr=None):
+        """The rewiring of a picked swap choice (`_PickAndUpdate@0x100016cf5` re-attaches the
+        pruned x to its previous parents, then `@0x100017f5a-0x100019281` exchanges the fathers
+        (kind 1), mothers (kind 2) or both (kind 3) of that family and of `marr_z`, and with
+        `move_kids` the two sibships as well). `self` is the pedigree after `detach_kid(x)`;
+        `prev_marr` is None when x was an only child (then `new_marr` names the free slot)."""
+        if prev_marr is None:
+            prev_marr = new_marr
+            self.add_marriage(prev_marr, prev_pa, prev_ma, [x])
+        else:
+            self.marriages[prev_marr].kids.append(x)
+        m0, mz = self.marriages[prev_marr], self.marriages[marr_z]
+        assert z in mz.kids and not m0.selfing and not mz.selfing
+        if kind in (1, 3):
+            m0.pa, mz.pa = mz.pa, m0.pa
+        if kind in (2, 3):
+            m0.ma, mz.ma = mz.ma, m0.ma
+        if move_kids:
+            k0 = [k for k in m0.kids if k != x]
+            kz = [k for k in mz.kids if k != z]
+            m0.kids, mz.kids = [x] + kz, [z] + k0
+        return prev_marr
+
+    def swap_sites(self):
+        """Every (x, z, marr_x, marr_z, marr_of_x) such that x is a kid of marr_of_x, a parent in
+        marr_x with spouse z, and z is a kid of marr_z: the situations in which
+        `_EvalMoves@0x100015989` proposes swaps for x (selfing marriages excluded)."""
+        kid_of = {k: m for m, mm in self.marriages.items() for k in mm.kids}
+        out = []
+        for mx, mm in sorted(self.marriages.items()):
+            if mm.selfing:
+                continue
+            for x, z in ((mm.pa, mm.ma), (mm.ma, mm.pa)):
+                if x in kid_of and z in kid_of and kid_of[x] != kid_of[z]:
+                    if not self.marriages[kid_of[x]].selfing and not self.marriages[kid_of[z]].selfing:
+                        out.append((x, z, mx, kid_of[z], kid_of[x]))
+        return out
+
+    def copy(self):
+        q = Pedigree(self.cap_indiv, self.cap_marr)
+        q.active, q.founder = self.active.copy(), self.founder.copy()
+        q.marriages = {m: Marriage(mm.pa, mm.ma, list(mm.kids), mm.selfing) for m, mm in self.marriages.items()}
+        return q
+
     # -- components ----------------------------------------------------------------------------
     def components(self):
         """Returns (label[cap_indiv] with -1 for inactive slots, n_cc). Labels are assigned in

@@ -105,7 +105,7 @@ def fold(fn):
             elif mn=='jmp':
                 out.append('%x:  goto L_%s'%(a,o[0][2:]))
             elif mn=='call':
-                args=', '.join(str(reg.get(r,r)) for r in ['rdi','rsi','rdx','rcx','r8','r9'][:4])
+                args=', '.join(str(reg.get(r,r)) for r in ['rdi','rsi','rdx','rcx','r8','r9'][:int(__import__('os').environ.get('NARGS','4'))])
                 xa=', '.join(str(reg.get(r,'')) for r in ['xmm0','xmm1'] if r in reg)
                 out.append('%x:  CALL %s(%s | %s)'%(a,note or ops,args,xa))
                 for r in ['rax','rcx','rdx','rsi','rdi','r8','r9','r10','r11']: reg.pop(r,None)
