@@ -211,7 +211,9 @@ def parse_stats(stderr):
     for line in stderr.splitlines():
         if line.startswith("pedigraph-stats"):
             t = line.split()
-            out.append({"iter": int(t[2]), "steps": int(t[4]), "proposals": int(t[6]), "sweeps": int(t[8]), "seconds": float(t[10])})
+            kv = dict(zip(t[1::2], t[2::2]))
+            out.append({"iter": int(kv["iter"]), "steps": int(kv["steps"]), "proposals": int(kv["proposals"]), "sweeps": int(kv["sweeps"]),
+                        "swaps": int(kv.get("swaps", 0)), "swaps_picked": int(kv.get("swaps_picked", 0)), "seconds": float(kv["seconds"])})
     return out
 
 

@@ -8,8 +8,10 @@
 //
 // Each routine cites the reference routine it follows as pedigraph@<VM address> <symbol>.
 // Differences from the reference, all deliberate and listed in DESIGN.md §7:
-//   * swap moves (_ProposeSwapping@0x100020xxx, enabled by default in the reference) are not
-//     implemented yet: the sampler behaves as the reference does under -w;
+//   * swap proposals of kind 4 (two spouses) are not generated: the reference's enumeration of them
+//     can never fire (_EvalMoves@0x100016136-0x100016292 looks up the parents of the focal
+//     individual itself, which is pruned at that point); swaps that touch a selfing marriage are
+//     skipped (the reference reads an unset message there);
 //   * -c 1 (throttle) and -l (loopy BP) are rejected;
 //   * the sweep that ends _PickAndUpdate is merged with the one that follows the next
 //     _PruneIndiv (nothing reads messages in between), so a Gibbs step costs one sweep;
@@ -158,7 +160,7 @@ struct Marr {
     bool selfing = false, mark = false;
     int nEdges() const { return 2 + (int)kids.size(); }
 };
-struct Choice { int mnode, pa, ma, selfing, kind; };
+struct Choice { int mnode, pa, ma, selfing, kind; int swapKind = 0, marrZ = -1, swapZ = -1; };   // kind 3 = swap (aux: kind, marr_z, z | -1)
 
 struct Opts {
     std::string dir, seedfile = "rand.tem";
@@ -191,7 +193,9 @@ struct Ped {
     std::vector<std::pair<int, double>> cand[3];
     PF_ENGINE_T *eng = nullptr;
     FILE *fNode = nullptr, *fEdge = nullptr, *fPed = nullptr, *fGeno = nullptr, *fLL = nullptr;
-    long n_proposals = 0, n_sweeps = 0, n_steps = 0;
+    long n_proposals = 0, n_sweeps = 0, n_steps = 0, n_swaps = 0, n_swaps_picked = 0;
+    bool check = false;                              // PEDFAC_CHECK: verify every picked move against the next sweep
+    std::vector<double> chll_data;
     double t_sweep = 0, t_eval = 0, t_view = 0;      // seconds inside the engine calls / building views (PEDFAC_STATS)
 };
 
@@ -438,35 +442,49 @@ static void RevertSex(Ped &p, int x)
 // ---------------------------------------------------------------------------------------------
 // _Propagating_msg@0x10001ba10: build the view of the dirty components and sweep it
 
+struct ViewBuf {
+    std::vector<int> indiv, icc, marr, mpa, mma, kb{0}, kids, labels;
+    std::vector<uint8_t> founder, selfing;
+    pf_graph_view v;
+};
+
+// the worklists of _TurnOnSpotlight@0x10001bb90 for the components with want[label] != 0
+static void build_view(Ped &p, const std::vector<char> &want, ViewBuf &b)
+{
+    std::vector<int> local(p.nCC, -1);
+    for (int c = 0; c < p.nCC; c++)
+        if (want[c]) { local[c] = (int)b.labels.size(); b.labels.push_back(c); }
+    for (int i = 0; i < p.nIndivUsed; i++) {
+        if (!p.indivActive[i] || local[p.cc[i]] < 0) continue;
+        b.indiv.push_back(i); b.icc.push_back(local[p.cc[i]]); b.founder.push_back(p.indiv[i].founder ? 1 : 0);
+    }
+    for (int m = 0; m < p.nMarrUsed; m++) {
+        if (!p.marrActive[m] || local[p.cc[p.marr[m].pa]] < 0) continue;
+        const Marr &mm = p.marr[m];
+        b.marr.push_back(m); b.mpa.push_back(mm.pa); b.mma.push_back(mm.ma); b.selfing.push_back(mm.selfing ? 1 : 0);
+        b.kids.insert(b.kids.end(), mm.kids.begin(), mm.kids.end());
+        b.kb.push_back((int)b.kids.size());
+    }
+    pf_graph_view &v = b.v;
+    v.n_indiv = (int)b.indiv.size(); v.indiv = b.indiv.data(); v.indiv_cc = b.icc.data(); v.indiv_founder = b.founder.data();
+    v.n_marr = (int)b.marr.size(); v.marr = b.marr.data(); v.marr_pa = b.mpa.data(); v.marr_ma = b.mma.data();
+    v.marr_selfing = b.selfing.data(); v.marr_kid_begin = b.kb.data(); v.marr_kids = b.kids.data();
+    v.n_cc = (int)b.labels.size();
+}
+
 static void Propagating_msg(Ped &p)
 {
     if (p.nDirty == 0) return;     // the reference re-propagates everything; nothing would change
     const double t0 = now_s();
     const bool all = p.nDirty == p.nCC;
-    std::vector<int> indiv, icc, marr, mpa, mma, kb{0}, kids, labels;
-    std::vector<uint8_t> founder, selfing;
-    std::vector<int> local(p.nCC, -1);
-    for (int c = 0; c < p.nCC; c++)
-        if (all || p.ccDirty[c]) { local[c] = (int)labels.size(); labels.push_back(c); }
-    for (int i = 0; i < p.nIndivUsed; i++) {                 // _TurnOnSpotlight@0x10001bb90
-        if (!p.indivActive[i] || local[p.cc[i]] < 0) continue;
-        indiv.push_back(i); icc.push_back(local[p.cc[i]]); founder.push_back(p.indiv[i].founder ? 1 : 0);
-    }
-    for (int m = 0; m < p.nMarrUsed; m++) {
-        if (!p.marrActive[m] || local[p.cc[p.marr[m].pa]] < 0) continue;
-        const Marr &mm = p.marr[m];
-        marr.push_back(m); mpa.push_back(mm.pa); mma.push_back(mm.ma); selfing.push_back(mm.selfing ? 1 : 0);
-        kids.insert(kids.end(), mm.kids.begin(), mm.kids.end());
-        kb.push_back((int)kids.size());
-    }
-    pf_graph_view v;
-    v.n_indiv = (int)indiv.size(); v.indiv = indiv.data(); v.indiv_cc = icc.data(); v.indiv_founder = founder.data();
-    v.n_marr = (int)marr.size(); v.marr = marr.data(); v.marr_pa = mpa.data(); v.marr_ma = mma.data();
-    v.marr_selfing = selfing.data(); v.marr_kid_begin = kb.data(); v.marr_kids = kids.data();
-    v.n_cc = (int)labels.size();
+    std::vector<char> want(p.nCC, 0);
+    for (int c = 0; c < p.nCC; c++) want[c] = all || p.ccDirty[c];
+    ViewBuf b;
+    build_view(p, want, b);
+    const std::vector<int> &labels = b.labels;
     std::vector<double> ll(labels.size() + 1);
     const double t1 = now_s();
-    if (PFN(sweep)(p.eng, 0, &v, ll.data()) != PF_OK) die("sweep failed");
+    if (PFN(sweep)(p.eng, 0, &b.v, ll.data()) != PF_OK) die("sweep failed");
     p.t_view += t1 - t0; p.t_sweep += now_s() - t1;
     p.n_sweeps++;
     for (size_t j = 0; j < labels.size(); j++) p.LLcc[labels[j]] = ll[j];
@@ -552,7 +570,71 @@ static bool checkMatchingCC(Ped &p, int pa, int ma, int kid)
 
 static bool by_ll_desc(const std::pair<int, double> &a, const std::pair<int, double> &b) { return a.second > b.second; }
 
-// _EvalMoves@0x100015010 (without the swap block @0x100015989-0x100016651)
+// The swap block of _EvalMoves@0x100015989-0x100016651 with _ProposeSwapping@0x1000223d0: for every
+// marriage of the focal individual x whose other parent z has parents itself, exchange the fathers
+// (kind 1), the mothers (kind 2) or both (kind 3) between x's previous family and z's family; kinds
+// 1 and 2 come in two flavours (siblings stay / siblings move too). All swaps of a step are scored
+// by one engine call on the view of the three components involved.
+static void ProposeSwaps(Ped &p, int x, bool redPa, bool redMa)
+{
+    const int P = p.prev[0], Q = p.prev[1], M0 = p.prev[2];
+    if (P < 0) return;
+    const int cx = p.cc[x];
+    if (p.cc[P] == cx || p.cc[Q] == cx) return;
+    const Indiv &ix = p.indiv[x];
+    auto spouse = [&](int m) { return p.marr[m].pa == x ? p.marr[m].ma : p.marr[m].pa; };
+    auto parents_marr = [&](int z) { const Indiv &iz = p.indiv[z]; for (size_t k = 0; k < iz.M.size(); k++) if (iz.edge[k] > 1) return iz.M[k]; return -1; };
+    for (int m : ix.M) {                                       // @0x1000159fd-0x100015bec
+        const int mz = parents_marr(spouse(m));
+        if (mz < 0) continue;
+        const int a = p.marr[mz].pa, b = p.marr[mz].ma;
+        p.indiv[a].reductive = isReductiveParent(p, a);
+        p.indiv[b].reductive = isReductiveParent(p, b);
+    }
+    std::vector<pf_swap> sw;
+    auto propose = [&](int kind, int z, int mz, int mx) {      // _ProposeSwapping@0x1000223d0
+        auto add = [&](int move) {
+            sw.push_back(pf_swap{kind, move, x, z, mz, mx, P, Q, M0, 0});
+            Choice c{M0, P, Q, 0, 3};
+            c.swapKind = kind; c.marrZ = mz; c.swapZ = move ? z : -1;
+            p.ch.push_back(c); p.chll.push_back(0.0);
+        };
+        if (kind == 3) { add(1); return; }
+        add(0);
+        if (M0 == -1 && p.marr[mz].nEdges() == 3) return;      // @0x1000226c4-0x1000226f8
+        add(1);
+    };
+    const size_t first = p.ch.size();
+    for (int mx : ix.M) {                                      // @0x100015bec-0x100016651
+        const int z = spouse(mx);
+        const int mz = parents_marr(z);
+        if (mz < 0) continue;
+        if (p.marr[mz].selfing || p.marr[mx].selfing || P == Q) continue;   // see the header of this file
+        const int paz = p.marr[mz].pa, maz = p.marr[mz].ma;
+        const bool rp = p.indiv[paz].reductive, rm = p.indiv[maz].reductive;
+        if (redPa && redMa && rp && rm) continue;
+        const bool k1 = !(redPa && rp), k2 = !(redMa && rm);
+        if (k1) propose(1, z, mz, mx);
+        if (k2) { propose(2, z, mz, mx); if (k1) propose(3, z, mz, mx); }
+        // kind 4 (pairs of x's marriages, @0x1000160da-0x100016638) never fires in the reference
+    }
+    if (sw.empty()) return;
+    const double t0 = now_s();
+    std::vector<char> want(p.nCC, 0);
+    want[cx] = want[p.cc[P]] = want[p.cc[Q]] = 1;
+    ViewBuf b;
+    build_view(p, want, b);
+    std::vector<double> lsum(sw.size());
+    const double t1 = now_s();
+    if (PFN(eval_swaps)(p.eng, 0, &b.v, (int)sw.size(), sw.data(), lsum.data()) != PF_OK) die("eval_swaps failed");
+    p.t_view += t1 - t0; p.t_eval += now_s() - t1;
+    p.n_proposals += (long)sw.size(); p.n_swaps += (long)sw.size();
+    const int cp = p.cc[P], cq = p.cc[Q];
+    for (size_t k = 0; k < sw.size(); k++)                      // _calculateBundlell@0x100022291-0x1000223a8
+        p.chll[first + k] = pf_compose_swap_ll(p.LLtot, lsum[k], p.LLcc[cx], p.LLcc[cp], cp != cq && cp != cx, p.LLcc[cq]);
+}
+
+// _EvalMoves@0x100015010
 static void EvalMoves(Ped &p, const Opts &o, int kid)
 {
     p.ch.clear(); p.chll.clear();
@@ -602,6 +684,7 @@ static void EvalMoves(Ped &p, const Opts &o, int kid)
         add_choice(p, b, PF_PROP_PRONG, -1, -1, m);
     }
     flush(p, kid, b);
+    if (!o.diswap) ProposeSwaps(p, kid, redPa, redMa);
 }
 
 // _AddObsFracPrior@0x100019800
@@ -730,7 +813,71 @@ static void PruneIndiv(Ped &p, int id)
     p.indiv[ma].reductive = isReductiveParent(p, ma);
 }
 
-// _PickAndUpdate@0x100016a60 (attach moves; swap choices do not exist here)
+// The swap branches of _PickAndUpdate@0x100017f5a-0x100019281. The kid has just been re-attached
+// to its previous parents in marriage m (sp, sq = the selected pa, ma); now the fathers (kind 1),
+// mothers (kind 2) or both (kind 3) of m and of marr_z change places, and when the choice carries z
+// (aux[1] >= 0) the two sibships do too: m keeps the kid and gets z's siblings, marr_z keeps z and
+// gets the kid's siblings.
+static void ApplySwap(Ped &p, const Choice &c, int kid, int m, int sp, int sq)
+{
+    const int mz = c.marrZ;
+    auto retarget_last = [&](int who, int from, int to) {      // search from the end (@0x100017fda-0x100018068)
+        Indiv &w = p.indiv[who];
+        for (int k = (int)w.M.size() - 1; k >= 0; k--) if (w.M[k] == from) { w.M[k] = to; return; }
+    };
+    auto retarget_first = [&](int who, int from, int to) {     // search from the start (@0x10001808e-0x100018135)
+        Indiv &w = p.indiv[who];
+        for (size_t k = 0; k < w.M.size(); k++) if (w.M[k] == from) { w.M[k] = to; return; }
+    };
+    const int paz = p.marr[mz].pa, maz = p.marr[mz].ma;
+    if (c.swapKind == 1) {
+        retarget_last(sp, m, mz); p.marr[m].pa = paz;
+        retarget_first(paz, mz, m); p.marr[mz].pa = sp;
+    } else if (c.swapKind == 2) {
+        retarget_last(sq, m, mz); p.marr[m].ma = maz;
+        retarget_first(maz, mz, m); p.marr[mz].ma = sq;
+    } else {
+        retarget_last(sp, m, mz); p.marr[m].pa = paz;
+        retarget_last(sq, m, mz); p.marr[m].ma = maz;
+        retarget_first(maz, mz, m); retarget_first(paz, mz, m);
+        p.marr[mz].pa = sp; p.marr[mz].ma = sq;
+    }
+    if (c.swapZ < 0) return;
+    const int z = c.swapZ;                                      // @0x100018b9e-0x10001927f
+    Marr &A = p.marr[m], &B = p.marr[mz];
+    const int nA = (int)A.kids.size(), nB = (int)B.kids.size();    // vf0 - 2, vf4 - 2
+    A.kids.resize(std::max(nA, nB) + 1); B.kids.resize(nA + nB + 1);
+    auto set_entry = [&](int who, int from, int to, int edge) {
+        Indiv &w = p.indiv[who];
+        for (size_t k = 0; k < w.M.size(); k++) if (w.M[k] == from) { w.M[k] = to; w.edge[k] = edge; return; }
+    };
+    int moved = 0;
+    for (int i = 0; i < nA - 1; i++) {                         // the kid's siblings queue up behind marr_z's kids
+        if (A.kids[i] == kid) continue;
+        B.kids[nB + moved++] = A.kids[i];
+    }
+    if (nA > 1) {
+        Indiv &w = p.indiv[kid];
+        for (int k = (int)w.M.size() - 1; k >= 0; k--) if (w.M[k] == m) { w.edge[k] = 2; break; }
+        A.kids[0] = kid;
+    }
+    if (nB > 1) {
+        int pos = 0;
+        for (int i = 0; i < nB; i++) {
+            const int y = B.kids[i];
+            if (y == z) { set_entry(z, mz, mz, 2); B.kids[0] = z; }
+            else { pos++; set_entry(y, mz, m, pos + 2); A.kids[pos] = y; }
+        }
+    }
+    for (int j = 0; j < moved; j++) {
+        const int y = B.kids[nB + j];
+        set_entry(y, m, mz, j + 1 + 2);
+        B.kids[j + 1] = y;
+    }
+    A.kids.resize(nB); B.kids.resize(nA);
+}
+
+// _PickAndUpdate@0x100016a60
 static void PickAndUpdate(Ped &p, int kid)
 {
     NormalizeAndSelect(p);
@@ -742,12 +889,16 @@ static void PickAndUpdate(Ped &p, int kid)
         if (!(u < 0.5)) std::swap(p.neu[0], p.neu[1]);
     }
     fprintf(p.fLL, "%d %d %f\n", p.iter, kid, p.picked >= 0 ? p.chll[p.picked] : 0.0);
-    if (p.neu[0] != p.prev[0] && p.prev[0] > -1) {
-        TrimPed(p, p.prev[0]); UpdateConComp(p, p.prev[0]); RevertSex(p, p.prev[0]);
+    const bool swap = p.picked >= 0 && p.ch[p.picked].kind == 3;
+    if (!swap) {                                               // @0x100016be2: a swap keeps the previous parents
+        if (p.neu[0] != p.prev[0] && p.prev[0] > -1) {
+            TrimPed(p, p.prev[0]); UpdateConComp(p, p.prev[0]); RevertSex(p, p.prev[0]);
+        }
+        if (p.prev[0] != p.prev[1] && p.neu[1] != p.prev[1] && p.prev[1] > -1) {
+            TrimPed(p, p.prev[1]); UpdateConComp(p, p.prev[1]); RevertSex(p, p.prev[0]);   // sic: prev.pa
+        }
     }
-    if (p.prev[0] != p.prev[1] && p.neu[1] != p.prev[1] && p.prev[1] > -1) {
-        TrimPed(p, p.prev[1]); UpdateConComp(p, p.prev[1]); RevertSex(p, p.prev[0]);   // sic: prev.pa
-    }
+    const int sel_pa = p.neu[0], sel_ma = p.neu[1];            // v54 / v58 of the swap rewiring below
     int m = p.neu[2], pa = p.neu[0], ma = p.neu[1];
     Indiv &k = p.indiv[kid];
     if (m != -1) {
@@ -785,10 +936,23 @@ static void PickAndUpdate(Ped &p, int kid)
         hist_edge(p, 1, m, kid);
     }
     hist_node(p, 3, kid);
+    if (swap) { pa = sel_pa; ma = sel_ma; ApplySwap(p, p.ch[p.picked], kid, m, pa, ma); p.n_swaps_picked++; }
     mark_dirty(p, p.cc[kid]);
     p.neu[0] = pa; p.neu[1] = ma; p.neu[2] = m;
     p.indiv[pa].sex = 1; p.indiv[ma].sex = 2;
     UpdateUnobsDegree(p, pa); UpdateUnobsDegree(p, ma); UpdateUnobsDegree(p, kid);
+    if (swap) {                                                // @0x10001938b-0x1000195f3: one row per kid of both families
+        auto family = [&](int mm_, bool parents) {
+            const Marr &f = p.marr[mm_];
+            if (parents) { UpdateUnobsDegree(p, f.pa); UpdateUnobsDegree(p, f.ma); }
+            for (int c : f.kids) {
+                UpdateUnobsDegree(p, c);
+                fprintf(p.fPed, "%d %d %d %d\n", p.iter, p.indiv[c].userID, p.indiv[f.pa].userID, p.indiv[f.ma].userID);
+            }
+        };
+        family(m, false);
+        family(p.ch[p.picked].marrZ, true);
+    } else
     fprintf(p.fPed, "%d %d %d %d\n", p.iter, k.userID, p.indiv[pa].userID, p.indiv[ma].userID);
     // the reference calls Propagating_msg here; the dirty flags carry over to the sweep at the
     // start of the next Gibbs step instead (see the header of this file)
@@ -805,8 +969,20 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
     Propagating_msg(p);
     EvalMoves(p, o, id);
     p.t++;
+    if (p.check) p.chll_data = p.chll;
     AddObsFracPrior(p, id);
     PickAndUpdate(p, id);
+    if (p.check && p.picked >= 0 && !p.ch.empty()) {
+        // the log-likelihood a proposal was scored with is the total the pedigree has once the move
+        // is made: re-propagate now and compare (every move kind, swaps included)
+        Propagating_msg(p);
+        const double want = p.chll_data[p.picked], got = p.LLtot;
+        if (!(fabs(want - got) <= 1e-9 * std::max(1.0, fabs(got)))) {
+            fprintf(stderr, "PEDFAC_CHECK: iter %d kid %d choice %d (kind %d swap %d/%d): scored %.12f, pedigree has %.12f\n",
+                    p.iter, id, p.picked, p.ch[p.picked].kind, p.ch[p.picked].swapKind, p.ch[p.picked].swapZ, want, got);
+            exit(3);
+        }
+    }
     const int pa = p.neu[0], ma = p.neu[1], self = p.neu[3];
     auto enqueue = [&](int x) { p.unobsQueue.push_back(x); p.indiv[x].queued = true; };
     const bool qa = pa >= p.nObs && !p.indiv[pa].queued, qm = ma >= p.nObs && !p.indiv[ma].queued;
@@ -1184,11 +1360,12 @@ int main(int argc, char **argv)
     // measurement aids (not part of the reference contract): PEDFAC_STATS=1 prints per-iteration
     // counters and wall time to stderr; PEDFAC_MAX_STEPS=K stops after K Gibbs steps in total
     const bool stats = getenv("PEDFAC_STATS") != nullptr;
+    p.check = getenv("PEDFAC_CHECK") != nullptr;             // PEDFAC_CHECK=1: re-propagate after every move and compare with its score
     const long max_steps = getenv("PEDFAC_MAX_STEPS") ? atol(getenv("PEDFAC_MAX_STEPS")) : -1;
     auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
     for (p.iter = 0; p.iter < o.nIter; p.iter++) {             // _main@0x10001a812-0x10001aaea
         const double t_iter = now();
-        const long props0 = p.n_proposals, sweeps0 = p.n_sweeps, steps0 = p.n_steps;
+        const long props0 = p.n_proposals, sweeps0 = p.n_sweeps, steps0 = p.n_steps, swaps0 = p.n_swaps, picked0 = p.n_swaps_picked;
         p.unobsQueue.clear();
         int qBeg = 0, qEnd = -1;
         for (int k = 0; k < p.nObs; k++) {
@@ -1212,8 +1389,8 @@ int main(int argc, char **argv)
         fflush(stdout);
         if (stats)
         {
-            fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld seconds %.6f\n", p.iter,
-                    p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, now() - t_iter);
+            fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld swaps %ld swaps_picked %ld seconds %.6f\n", p.iter,
+                    p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, p.n_swaps - swaps0, p.n_swaps_picked - picked0, now() - t_iter);
             fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view);
             p.t_sweep = p.t_eval = p.t_view = 0;
         }

@@ -16,9 +16,21 @@ REF = ROOT / "oracle" / "pedigraph_ref"
 GPU = ROOT / "pedfac_b200" / "bin" / "pedigraph"
 
 
-def run(binary, run_dir, n_iter=2, extra=()):
+def run(binary, run_dir, n_iter=2, extra=(), env=None):
+    import os
     return subprocess.run([str(binary), "-d", str(run_dir), "-n", str(n_iter), "-r", str(Path(run_dir) / "rand"), *extra],
-                          capture_output=True, text=True, timeout=600)
+                          capture_output=True, text=True, timeout=900, env={**os.environ, **(env or {})})
+
+
+def swap_counts(stderr):
+    """(proposed, picked) swap moves summed over the iterations (PEDFAC_STATS lines)."""
+    prop = pick = 0
+    for line in stderr.splitlines():
+        if line.startswith("pedigraph-stats"):
+            t = line.split()
+            kv = dict(zip(t[1::2], t[2::2]))
+            prop += int(kv["swaps"]); pick += int(kv["swaps_picked"])
+    return prop, pick
 
 
 def make_run(tmp_path, name, n=80, S=60, soft=False, seed=46, seeds=(2590, 7579545)):
@@ -37,7 +49,7 @@ def test_outputs_follow_the_file_contract(tmp_path):
         assert needle in out
     ped = (rd / "out" / "ped.txt").read_text().splitlines()
     ll = (rd / "out" / "ll.txt").read_text().splitlines()
-    assert len(ped) == len(ll) > 0
+    assert len(ped) >= len(ll) > 0          # a picked swap prints one row per kid of both families
     assert all(re.fullmatch(r"\d+ \d+ \d+ \d+", x) for x in ped)          # "%d %d %d %d\n"
     assert all(re.fullmatch(r"\d+ \d+ -?\d+\.\d{6}", x) for x in ll)       # "%d %d %f\n"
     assert (rd / "out" / "geno.txt").read_text() == ""                     # opened, never written
@@ -89,6 +101,27 @@ def test_soft_calls_and_error_paths(tmp_path):
     assert r.returncode != 0 and "not supported" in r.stderr
 
 
+def test_swap_moves_are_scored_consistently_and_can_be_disabled(tmp_path):
+    """Default mode proposes swap moves (_ProposeSwapping); PEDFAC_CHECK re-propagates after every
+    picked move (attach, prong and swap alike) and exits 3 unless the pedigree's total
+    log-likelihood equals the score the move was picked with. -w disables swaps."""
+    d, order, rd = make_run(tmp_path, "w1", n=200, S=150)
+    _, _, rd2 = make_run(tmp_path, "w2", n=200, S=150)
+    r = run(REF, rd, n_iter=4, env={"PEDFAC_CHECK": "1", "PEDFAC_STATS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    proposed, picked = swap_counts(r.stderr)
+    assert proposed > 50 and picked > 0
+    ped = (rd / "out" / "ped.txt").read_text().splitlines()
+    ll = (rd / "out" / "ll.txt").read_text().splitlines()
+    assert len(ped) > len(ll)                         # the picked swaps printed whole families
+    assert all(re.fullmatch(r"\d+ \d+ \d+ \d+", x) for x in ped)
+    r2 = run(REF, rd2, n_iter=4, extra=("-w",), env={"PEDFAC_CHECK": "1", "PEDFAC_STATS": "1"})
+    assert r2.returncode == 0, r2.stderr[-2000:]
+    assert swap_counts(r2.stderr) == (0, 0)
+    assert len((rd2 / "out" / "ped.txt").read_text().splitlines()) == len((rd2 / "out" / "ll.txt").read_text().splitlines())
+    assert (rd / "out" / "ped.txt").read_text() != (rd2 / "out" / "ped.txt").read_text()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("soft", [False, True])
 def test_gpu_sampler_reproduces_the_cpu_trace(tmp_path, soft):
@@ -96,9 +129,11 @@ def test_gpu_sampler_reproduces_the_cpu_trace(tmp_path, soft):
     of the picked choices agree to 1e-9 relative (ll.txt prints 6 decimals)."""
     d, order, rd = make_run(tmp_path, "g", n=260, S=180, soft=soft)
     _, _, rd2 = make_run(tmp_path, "h", n=260, S=180, soft=soft)
-    rg, rc = run(GPU, rd, n_iter=3), run(REF, rd2, n_iter=3)
+    env = {"PEDFAC_STATS": "1", "PEDFAC_CHECK": "1"}
+    rg, rc = run(GPU, rd, n_iter=4, env=env), run(REF, rd2, n_iter=4, env=env)
     assert rg.returncode == 0, rg.stderr
     assert rc.returncode == 0, rc.stderr
+    assert swap_counts(rg.stderr) == swap_counts(rc.stderr) and swap_counts(rg.stderr)[1] > 0   # swap moves are part of the trace
     assert (rd / "out" / "ped.txt").read_text() == (rd2 / "out" / "ped.txt").read_text()
     a = np.loadtxt(rd / "out" / "ll.txt"); b = np.loadtxt(rd2 / "out" / "ll.txt")
     np.testing.assert_array_equal(a[:, :2], b[:, :2])
