@@ -15,7 +15,7 @@ def header_symbols():
     txt = (ROOT / "include" / "pedfac_cuda.h").read_text()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     names = set(re.findall(r"\b(pf_[a-z0-9_]+)\s*\(", txt))
-    names.discard("pf_compose_ll")      # static inline helper
+    names -= {"pf_compose_ll", "pf_compose_swap_ll"}      # static inline helpers
     return names
 
 
