@@ -88,6 +88,7 @@ struct SoftChunk { char *base; size_t cap, used; };
 } // namespace
 
 struct pf_engine {
+    int eval_capacity = 0;            // resident eval_kernel blocks on this device
     pf_config cfg;
     int Sl = 0, Sp = 0;
     cudaStream_t stream = nullptr;
@@ -1154,12 +1155,15 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
         for (int b = prop_begin[i]; b < prop_begin[i + 1]; b += EVAL_G)
             hg[gi++] = EvalGroup{e->stub_row(chain, kid), b, std::min(EVAL_G, prop_begin[i + 1] - b), 0};
     }
-    // chunking: (chunks x group blocks) ~ one full wave of 148 SMs x 8 resident blocks, at least
-    // 4 lane-iterations per chunk, at most 128 (the running mantissa product needs renormalising
-    // only every 512 factors)
+    // chunking: (chunks x group blocks) fills one wave of resident blocks without spilling into a
+    // second, mostly empty one (measured at config C: a 1.45-wave grid 91 us, one wave 80 us); at
+    // least 4 lane-iterations per chunk, at most 128 (the running mantissa product needs
+    // renormalising only every 512 factors)
     const int group_blocks = (n_groups + EVAL_WARPS - 1) / EVAL_WARPS;
     const int max_chunks = std::max(1, (e->Sl + 127) / 128);
-    int n_chunks = std::max(1, std::min(max_chunks, (148 * 8 + group_blocks / 2) / group_blocks));
+    if (e->eval_capacity <= 0) e->eval_capacity = eval_resident_blocks();
+    const int waves = (group_blocks + e->eval_capacity - 1) / e->eval_capacity;    // > 1 only for huge proposal lists
+    int n_chunks = std::max(1, std::min(max_chunks, waves * e->eval_capacity / group_blocks));
     int chunk_loci = ((e->Sl + n_chunks - 1) / n_chunks + 31) / 32 * 32;
     chunk_loci = std::min(chunk_loci, 4096);
     n_chunks = (e->Sl + chunk_loci - 1) / chunk_loci;

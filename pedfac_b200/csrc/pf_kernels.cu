@@ -500,6 +500,17 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_c
     }
 }
 
+// resident eval blocks on the current device (SM count x blocks per SM from the occupancy
+// calculator): run_evals sizes its grid to one full wave of exactly this many blocks
+int eval_resident_blocks()
+{
+    int dev = 0, sms = 148, per_sm = 4;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, eval_kernel, EVAL_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return sms * per_sm;
+}
+
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st)
 {
     dim3 grid(n_chunks, (P.n_groups + EVAL_WARPS - 1) / EVAL_WARPS);

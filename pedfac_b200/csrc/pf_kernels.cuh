@@ -166,6 +166,7 @@ struct ReduceParams {
 
 void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, cudaStream_t st);
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st);
+int eval_resident_blocks();
 void launch_reduce(const ReduceParams &P, cudaStream_t st);
 
 } // namespace pf
