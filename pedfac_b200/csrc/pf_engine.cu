@@ -88,6 +88,7 @@ struct SoftChunk { char *base; size_t cap, used; };
 } // namespace
 
 struct pf_engine {
+    int sm_count = 0;
     int eval_capacity = 0;            // resident eval_kernel blocks on this device
     pf_config cfg;
     int Sl = 0, Sp = 0;
@@ -420,7 +421,7 @@ static thread_local ViewWork g_work;
 // The band offset is fixed up by the caller once every view has been added. While a group is
 // being filled, SweepGroup::task_end counts its tasks and n_rows / emis_count its transient rows
 // and genotype entries.
-static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only)
+static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only, const SweepShape &shape)
 {
     if (!v) return fail(PF_EINVAL, "null view");
     const int nI = v->n_indiv, nM = v->n_marr;
@@ -642,7 +643,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 const int i = order_i[oi];
                 const bool leaf = w.adj_off[i + 1] - w.adj_off[i] <= 1;
                 bool cached_leaf = false;
-                if (w.Ui[i] >= 0 && leaf && e->h_kind[v->indiv[i]] != EMIS_NONE && G.n_rows < SWEEP_LEAF_ROW_BUDGET) {
+                if (w.Ui[i] >= 0 && leaf && e->h_kind[v->indiv[i]] != EMIS_NONE && G.n_rows < shape.leaf_row_budget) {
                     w.up_i_row[i] = SCRATCH_BIT | G.n_rows++;
                     cached_leaf = true;
                 }
@@ -653,7 +654,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 const unsigned long long pp = (unsigned long long)(uintptr_t)e->h_eptr[slot];
                 E.ptr_lo = (unsigned)(pp & 0xffffffffu); E.ptr_hi = (unsigned)(pp >> 32);
                 const int bytes = emis_tile_bytes(E.kind);
-                if (!cached_leaf && bytes > 0 && G.emis_bytes + bytes <= SWEEP_EMIS_SMEM_MAX) { E.smem_off = (unsigned)G.emis_bytes; G.emis_bytes += (bytes + 7) & ~7; }
+                if (!cached_leaf && bytes > 0 && G.emis_bytes + bytes <= shape.emis_smem_max) { E.smem_off = (unsigned)G.emis_bytes; G.emis_bytes += (bytes + 7) & ~7; }
                 else E.smem_off = EMIS_NOT_STAGED;
                 w.emis_idx[i] = G.emis_count++;
                 plan.emis.push_back(E);
@@ -775,64 +776,86 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         const long long G = std::max<long long>(1, std::min<long long>(std::min<long long>(want_groups, est_comp), 65535));
         plan.target_tasks_per_group = (int)std::max<long long>(1, (est_tasks + G - 1) / G);
     }
-    int max_up = 0;
-    int out_base = 0;
-    for (int i = 0; i < n; i++) {
-        rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up, up_only);
-        if (rc) return rc;
-        out_base += views[i].n_cc;
-    }
-    plan.n_out = out_base;
-    *n_out_total = out_base;
-    if (plan.tasks.empty()) return PF_OK;
-
-    // levels: 0 = leaf caching, up band [1, 1 + max_up), down band starts at 1 + max_up
-    int n_levels = 1;
-    for (auto &t : plan.tasks) {
-        if (t.level == -1) t.level = 1 + max_up;
-        else if (t.level <= -2) t.level = 1 + max_up + (-t.level - 2);
-        n_levels = std::max(n_levels, t.level + 1);
-    }
-    plan.n_levels = n_levels;
-    const int G = (int)plan.groups.size();
-    if (G > 65535) return fail(PF_EINVAL, "too many task groups (%d)", G);
-
-    // counting sort by (group, level); groups own contiguous task ranges in emission order already
-    std::vector<int> level_off((size_t)G * (n_levels + 1) + 1, 0);
-    for (auto &t : plan.tasks) level_off[(size_t)t.group * (n_levels + 1) + t.level + 1]++;
-    std::vector<int> start((size_t)G * n_levels, 0);
-    {
-        int base = 0;
-        for (int g = 0; g < G; g++) {
-            int *lo = &level_off[(size_t)g * (n_levels + 1)];
-            int run = base;
-            for (int l = 0; l < n_levels; l++) { const int c = lo[l + 1]; start[(size_t)g * n_levels + l] = run; lo[l] = run; run += c; }
-            lo[n_levels] = run;
-            plan.groups[g].task_begin = base;
-            plan.groups[g].task_end = run;
-            base = run;
-        }
-    }
-    // shared-memory budget per group: stage the plan slice if it is small, then as many transient
-    // rows as fit; the launch uses the largest layout
-    int smem_bytes = 0, scratch_rows = 0;
+    // Build the plan for the latency shape first; if the launch then has more heavy blocks than
+    // the GPU has SMs (a block of a large component runs ~100 us whatever the number of tiles),
+    // rebuild it for the throughput shape, which overlaps two blocks per SM (see SweepShape).
+    int sm_count = e->sm_count;
+    if (sm_count <= 0) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device); e->sm_count = sm_count = sm_count > 0 ? sm_count : 148; }
+    const int target_tasks = plan.target_tasks_per_group;
+    bool throughput_shape = false;
+    int n_levels = 1, G = 0, smem_bytes = 0, scratch_rows = 0, max_up = 0;
     bool all_staged = true;
-    for (int g = 0; g < G; g++) {
-        const int slice0 = (plan.groups[g].task_end - plan.groups[g].task_begin) * 8 + plan.groups[g].pool_len * 4 + plan.groups[g].emis_count * (int)sizeof(EmisEnt);
-        if (slice0 > SWEEP_PLAN_SMEM_MAX) all_staged = false;
-    }
-    for (int g = 0; g < G; g++) {
-        SweepGroup &sg = plan.groups[g];
-        const int slice = (sg.task_end - sg.task_begin) * 8 + sg.pool_len * 4 + sg.emis_count * (int)sizeof(EmisEnt);
-        (void)slice;
-        sg.staged = all_staged ? 1 : 0;
-        sg.n_rows_smem = 0;
-        const SweepSmem L0 = sweep_smem_layout(sg, n_levels);
-        if (L0.total > SWEEP_SMEM_MAX) return fail(PF_EINVAL, "sweep plan too deep for shared memory (%d levels)", n_levels);
-        sg.n_rows_smem = std::min(sg.n_rows, (SWEEP_SMEM_MAX - L0.total) / SMEM_ROW_BYTES);
-        sg.scratch_base = scratch_rows;
-        scratch_rows += sg.n_rows;
-        smem_bytes = std::max(smem_bytes, sweep_smem_layout(sg, n_levels).total);
+    std::vector<int> level_off, start;
+    for (int pass = 0; pass < 2; pass++) {
+        const SweepShape shape = throughput_shape ? SWEEP_THROUGHPUT : SWEEP_LATENCY;
+        plan = Plan();
+        plan.target_tasks_per_group = target_tasks;
+        max_up = 0;
+        int out_base = 0;
+        for (int i = 0; i < n; i++) {
+            rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up, up_only, shape);
+            if (rc) return rc;
+            out_base += views[i].n_cc;
+        }
+        plan.n_out = out_base;
+        *n_out_total = out_base;
+        if (plan.tasks.empty()) return PF_OK;
+
+        // levels: 0 = leaf caching, up band [1, 1 + max_up), down band starts at 1 + max_up
+        n_levels = 1;
+        for (auto &t : plan.tasks) {
+            if (t.level == -1) t.level = 1 + max_up;
+            else if (t.level <= -2) t.level = 1 + max_up + (-t.level - 2);
+            n_levels = std::max(n_levels, t.level + 1);
+        }
+        plan.n_levels = n_levels;
+        G = (int)plan.groups.size();
+        if (G > 65535) return fail(PF_EINVAL, "too many task groups (%d)", G);
+        if (pass == 0) {
+            int heavy = 0, biggest = 0, emis_bytes = 0;
+            for (auto &sg : plan.groups) { biggest = std::max(biggest, sg.task_end); emis_bytes = std::max(emis_bytes, sg.emis_bytes); }   // task_end counts the group's tasks here
+            for (auto &sg : plan.groups) if (sg.task_end >= 48 && 4 * sg.task_end >= biggest) heavy++;
+            // with large genotype tiles (soft calls: 192+ B per individual) half the shared memory
+            // leaves too few message rows: measured on config D the small shape LOSES 17 %, on
+            // config C (hard calls, 8 B per individual) it wins 21 %
+            if ((long long)heavy * n_tiles > sm_count && emis_bytes <= 16 * 1024) { throughput_shape = true; continue; }
+        }
+
+        // counting sort by (group, level); groups own contiguous task ranges in emission order already
+        level_off.assign((size_t)G * (n_levels + 1) + 1, 0);
+        for (auto &t : plan.tasks) level_off[(size_t)t.group * (n_levels + 1) + t.level + 1]++;
+        start.assign((size_t)G * n_levels, 0);
+        {
+            int base = 0;
+            for (int g = 0; g < G; g++) {
+                int *lo = &level_off[(size_t)g * (n_levels + 1)];
+                int run = base;
+                for (int l = 0; l < n_levels; l++) { const int c = lo[l + 1]; start[(size_t)g * n_levels + l] = run; lo[l] = run; run += c; }
+                lo[n_levels] = run;
+                plan.groups[g].task_begin = base;
+                plan.groups[g].task_end = run;
+                base = run;
+            }
+        }
+        // shared-memory budget per group: stage the plan slice if it is small, then as many transient
+        // rows as fit; the launch uses the largest layout
+        smem_bytes = 0; scratch_rows = 0; all_staged = true;
+        for (int g = 0; g < G; g++) {
+            const int slice0 = (plan.groups[g].task_end - plan.groups[g].task_begin) * 8 + plan.groups[g].pool_len * 4 + plan.groups[g].emis_count * (int)sizeof(EmisEnt);
+            if (slice0 > shape.plan_smem_max) all_staged = false;
+        }
+        for (int g = 0; g < G; g++) {
+            SweepGroup &sg = plan.groups[g];
+            sg.staged = all_staged ? 1 : 0;
+            sg.n_rows_smem = 0;
+            const SweepSmem L0 = sweep_smem_layout(sg, n_levels);
+            if (L0.total > shape.smem_max) return fail(PF_EINVAL, "sweep plan too deep for shared memory (%d levels)", n_levels);
+            sg.n_rows_smem = std::min(sg.n_rows, (shape.smem_max - L0.total) / SMEM_ROW_BYTES);
+            sg.scratch_base = scratch_rows;
+            scratch_rows += sg.n_rows;
+            smem_bytes = std::max(smem_bytes, sweep_smem_layout(sg, n_levels).total);
+        }
+        break;
     }
     // tag the transient rows that live in shared memory (row_ref_pos is sorted; groups own
     // consecutive pool slices)
@@ -904,7 +927,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         memcpy(e->last_plan, st, sizeof st);
     }
     e->prof_begin(0);
-    launch_sweep(P, n_tiles, smem_bytes, all_staged, e->stream);
+    launch_sweep(P, n_tiles, smem_bytes, all_staged, throughput_shape, e->stream);
     e->prof_end();
     e->launches++;
     CU(cudaGetLastError());

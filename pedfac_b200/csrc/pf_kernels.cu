@@ -312,8 +312,8 @@ __device__ __forceinline__ void cp_async8(unsigned smem_dst, const void *gsrc)
 
 // STAGED: every group's plan slice lives in shared memory (the normal case); otherwise plans are
 // read from global memory. Two instantiations keep every pointer in a known address space.
-template <bool STAGED>
-__global__ void __launch_bounds__(SWEEP_WARPS * 32, 1) sweep_kernel(const __grid_constant__ SweepParams P)
+template <bool STAGED, int SWEEP_WARPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(SWEEP_WARPS * 32, MIN_BLOCKS) sweep_kernel(const __grid_constant__ SweepParams P)
 {
     extern __shared__ __align__(16) char smem[];
     const DevView &D = P.D;
@@ -407,17 +407,25 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, 1) sweep_kernel(const __grid
     }
 }
 
-void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, cudaStream_t st)
+void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, bool throughput_shape, cudaStream_t st)
 {
+    constexpr SweepShape L = SWEEP_LATENCY, T = SWEEP_THROUGHPUT;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_MAX);
-        cudaFuncSetAttribute(sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SWEEP_SMEM_MAX);
+        cudaFuncSetAttribute(sweep_kernel<true, L.warps, L.blocks_per_sm>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_max);
+        cudaFuncSetAttribute(sweep_kernel<false, L.warps, L.blocks_per_sm>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_max);
+        cudaFuncSetAttribute(sweep_kernel<true, T.warps, T.blocks_per_sm>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_max);
+        cudaFuncSetAttribute(sweep_kernel<false, T.warps, T.blocks_per_sm>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_max);
         attr_set = true;
     }
     dim3 grid(n_tiles, P.n_groups);
-    if (staged) sweep_kernel<true><<<grid, SWEEP_WARPS * 32, smem_bytes, st>>>(P);
-    else sweep_kernel<false><<<grid, SWEEP_WARPS * 32, smem_bytes, st>>>(P);
+    if (!throughput_shape) {
+        if (staged) sweep_kernel<true, L.warps, L.blocks_per_sm><<<grid, L.warps * 32, smem_bytes, st>>>(P);
+        else sweep_kernel<false, L.warps, L.blocks_per_sm><<<grid, L.warps * 32, smem_bytes, st>>>(P);
+    } else {
+        if (staged) sweep_kernel<true, T.warps, T.blocks_per_sm><<<grid, T.warps * 32, smem_bytes, st>>>(P);
+        else sweep_kernel<false, T.warps, T.blocks_per_sm><<<grid, T.warps * 32, smem_bytes, st>>>(P);
+    }
 }
 
 // ---- proposal evaluation ---------------------------------------------------------------------

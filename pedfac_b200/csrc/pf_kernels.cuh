@@ -100,14 +100,21 @@ struct SweepParams {
     int clock_group;
 };
 
-constexpr int SWEEP_WARPS = 16;
 constexpr int TILE_LOCI = 32;
 constexpr int SMEM_ROW_BYTES = 3 * TILE_LOCI * 8;
-constexpr int SWEEP_SMEM_MAX = 195 * 1024;       // dynamic shared memory budget of one block: stays under the
-                                                 // 196 KB carve-out so that 32 KB of L1 remain
-constexpr int SWEEP_PLAN_SMEM_MAX = 56 * 1024;   // larger plan slices are read from global memory
-constexpr int SWEEP_EMIS_SMEM_MAX = 72 * 1024;
-constexpr int SWEEP_LEAF_ROW_BUDGET = 160;       // transient rows per group below which leaves get a cached row
+
+// The sweep kernel is built in two shapes. A block is latency-bound (its levels are a chain of
+// single-warp tasks), so what matters is how many blocks an SM can overlap:
+//   latency shape    16 warps, 1 block per SM, 195 KB of shared memory: the fastest single block;
+//                    used while the launch's heavy blocks fit on the SMs in one wave (a Gibbs-step
+//                    sweep of a 2 000-locus shard)
+//   throughput shape  8 warps, 2 blocks per SM, 98 KB each: a block is ~1.4x slower (more message
+//                    rows spill to L2, fewer warps for the wide levels) but two run side by side;
+//                    used when there are more heavy blocks than SMs (10 000 loci, many chains)
+// The budgets keep the total under the 196 KB carve-out so that 32 KB of L1 remain.
+struct SweepShape { int warps, blocks_per_sm, smem_max, plan_smem_max, emis_smem_max, leaf_row_budget; };
+constexpr SweepShape SWEEP_LATENCY{16, 1, 195 * 1024, 56 * 1024, 72 * 1024, 160};
+constexpr SweepShape SWEEP_THROUGHPUT{8, 2, 98 * 1024, 28 * 1024, 36 * 1024, 64};
 
 // staged bytes of one individual's 32-locus genotype tile
 __host__ __device__ inline int emis_tile_bytes(unsigned kind)
@@ -164,7 +171,7 @@ struct ReduceParams {
     int n_parts, n;
 };
 
-void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, cudaStream_t st);
+void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, bool throughput_shape, cudaStream_t st);
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st);
 int eval_resident_blocks();
 void launch_reduce(const ReduceParams &P, cudaStream_t st);
