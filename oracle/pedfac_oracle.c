@@ -194,7 +194,7 @@ int pfo_sweep(pfo_engine *e, int32_t chain, const pf_graph_view *v, double *ll_c
     size_t nedges = 0;
     for (int j = 0; j < nM; j++) nedges += 2 + (v->marr_kid_begin[j + 1] - v->marr_kid_begin[j]);
     size_t need = sizeof(double) * T3 * (6 * (size_t)nI) + sizeof(double) * nI
-                + (sizeof(iadj) + 64) * (size_t)(nI + 1) + (sizeof(madj) + 192) * (size_t)(nM + 1)
+                + (sizeof(iadj) + 256) * (size_t)(nI + 1) + (sizeof(madj) + 256) * (size_t)(nM + 1)
                 + (sizeof(int) * 2 + 2) * (nedges + 16) + 4096;
     if (need > e->arena_cap) {
         free(e->arena);
@@ -219,6 +219,7 @@ int pfo_sweep(pfo_engine *e, int32_t chain, const pf_graph_view *v, double *ll_c
             for (int i = 0; i < nI; i++) {
                 ia[i].mar = arena_get(e, sizeof(int) * (ia[i].nM + 1));
                 ia[i].edge = arena_get(e, sizeof(int) * (ia[i].nM + 1));
+                if (!ia[i].mar || !ia[i].edge) { rc = PF_ENOMEM; snprintf(g_err, sizeof g_err, "arena too small"); goto done_reset; }
                 ia[i].nM = 0;
             }
         }
@@ -251,6 +252,7 @@ int pfo_sweep(pfo_engine *e, int32_t chain, const pf_graph_view *v, double *ll_c
             ma[j].in = e->m_in[slot]; ma[j].out = e->m_out[slot];
         }
         ma[j].passIn = arena_get(e, ne); ma[j].passOut = arena_get(e, ne);   /* _ResetMsg@0x10001c210 */
+        if (!ma[j].passIn || !ma[j].passOut) { rc = PF_ENOMEM; snprintf(g_err, sizeof g_err, "arena too small"); goto done_reset; }
         memset(ma[j].passIn, 0, ne); memset(ma[j].passOut, 0, ne);
     }
     double *pOut = arena_get(e, sizeof(double) * T3 * nI);   /* pnode->out */

@@ -146,3 +146,15 @@ def test_oracle_prefilter_orders_by_score():
         allv.sort(key=lambda t: (-t[0], t[1]))
         np.testing.assert_array_equal(slots[k], [c for _, c in allv[:5]])
         np.testing.assert_allclose(scores[k], [v for v, _ in allv[:5]], rtol=1e-14)
+
+
+def test_many_individuals_few_loci():
+    """The per-sweep arena must be sized by the pedigree as well as by the loci (a 5000-individual
+    sweep over 16 loci once ran out of adjacency space and crashed)."""
+    rng = np.random.default_rng(77)
+    sc = random_forest(rng, 400, 2, n_marr_target=150, max_kids=5, kinds=("hard", "none"), max_comp=60)
+    eng = OracleEngine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(eng)
+    view, glob = sc.ped.view()
+    ll = eng.sweep(view)
+    assert np.isfinite(ll).all() and len(ll) == len(glob)
