@@ -105,7 +105,7 @@ struct pf_engine {
     std::vector<SoftChunk> soft_chunks;
     std::vector<double> h_eps;            // local shard, for validation only
 
-    DevBuf scratch, plan, partial, result, counters, clockbuf;
+    DevBuf scratch, plan, partial, result, counters, clockbuf, sweep_counter;
     Staging staging;
     double *h_result = nullptr; size_t h_result_cap = 0;
 
@@ -144,7 +144,7 @@ extern "C" int pf_destroy(pf_engine *e)
     cudaFree(e->d_rows); cudaFree(e->d_eps); cudaFree(e->d_hard);
     cudaFree(e->d_kind); cudaFree(e->d_eptr); cudaFree(e->d_denom);
     for (auto &c : e->soft_chunks) cudaFree(c.base);
-    e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release(); e->counters.release();
+    e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release(); e->counters.release(); e->sweep_counter.release();
     e->staging.release();
     if (e->h_result) cudaFreeHost(e->h_result);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -912,6 +912,14 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     P.partial = static_cast<double *>(e->partial.p);
     P.n_out = plan.n_out;
     P.clocks = nullptr; P.clock_group = 0;
+    // few outputs: the sweep's last block reduces them itself; many (wide sweeps): separate launch
+    const bool fused_reduce = plan.n_out > 0 && plan.n_out <= 256;
+    if (e->sweep_counter.cap == 0) {
+        CU(e->sweep_counter.reserve(256));
+        CU(cudaMemsetAsync(e->sweep_counter.p, 0, e->sweep_counter.cap, e->stream));
+    }
+    P.out = fused_reduce ? out_dev : nullptr;
+    P.counter = static_cast<unsigned *>(e->sweep_counter.p);
     if (getenv("PF_SWEEP_CLOCKS")) {
         // measurement aid: per-level clocks of the largest group, printed after the launch
         CU(e->clockbuf.reserve((size_t)(n_levels + 2) * sizeof(long long)));
@@ -940,7 +948,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         for (int l = 0; l < n_levels; l++) fprintf(stderr, " %d:%lld", lo[l + 1] - lo[l], hc[l + 1] - hc[l]);
         fprintf(stderr, "\n");
     }
-    if (plan.n_out > 0) {
+    if (plan.n_out > 0 && !fused_reduce) {
         ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_tiles, plan.n_out};
         e->prof_begin(2);
         launch_reduce(R, e->stream);

@@ -150,7 +150,7 @@ __device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &
         LogProd z; lp_init(z);
         if (C.s < C.Sl) lp_mul(z, (v.x + v.y) + v.z);
         z = lp_warp_reduce(z);
-        if (C.lane == 0) P.partial[(size_t)C.tile * P.n_out + t[2]] = lp_log(z);
+        if (C.lane == 0) { P.partial[(size_t)C.tile * P.n_out + t[2]] = lp_log(z); __threadfence(); }
     }
 }
 
@@ -404,6 +404,32 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, MIN_BLOCKS) sweep_kernel(con
         }
         if (lev + 1 < P.n_levels) __syncthreads();
         if (clk) P.clocks[lev + 1] = clock64();
+    }
+    // fused fixed-order reduction of the per-tile log Z sums (Gibbs-step sweeps have a handful of
+    // outputs; a separate launch cost ~6 us): the last block of the grid to finish adds the tiles
+    // exactly as reduce_kernel does — lanes take tiles lane, lane+32, ..., then an xor butterfly
+    if (P.out != nullptr) {
+        __shared__ bool s_last;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned done = atomicAdd(P.counter, 1u);
+            s_last = done == gridDim.x * gridDim.y - 1;
+            if (s_last) *P.counter = 0;             // ready for the next launch
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            const int n_parts = gridDim.x;
+            for (int i = warp; i < P.n_out; i += SWEEP_WARPS) {
+                double acc = 0.0;
+#pragma unroll 4
+                for (int c = lane; c < n_parts; c += 32) acc += __ldcg(P.partial + (size_t)c * P.n_out + i);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) P.out[i] = acc;
+            }
+        }
     }
 }
 

@@ -98,6 +98,8 @@ struct SweepParams {
     int n_out;
     long long *clocks;      // measurement aid: per-level clock64() of block (0, largest group), or null
     int clock_group;
+    double *out;            // fused reduction (small n_out): the last block to finish adds the tiles, else null
+    unsigned *counter;      // arrival counter of the fused reduction (zero between launches)
 };
 
 constexpr int TILE_LOCI = 32;
