@@ -125,6 +125,13 @@ int pf_sweep(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_
 int pf_eval(pf_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_proposal *props,
             double *lsum);
 
+/* pf_sweep followed by pf_eval in one submission with a single host wait: what a Gibbs step does
+ * first (_Propagating_msg@0x10001ba10 after _PruneIndiv, then the single-parent proposals of
+ * _EvalMoves@0x100015010, whose enumeration depends on the graph only). Same results as the two
+ * calls; n may be 0. */
+int pf_sweep_eval(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc,
+                  int32_t kid, int32_t n, const pf_proposal *props, double *lsum);
+
 /* Same as pf_sweep / pf_eval but results stay on the device (ll_cc_dev / lsum_dev are device
  * pointers, written on the engine's stream, no host synchronisation): the form used when an
  * NCCL all-reduce over locus shards follows. */

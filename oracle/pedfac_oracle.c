@@ -545,6 +545,14 @@ int pfo_eval(pfo_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_prop
  * sort descending (_compareLLonGC), keep top_k. The age-window test is the caller's (it chooses
  * the candidate set); the -LLcc terms of @0x10001f183-0x10001f241 arrive as cand_bias.
  * Ties: earlier candidate first. */
+int pfo_sweep_eval(pfo_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc,
+                   int32_t kid, int32_t n, const pf_proposal *props, double *lsum)
+{
+    int rc = pfo_sweep(e, chain, view, ll_cc);
+    if (rc != PF_OK || n == 0) return rc;
+    return pfo_eval(e, chain, kid, n, props, lsum);
+}
+
 /* ---------------------------------------------------------------------------------------- */
 /* Swap proposals: _ProposeSwapping@0x1000223d0 and its helpers, on the per-edge messages the
  * last sweep left on the marriages (mnode->in / mnode->out).                                 */

@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "eval_swaps", "eval_swaps_dev", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
+    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -88,6 +88,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("eval_batch", C.c_int, vp, C.c_int32, _i32p, _i32p, _i32p, vp, _f64p)
     sig("sweep_batch_dev", C.c_int, vp, C.c_int32, _i32p, C.POINTER(PfGraphView), vp)
     sig("eval_batch_dev", C.c_int, vp, C.c_int32, _i32p, _i32p, _i32p, vp, vp)
+    sig("sweep_eval", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), _f64p, C.c_int32, C.c_int32, vp, _f64p)
     sig("eval_swaps", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), C.c_int32, vp, _f64p)
     sig("eval_swaps_dev", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), C.c_int32, vp, vp)
     sig("prefilter", C.c_int, vp, C.c_int32, C.c_int32, _i32p, _u8p, C.c_int32, _i32p, _f64p,
@@ -251,6 +252,15 @@ class CEngine:
         out = np.empty(max(len(props), 1), dtype=np.float64)
         self._check(self._fn("eval")(self._h, chain, kid, len(props), C.c_void_p(props.ctypes.data), ptr(out, _f64p)))
         return out[:len(props)]
+
+    def sweep_eval(self, view: GraphView, kid: int, props, chain: int = 0):
+        """`pf_sweep_eval`: (ll_cc, lsum) of a sweep and an eval submitted together."""
+        props = make_proposals(props)
+        ll = np.empty(max(view.n_cc, 1), dtype=np.float64)
+        out = np.empty(max(len(props), 1), dtype=np.float64)
+        self._check(self._fn("sweep_eval")(self._h, chain, C.byref(view.struct), ptr(ll, _f64p), kid, len(props),
+                                           C.c_void_p(props.ctypes.data), ptr(out, _f64p)))
+        return ll[:view.n_cc], out[:len(props)]
 
     def eval_swaps(self, view: GraphView, swaps, chain: int = 0) -> np.ndarray:
         swaps = make_swaps(swaps)

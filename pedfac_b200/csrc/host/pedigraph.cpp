@@ -472,26 +472,38 @@ static void build_view(Ped &p, const std::vector<char> &want, ViewBuf &b)
     v.n_cc = (int)b.labels.size();
 }
 
+// the dirty components as a view (all of them when everything is dirty)
+static void dirty_view(Ped &p, ViewBuf &b)
+{
+    const bool all = p.nDirty == p.nCC;
+    std::vector<char> want(p.nCC, 0);
+    for (int c = 0; c < p.nCC; c++) want[c] = all || p.ccDirty[c];
+    build_view(p, want, b);
+}
+
+// store the component log-likelihoods a sweep returned and recompute the total
+// (_UpdateProb@0x10001dd0c-0x10001dd65)
+static void store_sweep(Ped &p, const ViewBuf &b, const std::vector<double> &ll)
+{
+    p.n_sweeps++;
+    for (size_t j = 0; j < b.labels.size(); j++) p.LLcc[b.labels[j]] = ll[j];
+    p.LLtot = 0;
+    for (int c = 0; c < p.nCC; c++) p.LLtot = p.LLcc[c] + p.LLtot;
+    std::fill(p.ccDirty.begin(), p.ccDirty.begin() + std::max(p.nCC, 0), 0);
+    p.nDirty = 0;
+}
+
 static void Propagating_msg(Ped &p)
 {
     if (p.nDirty == 0) return;     // the reference re-propagates everything; nothing would change
     const double t0 = now_s();
-    const bool all = p.nDirty == p.nCC;
-    std::vector<char> want(p.nCC, 0);
-    for (int c = 0; c < p.nCC; c++) want[c] = all || p.ccDirty[c];
     ViewBuf b;
-    build_view(p, want, b);
-    const std::vector<int> &labels = b.labels;
-    std::vector<double> ll(labels.size() + 1);
+    dirty_view(p, b);
+    std::vector<double> ll(b.labels.size() + 1);
     const double t1 = now_s();
     if (PFN(sweep)(p.eng, 0, &b.v, ll.data()) != PF_OK) die("sweep failed");
     p.t_view += t1 - t0; p.t_sweep += now_s() - t1;
-    p.n_sweeps++;
-    for (size_t j = 0; j < labels.size(); j++) p.LLcc[labels[j]] = ll[j];
-    p.LLtot = 0;                                               // _UpdateProb@0x10001dd0c-0x10001dd65
-    for (int c = 0; c < p.nCC; c++) p.LLtot = p.LLcc[c] + p.LLtot;
-    std::fill(p.ccDirty.begin(), p.ccDirty.begin() + std::max(p.nCC, 0), 0);
-    p.nDirty = 0;
+    store_sweep(p, b, ll);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -521,6 +533,24 @@ static void flush(Ped &p, int kid, Batch &b)
     const double t0 = now_s();
     if (PFN(eval)(p.eng, 0, kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("eval failed");
     p.t_eval += now_s() - t0;
+    p.n_proposals += (long)b.props.size();
+    for (size_t k = 0; k < b.props.size(); k++) p.chll[b.slot[k]] = compose(p, kid, b.props[k], lsum[k]);
+    b.props.clear(); b.slot.clear();
+}
+
+// The pending sweep (_Propagating_msg after _PruneIndiv) and the first batch of proposals of the
+// same Gibbs step in one engine submission: the proposal list depends on the graph only.
+static void sweep_and_flush(Ped &p, int kid, Batch &b)
+{
+    if (p.nDirty == 0) { flush(p, kid, b); return; }
+    const double t0 = now_s();
+    ViewBuf vb;
+    dirty_view(p, vb);
+    std::vector<double> ll(vb.labels.size() + 1), lsum(b.props.size() + 1);
+    const double t1 = now_s();
+    if (PFN(sweep_eval)(p.eng, 0, &vb.v, ll.data(), kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("sweep_eval failed");
+    p.t_view += t1 - t0; p.t_sweep += now_s() - t1;
+    store_sweep(p, vb, ll);
     p.n_proposals += (long)b.props.size();
     for (size_t k = 0; k < b.props.size(); k++) p.chll[b.slot[k]] = compose(p, kid, b.props[k], lsum[k]);
     b.props.clear(); b.slot.clear();
@@ -657,7 +687,7 @@ static void EvalMoves(Ped &p, const Opts &o, int kid)
     }
     if (redPa) p.indivActive[ppa] = 1;
     if (redMa) p.indivActive[pma] = 1;
-    flush(p, kid, b);                                          // single-parent scores are needed for the top-10 cut
+    sweep_and_flush(p, kid, b);                                // single-parent scores are needed for the top-10 cut
     for (int s = 0; s < 3; s++) {
         p.cand[s].clear();
         for (auto &cs : cand_slot[s]) p.cand[s].push_back({cs.first, p.chll[cs.second]});
@@ -966,8 +996,7 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
     p.t++;
     p.n_steps++;
     PruneIndiv(p, id);
-    Propagating_msg(p);
-    EvalMoves(p, o, id);
+    EvalMoves(p, o, id);                                       // runs the pending sweep together with its first batch
     p.t++;
     if (p.check) p.chll_data = p.chll;
     AddObsFracPrior(p, id);

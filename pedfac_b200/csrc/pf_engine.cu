@@ -88,6 +88,7 @@ struct SoftChunk { char *base; size_t cap, used; };
 } // namespace
 
 struct pf_engine {
+    bool no_mailbox = false;          // PEDFAC_NO_MAILBOX=1 or no mapped memory: results by copy + stream synchronise
     int sm_count = 0;
     int eval_capacity = 0;            // resident eval_kernel blocks on this device
     pf_config cfg;
@@ -108,6 +109,9 @@ struct pf_engine {
     DevBuf scratch, plan, partial, result, counters, clockbuf, sweep_counter;
     Staging staging;
     double *h_result = nullptr; size_t h_result_cap = 0;
+    // mapped pinned mailbox for small results: [0] = sequence flag, [8..] = values (see publish_kernel)
+    static constexpr int MAILBOX_MAX = 4096;
+    unsigned long long *h_mail = nullptr, *d_mail = nullptr, mail_seq = 0;
 
     std::vector<int> loc;                 // slot -> index in the view being planned
     int64_t launches = 0;
@@ -147,6 +151,7 @@ extern "C" int pf_destroy(pf_engine *e)
     e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release(); e->counters.release(); e->sweep_counter.release();
     e->staging.release();
     if (e->h_result) cudaFreeHost(e->h_result);
+    if (e->h_mail) cudaFreeHost(e->h_mail);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return PF_OK;
@@ -205,6 +210,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->soft_kind_of_row.assign(cfg->cap_indiv, EMIS_NONE);
     e->h_eps.assign(e->Sl, 0.0);
     e->loc.assign(cfg->cap_indiv, -1);
+    e->no_mailbox = getenv("PEDFAC_NO_MAILBOX") != nullptr;
     *out = e;
     return PF_OK;
 }
@@ -959,11 +965,48 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     return PF_OK;
 }
 
-static int fetch_result(pf_engine *e, double *host_out, int n)
+static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2 = nullptr, int n2 = 0)
 {
+    const int n1 = n;
+    n += n2;
     if (n <= 0) { CU(cudaStreamSynchronize(e->stream)); return PF_OK; }
+    if (n <= pf_engine::MAILBOX_MAX && !e->no_mailbox) {
+        if (!e->h_mail) {
+            void *hp = nullptr, *dp = nullptr;
+            if (cudaHostAlloc(&hp, (size_t)(pf_engine::MAILBOX_MAX + 8) * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+                cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) {
+                cudaGetLastError();
+                if (hp) cudaFreeHost(hp);
+                e->no_mailbox = true;
+            } else {
+                e->h_mail = static_cast<unsigned long long *>(hp); e->d_mail = static_cast<unsigned long long *>(dp);
+                e->h_mail[0] = 0;
+            }
+        }
+        if (e->h_mail) {
+            const unsigned long long seq = ++e->mail_seq;
+            launch_publish(static_cast<const double *>(e->result.p), reinterpret_cast<double *>(e->d_mail + 8), n, e->d_mail, seq, e->stream);
+            e->launches++;
+            CU(cudaGetLastError());
+            volatile unsigned long long *flag = e->h_mail;
+            for (unsigned spins = 1; *flag != seq; spins++) {
+                __builtin_ia32_pause();
+                if ((spins & 0x3fff) == 0) {                 // a faulting kernel never raises the flag
+                    const cudaError_t q = cudaStreamQuery(e->stream);
+                    if (q != cudaSuccess && q != cudaErrorNotReady) return fail(PF_ECUDA, "CUDA error while waiting for results: %s", cudaGetErrorString(q));
+                    if (q == cudaSuccess && *flag != seq) { CU(cudaStreamSynchronize(e->stream)); break; }
+                }
+            }
+            __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            const double *vals = reinterpret_cast<const double *>(e->h_mail + 8);
+            if (n1 > 0) memcpy(host_out, vals, (size_t)n1 * sizeof(double));
+            if (n2 > 0) memcpy(host_out2, vals + n1, (size_t)n2 * sizeof(double));
+            return PF_OK;
+        }
+    }
     if ((size_t)n * sizeof(double) > e->h_result_cap) {
         if (e->h_result) cudaFreeHost(e->h_result);
+    if (e->h_mail) cudaFreeHost(e->h_mail);
         e->h_result = nullptr; e->h_result_cap = 0;
         const size_t want = (size_t)n * sizeof(double) * 2 + 4096;
         CU(cudaMallocHost(&e->h_result, want));
@@ -971,7 +1014,8 @@ static int fetch_result(pf_engine *e, double *host_out, int n)
     }
     CU(cudaMemcpyAsync(e->h_result, e->result.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    memcpy(host_out, e->h_result, (size_t)n * sizeof(double));
+    if (n1 > 0) memcpy(host_out, e->h_result, (size_t)n1 * sizeof(double));
+    if (n2 > 0) memcpy(host_out2, e->h_result + n1, (size_t)n2 * sizeof(double));
     return PF_OK;
 }
 
@@ -1012,6 +1056,32 @@ extern "C" int pf_sweep_dev(pf_engine *e, int32_t chain, const pf_graph_view *vi
     if (!e || !view) return fail(PF_EINVAL, "null argument");
     int n_out = 0;
     return run_sweeps(e, 1, &chain, view, ll_cc_dev, &n_out);
+}
+
+// forward: defined with the proposal evaluation below
+static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *kids, const int32_t *prop_begin,
+                     const pf_proposal *props, double *out_dev);
+
+// One Gibbs step's first round trip in a single submission: the sweep of the dirty components and
+// the evaluation of the focal individual's single-parent proposals are enqueued back to back and
+// the host waits once (the proposal list depends on the graph only, not on the sweep's results).
+extern "C" int pf_sweep_eval(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc,
+                             int32_t kid, int32_t n, const pf_proposal *props, double *lsum)
+{
+    if (!e || !view || n < 0) return fail(PF_EINVAL, "null argument");
+    if ((view->n_cc > 0 && !ll_cc) || (n > 0 && (!props || !lsum))) return fail(PF_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    const int n_cc = std::max(view->n_cc, 0);
+    CU(e->result.reserve((size_t)std::max(n_cc + n, 1) * sizeof(double)));
+    int n_out = 0;
+    int rc = run_sweeps(e, 1, &chain, view, static_cast<double *>(e->result.p), &n_out);
+    if (rc) return rc;
+    if (n > 0) {
+        const int32_t pb[2] = {0, n};
+        rc = run_evals(e, 1, &chain, &kid, pb, props, static_cast<double *>(e->result.p) + n_out);
+        if (rc) return rc;
+    }
+    return fetch_result(e, ll_cc, n_out, lsum, n);
 }
 
 // ---------------------------------------------------------------------------------------------

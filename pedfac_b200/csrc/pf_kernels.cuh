@@ -177,5 +177,6 @@ void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st);
 int eval_resident_blocks();
 void launch_reduce(const ReduceParams &P, cudaStream_t st);
+void launch_publish(const double *src, double *dst_mapped, int n, unsigned long long *flag_mapped, unsigned long long seq, cudaStream_t st);
 
 } // namespace pf

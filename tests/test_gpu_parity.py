@@ -306,3 +306,29 @@ def test_gpu_full_size_properties(name, n, S, soft):
     np.testing.assert_allclose(gsub.sweep(vs), o.sweep(vs), rtol=1e-12)
     for x in vs.indiv[:10]:
         np.testing.assert_allclose(gsub.get_stub(int(x)), o.get_stub(int(x)), rtol=1e-12)
+
+
+def test_gpu_sweep_eval_equals_sweep_then_eval():
+    """pf_sweep_eval (one submission, one host wait) returns exactly what pf_sweep followed by
+    pf_eval returns, and agrees with the oracle."""
+    rng = np.random.default_rng(4242)
+    sc = random_forest(rng, n_indiv=150, S=97, max_kids=5, max_comp=40)
+    g = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    o = OracleEngine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(g); sc.upload(o)
+    labels, _ = sc.ped.components()
+    view, glob = sc.ped.view(labels)
+    has_parents = {k for mm in sc.ped.marriages.values() for k in mm.kids}
+    kid = next(int(i) for i in np.flatnonzero(sc.ped.active) if int(i) not in has_parents)
+    others = [int(i) for i in np.flatnonzero(sc.ped.active) if labels[i] != labels[kid]]
+    props = [(PF_PROP_TRIO, -1, -1, -1)] + [(PF_PROP_TRIO, c, -1, -1) for c in others[:37]] + [(PF_PROP_SELFING, others[0], -1, -1)]
+    ll1 = g.sweep(view); l1 = g.eval(kid, props)
+    ll2, l2 = g.sweep_eval(view, kid, props)
+    np.testing.assert_array_equal(ll1, ll2)
+    np.testing.assert_array_equal(l1, l2)
+    ll3, l3 = o.sweep_eval(view, kid, props)
+    np.testing.assert_allclose(ll2, ll3, rtol=1e-12, atol=1e-11)
+    np.testing.assert_allclose(l2, l3, rtol=1e-12, atol=1e-11)
+    ll4, l4 = g.sweep_eval(view, kid, [])
+    np.testing.assert_array_equal(ll4, ll1)
+    assert len(l4) == 0
