@@ -47,6 +47,56 @@ __device__ __forceinline__ void st_row(const SweepCtx &C, int ref, Tri v)
     p[0] = v.x; p[C.Sp] = v.y; p[2 * C.Sp] = v.z;
 }
 
+// Specialised accessors (fewer tests on the task's critical path than the generic pair above):
+// persistent rows (stubs, prongs) are only ever stored; transient rows are in shared memory or
+// spilled to the scratch array, never persistent.
+__device__ __forceinline__ void st_persist(const SweepCtx &C, int row, Tri v)
+{
+    double *p = C.rows_lane + (size_t)row * 3 * C.Sp;
+    p[0] = v.x; p[C.Sp] = v.y; p[2 * C.Sp] = v.z;
+}
+__device__ __forceinline__ Tri ld_t(const SweepCtx &C, int ref)
+{
+    const int idx = ref & (SMEM_ROW_BIT - 1);
+    if (ref & SMEM_ROW_BIT) {
+        const double *p = C.smem_lane + idx * (3 * TILE_LOCI);
+        return Tri{p[0], p[TILE_LOCI], p[2 * TILE_LOCI]};
+    }
+    const double *p = C.scratch_lane + (size_t)idx * 3 * C.Sp;
+    return Tri{p[0], p[C.Sp], p[2 * C.Sp]};
+}
+__device__ __forceinline__ void st_t(const SweepCtx &C, int ref, Tri v)
+{
+    const int idx = ref & (SMEM_ROW_BIT - 1);
+    if (ref & SMEM_ROW_BIT) {
+        double *p = C.smem_lane + idx * (3 * TILE_LOCI);
+        p[0] = v.x; p[TILE_LOCI] = v.y; p[2 * TILE_LOCI] = v.z;
+        return;
+    }
+    double *p = C.scratch_lane + (size_t)idx * 3 * C.Sp;
+    p[0] = v.x; p[C.Sp] = v.y; p[2 * C.Sp] = v.z;
+}
+// transient row number idx of this group (tasks that walk consecutive rows of a bank)
+__device__ __forceinline__ Tri ld_i(const SweepCtx &C, int idx)
+{
+    if (idx < C.n_rows_smem) {
+        const double *p = C.smem_lane + idx * (3 * TILE_LOCI);
+        return Tri{p[0], p[TILE_LOCI], p[2 * TILE_LOCI]};
+    }
+    const double *p = C.scratch_lane + (size_t)idx * 3 * C.Sp;
+    return Tri{p[0], p[C.Sp], p[2 * C.Sp]};
+}
+__device__ __forceinline__ void st_i(const SweepCtx &C, int idx, Tri v)
+{
+    if (idx < C.n_rows_smem) {
+        double *p = C.smem_lane + idx * (3 * TILE_LOCI);
+        p[0] = v.x; p[TILE_LOCI] = v.y; p[2 * TILE_LOCI] = v.z;
+        return;
+    }
+    double *p = C.scratch_lane + (size_t)idx * 3 * C.Sp;
+    p[0] = v.x; p[C.Sp] = v.y; p[2 * C.Sp] = v.z;
+}
+
 // reference to transient row idx of this group (used when a task walks consecutive scratch rows)
 __device__ __forceinline__ int scratch_ref(const SweepCtx &C, int idx)
 {
@@ -102,7 +152,7 @@ __device__ __forceinline__ Tri local_of(const SweepCtx &C, int member)
 
 __device__ __forceinline__ Tri prod_rows(const SweepCtx &C, const int *rows, int n, Tri acc)
 {
-    for (int j = 0; j < n; j++) acc = mul(acc, ld_row(C, rows[j]));
+    for (int j = 0; j < n; j++) acc = mul(acc, ld_t(C, rows[j]));
     return acc;
 }
 
@@ -139,7 +189,7 @@ __device__ __forceinline__ Tri fam_to_kid(const Sym3 &P, Tri a, Tri b, int selfi
 // up message of a family member: a stored row, or recomputed for a leaf without a cached row
 __device__ __forceinline__ Tri up_msg(const SweepCtx &C, int ref)
 {
-    return ref < 0 ? local_of(C, ref & 0x7fffffff) : ld_row(C, ref);
+    return ref < 0 ? local_of(C, ref & 0x7fffffff) : ld_t(C, ref);
 }
 
 __device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &C, const int *t)
@@ -157,7 +207,7 @@ __device__ __forceinline__ void task_root(const SweepParams &P, const SweepCtx &
 // LEAF_IN: member, up_i_row — decode a leaf's local factor once into its cached row (level 0)
 __device__ __forceinline__ void task_leaf_in(const SweepCtx &C, const int *t)
 {
-    st_row(C, t[1], local_of(C, t[0]));
+    st_t(C, t[1], local_of(C, t[0]));
 }
 
 // product of the kid factors K(up_msg(ref)) of refs[0..n), four at a time so that the twelve
@@ -188,7 +238,7 @@ __device__ __forceinline__ void task_fam_up(const SweepCtx &C, const int *t)
     const int flags = t[0], selfing = flags & 1, urole = flags >> 1, nC = t[2];
     const int *q = t + 3;
     for (int x = 0; x < nC; x++) {
-        st_row(C, q[1], prod_rows(C, q + 3, q[2], local_of(C, q[0])));
+        st_t(C, q[1], prod_rows(C, q + 3, q[2], local_of(C, q[0])));
         q += 3 + q[2];
     }
     const Tri one{1.0, 1.0, 1.0};
@@ -197,14 +247,14 @@ __device__ __forceinline__ void task_fam_up(const SweepCtx &C, const int *t)
     Sym3 P = sym_ones();
     fold_kids(C, P, q + 3, 1, q[2]);
     const Tri out = urole == 0 ? fam_to_pa(P, b, selfing) : urole == 1 ? fam_to_pa(P, a, 0) : fam_to_kid(P, a, b, selfing);
-    st_row(C, t[1], out);
+    st_t(C, t[1], out);
 }
 
 // message + stub of one down member
 __device__ __forceinline__ void put_down(const SweepCtx &C, const int *ent, Tri up, Tri dn)
 {
-    st_row(C, ent[1], mul(up, dn));
-    if (ent[2] >= 0) st_row(C, ent[2], dn);
+    st_persist(C, ent[1], mul(up, dn));
+    if (ent[2] >= 0) st_t(C, ent[2], dn);
 }
 
 // FAM_DOWN: flags, prong_row, u_member, u_dn_row (-1 = root), nSib, sib[nSib],
@@ -215,7 +265,7 @@ __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
 {
     const int flags = t[0], selfing = flags & 1, urole = flags >> 1, nSib = t[4];
     Tri in_u = local_of(C, t[2]);
-    if (t[3] >= 0) in_u = mul(in_u, ld_row(C, t[3]));
+    if (t[3] >= 0) in_u = mul(in_u, ld_t(C, t[3]));
     in_u = prod_rows(C, t + 5, nSib, in_u);
     const int *pa = t + 5 + nSib, *ma = pa + 3;
     const int nk = ma[3];
@@ -236,7 +286,7 @@ __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
         Sym3 Pall = Pu;
 #pragma unroll
         for (int j = 0; j < FAM_SMALL_MAX; j++) if (j < nk) sym_mul(Pall, K[j]);
-        st_row(C, t[1], fam_to_kid(Pall, a, b, selfing));                 // prong
+        st_persist(C, t[1], fam_to_kid(Pall, a, b, selfing));             // prong
         if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(Pall, b, selfing));
         if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(Pall, a, 0));
 #pragma unroll
@@ -253,25 +303,25 @@ __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
     // (exclusive prefix x exclusive suffix over chunks); KID_CHUNK tasks on the next level turn
     // them into the kids' messages in parallel on the block's other warps
     const int base = tmp & (SMEM_ROW_BIT - 1);
-    st_row(C, scratch_ref(C, base), a);
-    st_row(C, scratch_ref(C, base + 1), b);
+    st_i(C, base, a);
+    st_i(C, base + 1, b);
     const int nc = (nk + FAM_CHUNK - 1) / FAM_CHUNK;
     Sym3 run = Pu;
     for (int c = 0; c < nc; c++) {
         const int r = base + 2 + 2 * c;
-        st_row(C, scratch_ref(C, r), Tri{run.a00, run.a01, run.a02});
-        st_row(C, scratch_ref(C, r + 1), Tri{run.a11, run.a12, run.a22});
+        st_i(C, r, Tri{run.a00, run.a01, run.a02});
+        st_i(C, r + 1, Tri{run.a11, run.a12, run.a22});
         fold_kids(C, run, kid + 3 * c * FAM_CHUNK, 3, min(FAM_CHUNK, nk - c * FAM_CHUNK));
     }
-    st_row(C, t[1], fam_to_kid(run, a, b, selfing));                      // prong: run = all kids now
+    st_persist(C, t[1], fam_to_kid(run, a, b, selfing));                  // prong: run = all kids now
     if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(run, b, selfing));
     if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(run, a, 0));
     Sym3 suf = sym_ones();
     for (int c = nc - 1; c >= 0; c--) {
         const int r = base + 2 + 2 * c;
-        const Tri p0 = ld_row(C, scratch_ref(C, r)), p1 = ld_row(C, scratch_ref(C, r + 1));
-        st_row(C, scratch_ref(C, r), Tri{p0.x * suf.a00, p0.y * suf.a01, p0.z * suf.a02});
-        st_row(C, scratch_ref(C, r + 1), Tri{p1.x * suf.a11, p1.y * suf.a12, p1.z * suf.a22});
+        const Tri p0 = ld_i(C, r), p1 = ld_i(C, r + 1);
+        st_i(C, r, Tri{p0.x * suf.a00, p0.y * suf.a01, p0.z * suf.a02});
+        st_i(C, r + 1, Tri{p1.x * suf.a11, p1.y * suf.a12, p1.z * suf.a22});
         if (c > 0) fold_kids(C, suf, kid + 3 * c * FAM_CHUNK, 3, min(FAM_CHUNK, nk - c * FAM_CHUNK));
     }
 }
@@ -282,8 +332,8 @@ __device__ __forceinline__ void task_kid_chunk(const SweepCtx &C, const int *t)
 {
     const int selfing = t[0] & 1, n = t[3];
     const int ab = t[1] & (SMEM_ROW_BIT - 1), orow = t[2] & (SMEM_ROW_BIT - 1);
-    const Tri a = ld_row(C, scratch_ref(C, ab)), b = ld_row(C, scratch_ref(C, ab + 1));
-    const Tri p0 = ld_row(C, scratch_ref(C, orow)), p1 = ld_row(C, scratch_ref(C, orow + 1));
+    const Tri a = ld_i(C, ab), b = ld_i(C, ab + 1);
+    const Tri p0 = ld_i(C, orow), p1 = ld_i(C, orow + 1);
     const Sym3 Pout{p0.x, p0.y, p0.z, p1.x, p1.y, p1.z};
     const int *mem = t + 4;
     Sym3 K[FAM_CHUNK];
