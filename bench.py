@@ -162,6 +162,24 @@ def cpu_count():
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference schedule (test infrastructure used as the timed baseline)
 
+def cpu_sample_loci(data, trace, budget_s, passes):
+    """How many loci the CPU arm can afford: one Gibbs-step pass is timed on 64 loci, then the
+    largest multiple of 64 (at most all loci) whose `passes` full passes fit in `budget_s`."""
+    from oracle.binding import OracleEngine
+    S = data.n_loci
+    S0 = min(S, 64)
+    o = OracleEngine(S, trace.cap_i, trace.cap_m, locus_range=(0, S0))
+    synth.upload(o, data)
+    o.sweep(trace.full_view)
+    t0 = time.perf_counter()
+    k = min(6, len(trace.ref_steps))
+    for view_a, kid, props, view_b in trace.ref_steps[:k]:
+        o.sweep(view_a); o.eval(kid, props); o.sweep(view_b)
+    per_locus_pass = (time.perf_counter() - t0) / k * len(trace.ref_steps) / S0
+    fit = int(budget_s / max(passes, 1) / max(per_locus_pass, 1e-9))
+    return int(min(S, max(64, fit // 64 * 64)))
+
+
 def run_cpu_reference(data, trace, S_sample, budget_s, steps, warmup):
     """Times the reference's own schedule — per Gibbs step: Propagating_msg over the dirty
     components, every proposal re-contracted over all loci, Propagating_msg again — on the first
@@ -296,7 +314,7 @@ def main():
             return 0
         data = synth.simulate(n_ind, S, soft=soft, seed=46)
         trace = Trace(data, args.trace_steps)
-        S_sample = min(S, 256)
+        S_sample = cpu_sample_loci(data, trace, args.cpu_budget * 3, args.steps + args.warmup)
         value, ms, sample = run_cpu_reference(data, trace, S_sample, args.cpu_budget * 3, args.steps, args.warmup)
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
@@ -486,7 +504,7 @@ def main():
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            v, _, sample = run_cpu_reference(data, trace, min(S, 256), args.cpu_budget, 1, 0)
+            v, _, sample = run_cpu_reference(data, trace, cpu_sample_loci(data, trace, args.cpu_budget, 1), args.cpu_budget, 1, 0)
             cpu = {"value": v, "unit": unit, "cores": 1, "kind": "port", "sample": sample, "host_cores_available": cpu_count()}
         out = {
             "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
