@@ -415,7 +415,8 @@ struct ViewWork {           // scratch vectors reused across calls
     std::vector<int> Ui, um, urole, depth_m, lvlA;
     std::vector<int> up_i_row, up_m_row, dn_row, in_u_row, emis_idx;
     std::vector<int> bfs_m, queue, cnt_a, cnt_b, cnt_c, tmp_row;
-    std::vector<char> vis_i, vis_m, label_seen;
+    std::vector<char> vis_i, vis_m, label_seen, in_chunk;
+    std::vector<int> it_off, it_cnt, it_type, it_first, it_n, it_kids, it_prow;   // sibship items per marriage (see item_factor)
 };
 
 } // namespace
@@ -478,6 +479,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
 
         w.Ui.assign(nI, -1); w.um.assign(nM, -1); w.urole.assign(nM, 0); w.depth_m.assign(nM, 0);
         w.lvlA.assign(nM, 0); w.vis_i.assign(nI, 0); w.vis_m.assign(nM, 0); w.label_seen.assign(v->n_cc, 0);
+        w.it_off.assign(nM, 0); w.it_cnt.assign(nM, 0); w.it_type.clear(); w.it_first.clear(); w.it_n.clear(); w.it_kids.clear(); w.it_prow.clear(); w.in_chunk.assign(nI, 0);
         w.up_i_row.assign(nI, -1); w.up_m_row.assign(nM, -1); w.in_u_row.assign(nM, -1); w.tmp_row.assign(nM, -1); w.dn_row.assign(nI, -1); w.emis_idx.assign(nI, -1);
         w.bfs_m.clear();
         std::vector<int> roots, comp_members_end;   // BFS order of individuals per component
@@ -605,6 +607,32 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             // and consumed within two consecutive levels of the down band, so every depth reuses
             // the same small bank of rows.
             for (size_t b = mb; b < me; b++) w.up_m_row[w.bfs_m[b]] = SCRATCH_BIT | G.n_rows++;
+            // sibship items of every marriage of the component: down kids that have marriages of
+            // their own are single items, leaf kids are grouped FAM_CHUNK at a time (a left-over
+            // single leaf is a single item)
+            for (size_t b = mb; b < me; b++) {
+                const int m = w.bfs_m[b];
+                w.it_off[m] = (int)w.it_type.size();
+                int run = 0;
+                for (int pass = 0; pass < 2; pass++)
+                    for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                        const int x = w.mem_i[k];
+                        if (x == w.um[m] || w.mem_role[k] != 2) continue;
+                        const bool leaf = w.adj_off[x + 1] - w.adj_off[x] <= 1;
+                        if (pass == 0 && !leaf) { w.it_type.push_back(0); w.it_first.push_back((int)w.it_kids.size()); w.it_n.push_back(1); w.it_prow.push_back(-1); w.it_kids.push_back(k); }
+                        if (pass == 1 && leaf) {
+                            if (run == 0) { w.it_type.push_back(0); w.it_first.push_back((int)w.it_kids.size()); w.it_n.push_back(0); w.it_prow.push_back(-1); }
+                            w.it_kids.push_back(k); w.it_n.back()++;
+                            if (++run == FAM_CHUNK) run = 0;
+                        }
+                    }
+                for (int it = w.it_off[m]; it < (int)w.it_type.size(); it++)
+                    if (w.it_n[it] >= 2) {
+                        w.it_type[it] = 1;
+                        for (int j = 0; j < w.it_n[it]; j++) w.in_chunk[w.mem_i[w.it_kids[w.it_first[it] + j]]] = 1;
+                    }
+                w.it_cnt[m] = (int)w.it_type.size() - w.it_off[m];
+            }
             if (!up_only) {
                 int max_depth = 0;
                 for (size_t b = mb; b < me; b++) max_depth = std::max(max_depth, w.depth_m[w.bfs_m[b]]);
@@ -615,11 +643,10 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 int bank_m = 0, bank_d = 0, bank_t = 0;
                 for (size_t b = mb; b < me; b++) {
                     const int m = w.bfs_m[b], d = w.depth_m[m];
-                    {   // large sibships park their prefix products in 2 scratch rows per down kid
-                        int nk = 0;
-                        for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) if (w.mem_i[k] != w.um[m] && w.mem_role[k] == 2) nk++;
+                    {   // sibships of more than one single kid park a, b and one row pair per item
+                        const int ni = w.it_cnt[m];
                         w.tmp_row[m] = -1;
-                        if (nk > FAM_SMALL_MAX) { w.tmp_row[m] = cnt_t[d]; cnt_t[d] += 2 + 2 * ((nk + FAM_CHUNK - 1) / FAM_CHUNK); bank_t = std::max(bank_t, cnt_t[d]); }
+                        if (ni >= 2 || (ni == 1 && w.it_type[w.it_off[m]] == 1)) { w.tmp_row[m] = cnt_t[d]; cnt_t[d] += 2 + 2 * ni; bank_t = std::max(bank_t, cnt_t[d]); }
                     }
                     for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
                         const int x = w.mem_i[k];
@@ -631,7 +658,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 const int base_m = G.n_rows, base_d = G.n_rows + bank_m, base_t = base_d + bank_d;
                 G.n_rows += bank_m + bank_d + bank_t;
                 (void)base_m;
-                for (size_t b = mb; b < me; b++) if (w.tmp_row[w.bfs_m[b]] >= 0) w.tmp_row[w.bfs_m[b]] = SCRATCH_BIT | (base_t + w.tmp_row[w.bfs_m[b]]);
+                for (size_t b = mb; b < me; b++) if (w.tmp_row[w.bfs_m[b]] >= 0) w.tmp_row[w.bfs_m[b]] += base_t;      // plain row numbers (ld_i / st_i)
                 for (int oi = ib; oi < ie; oi++) {
                     const int i = order_i[oi];
                     if (w.dn_row[i] >= 0) w.dn_row[i] = SCRATCH_BIT | (base_d + w.dn_row[i]);
@@ -649,7 +676,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 const int i = order_i[oi];
                 const bool leaf = w.adj_off[i + 1] - w.adj_off[i] <= 1;
                 bool cached_leaf = false;
-                if (w.Ui[i] >= 0 && leaf && e->h_kind[v->indiv[i]] != EMIS_NONE && G.n_rows < shape.leaf_row_budget) {
+                if (w.Ui[i] >= 0 && leaf && !w.in_chunk[i] && e->h_kind[v->indiv[i]] != EMIS_NONE && G.n_rows < shape.leaf_row_budget) {
                     w.up_i_row[i] = SCRATCH_BIT | G.n_rows++;
                     cached_leaf = true;
                 }
@@ -664,6 +691,13 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 else E.smem_off = EMIS_NOT_STAGED;
                 w.emis_idx[i] = G.emis_count++;
                 plan.emis.push_back(E);
+            }
+            // rows of the chunk products (written by KFOLD at level 0, read by FAM_UP and FAM_DOWN): last,
+            // so that they are the first to spill when shared memory is short
+            for (size_t b = mb; b < me; b++) {
+                const int m = w.bfs_m[b];
+                for (int it = w.it_off[m]; it < w.it_off[m] + w.it_cnt[m]; it++)
+                    if (w.it_type[it] == 1) { w.it_prow[it] = G.n_rows; G.n_rows += 2; }
             }
             // reference to the up message of member x: its row, or (leaf) LEAF_REF_BIT | member
             auto push_up_i = [&](int x, int role) {
@@ -687,6 +721,24 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 add_task(0, TASK_LEAF_IN);
                 pool.push_back(member(i, 0)); push_row(w.up_i_row[i]);
             }
+            // chunk products, also at level 0
+            for (size_t b = mb; b < me; b++) {
+                const int m = w.bfs_m[b];
+                for (int it = w.it_off[m]; it < w.it_off[m] + w.it_cnt[m]; it++) {
+                    if (w.it_type[it] != 1) continue;
+                    add_task(0, TASK_KFOLD);
+                    pool.push_back(w.it_prow[it]); pool.push_back(w.it_n[it]);
+                    for (int j = 0; j < w.it_n[it]; j++) push_up_i(w.mem_i[w.it_kids[w.it_first[it] + j]], 2);
+                }
+            }
+            // the sibship items of marriage m as {type, value} pairs
+            auto push_item_list = [&](int m) {
+                for (int it = w.it_off[m]; it < w.it_off[m] + w.it_cnt[m]; it++) {
+                    pool.push_back(w.it_type[it]);
+                    if (w.it_type[it] == 1) pool.push_back(w.it_prow[it]);
+                    else push_up_i(w.mem_i[w.it_kids[w.it_first[it]]], 2);
+                }
+            };
             for (size_t b = mb; b < me; b++) {
                 const int m = w.bfs_m[b];
                 const int flags = (v->marr_selfing[m] ? 1 : 0) | (w.urole[m] << 1);
@@ -714,9 +766,9 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 }
                 if (pa_k >= 0) push_up_i(w.mem_i[pa_k], 0); else pool.push_back(NO_REF);
                 if (ma_k >= 0) push_up_i(w.mem_i[ma_k], 1); else pool.push_back(NO_REF);
-                pool.push_back(nkid);
-                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
-                    if (w.mem_i[k] != u && w.mem_role[k] == 2) push_up_i(w.mem_i[k], 2);
+                (void)nkid;
+                pool.push_back(w.it_cnt[m]);
+                push_item_list(m);
                 if (up_only) continue;                              // log Z only: no down band
                 add_task(-(2 + 2 * w.depth_m[m]), TASK_FAM_DOWN);
                 pool.push_back(flags); pool.push_back(e->prong_row(chain, v->marr[m]));
@@ -731,29 +783,29 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                     if (w.dn_row[x] < 0) pool.push_back(-1); else push_row(w.dn_row[x]);
                 };
                 down_entry(pa_k); down_entry(ma_k);
-                pool.push_back(nkid);
-                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
-                    if (w.mem_i[k] != u && w.mem_role[k] == 2) down_entry(k);
-                if (w.tmp_row[m] < 0) pool.push_back(-1); else push_row(w.tmp_row[m]);
-                if (w.tmp_row[m] >= 0) {
-                    // KID_CHUNK tasks, one per FAM_CHUNK down kids (member order), on the next level
-                    std::vector<int> kk;
-                    for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++)
-                        if (w.mem_i[k] != u && w.mem_role[k] == 2) kk.push_back(k);
-                    const int tbase = w.tmp_row[m] & ~SCRATCH_BIT;
-                    for (size_t c0 = 0; c0 < kk.size(); c0 += FAM_CHUNK) {
-                        const int cn = (int)std::min<size_t>(FAM_CHUNK, kk.size() - c0);
-                        add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_KID_CHUNK);
-                        pool.push_back(flags);
-                        push_row(SCRATCH_BIT | tbase);
-                        push_row(SCRATCH_BIT | (tbase + 2 + 2 * (int)(c0 / FAM_CHUNK)));
-                        pool.push_back(cn);
-                        for (int j = 0; j < cn; j++) {
-                            const int x = w.mem_i[kk[c0 + j]];
-                            push_up_i(x, 2);
-                            pool.push_back(e->stub_row(chain, v->indiv[x]));
-                            if (w.dn_row[x] < 0) pool.push_back(-1); else push_row(w.dn_row[x]);
-                        }
+                pool.push_back(w.it_cnt[m]);
+                pool.push_back(w.tmp_row[m]);
+                push_item_list(m);
+                if (w.tmp_row[m] < 0) {
+                    if (w.it_cnt[m] == 1) {         // one single kid, finished inside FAM_DOWN: {ref (above), stub_row, dn_row}
+                        const int x = w.mem_i[w.it_kids[w.it_first[w.it_off[m]]]];
+                        pool.push_back(e->stub_row(chain, v->indiv[x]));
+                        if (w.dn_row[x] < 0) pool.push_back(-1); else push_row(w.dn_row[x]);
+                    }
+                    continue;
+                }
+                // one KID_CHUNK task per item on the next level
+                for (int it = w.it_off[m], i = 0; it < w.it_off[m] + w.it_cnt[m]; it++, i++) {
+                    add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_KID_CHUNK);
+                    pool.push_back(flags);
+                    pool.push_back(w.tmp_row[m]);
+                    pool.push_back(w.tmp_row[m] + 2 + 2 * i);
+                    pool.push_back(w.it_n[it]);
+                    for (int j = 0; j < w.it_n[it]; j++) {
+                        const int x = w.mem_i[w.it_kids[w.it_first[it] + j]];
+                        push_up_i(x, 2);
+                        pool.push_back(e->stub_row(chain, v->indiv[x]));
+                        if (w.dn_row[x] < 0) pool.push_back(-1); else push_row(w.dn_row[x]);
                     }
                 }
             }

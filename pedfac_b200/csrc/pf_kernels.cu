@@ -230,7 +230,28 @@ __device__ __forceinline__ void fold_kids(const SweepCtx &C, Sym3 &P, const int 
     for (; j < n; j++) sym_mul(P, kid_matrix(up_msg(C, refs[j * stride])));
 }
 
-// FAM_UP: flags, up_m_row, nC, { member, up_i_row, nD, below[nD] } * nC, pa_ref, ma_ref, nk, kid_ref[nk]
+// A sibship is a list of items {type, value}: type 0 = one kid, value = its up reference (a row, or
+// a leaf to decode); type 1 = a chunk of 2..FAM_CHUNK leaf kids whose factor product a KFOLD task
+// (level 0, in parallel on the block's warps) left in the transient rows value, value + 1. The
+// family tasks then work per item: a sibship of n leaves costs them n / FAM_CHUNK row loads
+// instead of n decodes, and the per-kid work of the down band is done by the KID_CHUNK tasks.
+__device__ __forceinline__ Sym3 item_factor(const SweepCtx &C, const int *it)
+{
+    if (it[0] == 0) return kid_matrix(up_msg(C, it[1]));
+    const Tri lo = ld_i(C, it[1]), hi = ld_i(C, it[1] + 1);
+    return Sym3{lo.x, lo.y, lo.z, hi.x, hi.y, hi.z};
+}
+
+// KFOLD: out_row (2 consecutive transient rows), n, kid_ref[n]
+__device__ __forceinline__ void task_kfold(const SweepCtx &C, const int *t)
+{
+    Sym3 P = sym_ones();
+    fold_kids(C, P, t + 2, 1, t[1]);
+    st_i(C, t[0], Tri{P.a00, P.a01, P.a02});
+    st_i(C, t[0] + 1, Tri{P.a11, P.a12, P.a22});
+}
+
+// FAM_UP: flags, up_m_row, nC, { member, up_i_row, nD, below[nD] } * nC, pa_ref, ma_ref, n_items, item[n_items]
 //   the nC non-leaf down members get their up message computed and stored first; pa_ref / ma_ref
 //   are NO_REF when that parent is the up individual (or the marriage is selfing)
 __device__ __forceinline__ void task_fam_up(const SweepCtx &C, const int *t)
@@ -245,7 +266,8 @@ __device__ __forceinline__ void task_fam_up(const SweepCtx &C, const int *t)
     const Tri a = q[0] == NO_REF ? one : up_msg(C, q[0]);
     const Tri b = q[1] == NO_REF ? one : up_msg(C, q[1]);
     Sym3 P = sym_ones();
-    fold_kids(C, P, q + 3, 1, q[2]);
+    const int n_items = q[2];
+    for (int i = 0; i < n_items; i++) sym_mul(P, item_factor(C, q + 3 + 2 * i));
     const Tri out = urole == 0 ? fam_to_pa(P, b, selfing) : urole == 1 ? fam_to_pa(P, a, 0) : fam_to_kid(P, a, b, selfing);
     st_t(C, t[1], out);
 }
@@ -258,9 +280,11 @@ __device__ __forceinline__ void put_down(const SweepCtx &C, const int *ent, Tri 
 }
 
 // FAM_DOWN: flags, prong_row, u_member, u_dn_row (-1 = root), nSib, sib[nSib],
-//           pa{ref, stub_row, dn_row}, ma{ref, stub_row, dn_row}, nk, kid{ref, stub_row, dn_row} * nk, tmp_row
+//           pa{ref, stub_row, dn_row}, ma{ref, stub_row, dn_row}, n_items, tmp_row, item[n_items]
+//           (+ stub_row, dn_row of the kid when the sibship is one single kid: tmp_row = -1)
 //   pa.ref / ma.ref = NO_REF when that parent is the up individual (or selfing mother);
-//   tmp_row = scratch rows of a large sibship (2 for a, b + 2 per chunk of FAM_CHUNK kids) or -1
+//   tmp_row = first of 2 + 2 * n_items bank rows: a, b, then per item the product of everything
+//   OUTSIDE that item, which the item's KID_CHUNK task on the next level turns into messages
 __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
 {
     const int flags = t[0], selfing = flags & 1, urole = flags >> 1, nSib = t[4];
@@ -268,61 +292,45 @@ __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
     if (t[3] >= 0) in_u = mul(in_u, ld_t(C, t[3]));
     in_u = prod_rows(C, t + 5, nSib, in_u);
     const int *pa = t + 5 + nSib, *ma = pa + 3;
-    const int nk = ma[3];
-    const int *kid = ma + 4;
+    const int n_items = ma[3], tmp = ma[4];
+    const int *item = ma + 5;
     const Tri one{1.0, 1.0, 1.0};
     const Tri a = urole == 0 ? in_u : pa[0] == NO_REF ? one : up_msg(C, pa[0]);
     const Tri b = urole == 1 ? in_u : ma[0] == NO_REF ? one : up_msg(C, ma[0]);
     Sym3 Pu = sym_ones();
     if (urole == 2) sym_mul(Pu, kid_matrix(in_u));
-    const int tmp = kid[3 * nk];
 
     if (tmp < 0) {
-        // small sibship (nk <= FAM_SMALL_MAX): everything from registers
-        Sym3 K[FAM_SMALL_MAX];
-#pragma unroll
-        for (int j = 0; j < FAM_SMALL_MAX; j++)
-            if (j < nk) K[j] = kid_matrix(up_msg(C, kid[3 * j]));
+        // no down kid, or one single kid: finished here
         Sym3 Pall = Pu;
-#pragma unroll
-        for (int j = 0; j < FAM_SMALL_MAX; j++) if (j < nk) sym_mul(Pall, K[j]);
-        st_persist(C, t[1], fam_to_kid(Pall, a, b, selfing));             // prong
+        Tri kmsg = one;
+        if (n_items) { kmsg = up_msg(C, item[1]); sym_mul(Pall, kid_matrix(kmsg)); }
+        st_persist(C, t[1], fam_to_kid(Pall, a, b, selfing));                 // prong
         if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(Pall, b, selfing));
         if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(Pall, a, 0));
-#pragma unroll
-        for (int j = 0; j < FAM_SMALL_MAX; j++) {
-            if (j >= nk) break;
-            Sym3 Pm = Pu;
-#pragma unroll
-            for (int i = 0; i < FAM_SMALL_MAX; i++) if (i != j && i < nk) sym_mul(Pm, K[i]);
-            put_down(C, kid + 3 * j, up_msg(C, kid[3 * j]), fam_to_kid(Pm, a, b, selfing));
-        }
+        if (n_items) put_down(C, item + 1, kmsg, fam_to_kid(Pu, a, b, selfing));   // item + 1 = {ref, stub_row, dn_row}
         return;
     }
-    // large sibship: park a, b and, per chunk, the product of all factors OUTSIDE the chunk
-    // (exclusive prefix x exclusive suffix over chunks); KID_CHUNK tasks on the next level turn
-    // them into the kids' messages in parallel on the block's other warps
-    const int base = tmp & (SMEM_ROW_BIT - 1);
-    st_i(C, base, a);
-    st_i(C, base + 1, b);
-    const int nc = (nk + FAM_CHUNK - 1) / FAM_CHUNK;
+    // park a, b and, per item, the product of all factors outside it (exclusive prefix x suffix)
+    st_i(C, tmp, a);
+    st_i(C, tmp + 1, b);
     Sym3 run = Pu;
-    for (int c = 0; c < nc; c++) {
-        const int r = base + 2 + 2 * c;
+    for (int i = 0; i < n_items; i++) {
+        const int r = tmp + 2 + 2 * i;
         st_i(C, r, Tri{run.a00, run.a01, run.a02});
         st_i(C, r + 1, Tri{run.a11, run.a12, run.a22});
-        fold_kids(C, run, kid + 3 * c * FAM_CHUNK, 3, min(FAM_CHUNK, nk - c * FAM_CHUNK));
+        sym_mul(run, item_factor(C, item + 2 * i));
     }
-    st_persist(C, t[1], fam_to_kid(run, a, b, selfing));                  // prong: run = all kids now
+    st_persist(C, t[1], fam_to_kid(run, a, b, selfing));                      // prong: run = all kids now
     if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(run, b, selfing));
     if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(run, a, 0));
     Sym3 suf = sym_ones();
-    for (int c = nc - 1; c >= 0; c--) {
-        const int r = base + 2 + 2 * c;
+    for (int i = n_items - 1; i >= 0; i--) {
+        const int r = tmp + 2 + 2 * i;
         const Tri p0 = ld_i(C, r), p1 = ld_i(C, r + 1);
         st_i(C, r, Tri{p0.x * suf.a00, p0.y * suf.a01, p0.z * suf.a02});
         st_i(C, r + 1, Tri{p1.x * suf.a11, p1.y * suf.a12, p1.z * suf.a22});
-        if (c > 0) fold_kids(C, suf, kid + 3 * c * FAM_CHUNK, 3, min(FAM_CHUNK, nk - c * FAM_CHUNK));
+        if (i > 0) sym_mul(suf, item_factor(C, item + 2 * i));
     }
 }
 
@@ -331,23 +339,23 @@ __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
 __device__ __forceinline__ void task_kid_chunk(const SweepCtx &C, const int *t)
 {
     const int selfing = t[0] & 1, n = t[3];
-    const int ab = t[1] & (SMEM_ROW_BIT - 1), orow = t[2] & (SMEM_ROW_BIT - 1);
+    const int ab = t[1], orow = t[2];
     const Tri a = ld_i(C, ab), b = ld_i(C, ab + 1);
     const Tri p0 = ld_i(C, orow), p1 = ld_i(C, orow + 1);
     const Sym3 Pout{p0.x, p0.y, p0.z, p1.x, p1.y, p1.z};
     const int *mem = t + 4;
-    Sym3 K[FAM_CHUNK];
+    Tri km[FAM_CHUNK];
 #pragma unroll
     for (int j = 0; j < FAM_CHUNK; j++)
-        if (j < n) K[j] = kid_matrix(up_msg(C, mem[3 * j]));
+        if (j < n) km[j] = up_msg(C, mem[3 * j]);
 #pragma unroll
     for (int j = 0; j < FAM_CHUNK; j++) {
         if (j >= n) break;
         Sym3 Pm = Pout;
 #pragma unroll
         for (int i = 0; i < FAM_CHUNK; i++)
-            if (i != j && i < n) sym_mul(Pm, K[i]);
-        put_down(C, mem + 3 * j, up_msg(C, mem[3 * j]), fam_to_kid(Pm, a, b, selfing));
+            if (i != j && i < n) sym_mul(Pm, kid_matrix(km[i]));
+        put_down(C, mem + 3 * j, km[j], fam_to_kid(Pm, a, b, selfing));
     }
 }
 
@@ -449,7 +457,8 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, MIN_BLOCKS) sweep_kernel(con
             case TASK_LEAF_IN: task_leaf_in(C, t); break;
             case TASK_FAM_UP: task_fam_up(C, t); break;
             case TASK_FAM_DOWN: task_fam_down(C, t); break;
-            default: task_kid_chunk(C, t); break;
+            case TASK_KID_CHUNK: task_kid_chunk(C, t); break;
+            default: task_kfold(C, t); break;
             }
         }
         if (lev + 1 < P.n_levels) __syncthreads();

@@ -46,15 +46,15 @@ namespace pf {
 // member = role | founder << 2 | (group-local genotype entry index) << 3; roles: 0 father,
 // 1 mother, 2 kid. flags = selfing | (role of u(m) in m) << 1.
 //   KID_CHUNK (large sibships; next level): flags, ab_row, outside_row, n, { up_ref, stub_row, dn_row } * n
-enum TaskKind : int { TASK_ROOT = 0, TASK_LEAF_IN = 1, TASK_FAM_UP = 2, TASK_FAM_DOWN = 3, TASK_KID_CHUNK = 4 };
+enum TaskKind : int { TASK_ROOT = 0, TASK_LEAF_IN = 1, TASK_FAM_UP = 2, TASK_FAM_DOWN = 3, TASK_KID_CHUNK = 4, TASK_KFOLD = 5 };
 constexpr int NO_REF = 0x1fffffff;
 #ifndef PF_FAM_CHUNK
-#define PF_FAM_CHUNK 1
+#define PF_FAM_CHUNK 3
 #endif
 #ifndef PF_FAM_SMALL_MAX
 #define PF_FAM_SMALL_MAX 1
 #endif
-constexpr int FAM_CHUNK = PF_FAM_CHUNK;           // kids per KID_CHUNK task
+constexpr int FAM_CHUNK = PF_FAM_CHUNK;           // leaf kids per sibship chunk (one KFOLD and one KID_CHUNK task each)
 constexpr int FAM_SMALL_MAX = PF_FAM_SMALL_MAX;   // sibships up to this size are finished inside FAM_DOWN
 constexpr int SMEM_ROW_BIT = 1 << 29;
 // in place of an up_i row reference: the member is a leaf (no marriage below it), its up message
