@@ -634,31 +634,49 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 w.it_cnt[m] = (int)w.it_type.size() - w.it_off[m];
             }
             if (!up_only) {
-                int max_depth = 0;
-                for (size_t b = mb; b < me; b++) max_depth = std::max(max_depth, w.depth_m[w.bfs_m[b]]);
-                std::vector<int> &cnt_m = w.cnt_a, &cnt_d = w.cnt_b;
-                cnt_m.assign(max_depth + 1, 0); cnt_d.assign(max_depth + 1, 0);
-                std::vector<int> &cnt_t = w.cnt_c;
-                cnt_t.assign(max_depth + 1, 0);
-                int bank_m = 0, bank_d = 0, bank_t = 0;
+                // Down-band levels by actual dependency instead of two per tree depth: FAM_DOWN(m)
+                // runs one level after the task that writes the down message of its up individual
+                // u — FAM_DOWN of u's up marriage when u is a parent there (or its single kid),
+                // that marriage's KID_CHUNK level when u is one of several kids. Going up through
+                // ancestors therefore costs one level per marriage, going down through a sibship two.
+                // (bfs_m lists a component's marriages parents-first.)
+                auto has_tmp = [&](int m) { const int ni = w.it_cnt[m]; return ni >= 2 || (ni == 1 && w.it_type[w.it_off[m]] == 1); };
+                int max_l = 0;
                 for (size_t b = mb; b < me; b++) {
-                    const int m = w.bfs_m[b], d = w.depth_m[m];
-                    {   // sibships of more than one single kid park a, b and one row pair per item
-                        const int ni = w.it_cnt[m];
-                        w.tmp_row[m] = -1;
-                        if (ni >= 2 || (ni == 1 && w.it_type[w.it_off[m]] == 1)) { w.tmp_row[m] = cnt_t[d]; cnt_t[d] += 2 + 2 * ni; bank_t = std::max(bank_t, cnt_t[d]); }
+                    const int m = w.bfs_m[b], u = w.um[m];
+                    int l = 0;
+                    if (w.Ui[u] >= 0) {
+                        const int mp = w.Ui[u];
+                        int role = 2;
+                        for (int k = w.mem_off[mp]; k < w.mem_off[mp + 1]; k++) if (w.mem_i[k] == u && w.mem_i[k] != w.um[mp]) role = w.mem_role[k];
+                        l = w.depth_m[mp] + 1 + ((role == 2 && has_tmp(mp)) ? 1 : 0);
                     }
+                    w.depth_m[m] = l;               // from here on depth_m holds the down-band level of FAM_DOWN(m)
+                    max_l = std::max(max_l, l + 1);
+                }
+                std::vector<int> &cnt_d = w.cnt_b, &cnt_t = w.cnt_c;
+                cnt_d.assign(max_l + 2, 0); cnt_t.assign(max_l + 2, 0);
+                int bank_d = 0, bank_t = 0;
+                for (size_t b = mb; b < me; b++) {
+                    const int m = w.bfs_m[b], l = w.depth_m[m];
+                    w.tmp_row[m] = -1;
+                    // sibships of more than one single kid park a, b and one row pair per item; the rows
+                    // are written at level l and read at l + 1: two banks by the parity of l
+                    if (has_tmp(m)) { w.tmp_row[m] = cnt_t[l]; cnt_t[l] += 2 + 2 * w.it_cnt[m]; bank_t = std::max(bank_t, cnt_t[l]); }
                     for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
                         const int x = w.mem_i[k];
                         if (x == w.um[m] || w.adj_off[x + 1] - w.adj_off[x] <= 1) continue;
-                        w.dn_row[x] = (cnt_d[d]++) * 2 + (d & 1);      // two banks: consecutive depths overlap in time
-                        bank_d = std::max(bank_d, 2 * cnt_d[d]);
+                        const int lw = l + ((w.mem_role[k] == 2 && has_tmp(m)) ? 1 : 0);   // level that writes the message to x
+                        w.dn_row[x] = (cnt_d[lw]++) * 2 + (lw & 1);        // read at lw + 1, reusable from lw + 2
+                        bank_d = std::max(bank_d, 2 * cnt_d[lw]);
                     }
                 }
-                const int base_m = G.n_rows, base_d = G.n_rows + bank_m, base_t = base_d + bank_d;
-                G.n_rows += bank_m + bank_d + bank_t;
-                (void)base_m;
-                for (size_t b = mb; b < me; b++) if (w.tmp_row[w.bfs_m[b]] >= 0) w.tmp_row[w.bfs_m[b]] += base_t;      // plain row numbers (ld_i / st_i)
+                const int base_d = G.n_rows, base_t = base_d + bank_d;
+                G.n_rows += bank_d + 2 * bank_t;
+                for (size_t b = mb; b < me; b++) {
+                    const int m = w.bfs_m[b];
+                    if (w.tmp_row[m] >= 0) w.tmp_row[m] += base_t + (w.depth_m[m] & 1) * bank_t;      // plain row numbers (ld_i / st_i)
+                }
                 for (int oi = ib; oi < ie; oi++) {
                     const int i = order_i[oi];
                     if (w.dn_row[i] >= 0) w.dn_row[i] = SCRATCH_BIT | (base_d + w.dn_row[i]);
@@ -770,7 +788,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 pool.push_back(w.it_cnt[m]);
                 push_item_list(m);
                 if (up_only) continue;                              // log Z only: no down band
-                add_task(-(2 + 2 * w.depth_m[m]), TASK_FAM_DOWN);
+                add_task(-(2 + w.depth_m[m]), TASK_FAM_DOWN);
                 pool.push_back(flags); pool.push_back(e->prong_row(chain, v->marr[m]));
                 pool.push_back(member(u, w.urole[m]));
                 if (w.Ui[u] < 0) pool.push_back(-1); else push_row(w.dn_row[u]);
@@ -796,7 +814,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 }
                 // one KID_CHUNK task per item on the next level
                 for (int it = w.it_off[m], i = 0; it < w.it_off[m] + w.it_cnt[m]; it++, i++) {
-                    add_task(-(2 + 2 * w.depth_m[m] + 1), TASK_KID_CHUNK);
+                    add_task(-(2 + w.depth_m[m] + 1), TASK_KID_CHUNK);
                     pool.push_back(flags);
                     pool.push_back(w.tmp_row[m]);
                     pool.push_back(w.tmp_row[m] + 2 + 2 * i);
