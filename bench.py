@@ -415,8 +415,7 @@ def main():
                     h_pinned[o: o + view.n_cc + len(props)].copy_(seg, non_blocking=True)
                     torch.cuda.current_stream().synchronize()
                 else:
-                    eng.sweep(view, chain=c)
-                    eng.eval(kid, props, chain=c)
+                    eng.sweep_eval(view, kid, props, chain=c)      # pf_sweep_eval: what pedigraph calls per Gibbs step
                 nbytes_in += view_bytes(view) + props.nbytes
                 nbytes_out += 8 * (view.n_cc + len(props))
             eng.sweep(trace.final_view, chain=c)
