@@ -11,6 +11,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -88,6 +89,9 @@ struct SoftChunk { char *base; size_t cap, used; };
 } // namespace
 
 struct pf_engine {
+    // PF_HOST_PROF=1: seconds spent building sweep plans / staging+launching / waiting for results
+    bool sweep_clocks = false;        // PF_SWEEP_CLOCKS=1: per-level clocks of the largest group after every sweep
+    bool host_prof = false; double t_plan = 0, t_submit = 0, t_wait = 0, t_evalprep = 0; long n_prof = 0, n_prof_calls = 0; double t_ph[6] = {0, 0, 0, 0, 0, 0};
     bool no_mailbox = false;          // PEDFAC_NO_MAILBOX=1 or no mapped memory: results by copy + stream synchronise
     int sm_count = 0;
     int eval_capacity = 0;            // resident eval_kernel blocks on this device
@@ -140,8 +144,15 @@ struct pf_engine {
 
 extern "C" const char *pf_last_error(void) { return g_err; }
 
+static double host_now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
 extern "C" int pf_destroy(pf_engine *e)
 {
+    if (e && e->host_prof && e->n_prof)
+        fprintf(stderr, "pf-host-prof plan phases us: adjacency %.1f traversals %.1f heights %.1f rows+items+genotype-entries %.1f emission %.1f\n",
+                1e6 * e->t_ph[0] / e->n_prof, 1e6 * e->t_ph[1] / e->n_prof, 1e6 * e->t_ph[2] / e->n_prof, 1e6 * e->t_ph[3] / e->n_prof, 1e6 * e->t_ph[4] / e->n_prof),
+        fprintf(stderr, "pf-host-prof sweeps %ld plan_us %.1f submit_us %.1f evalprep_us %.1f wait_us %.1f (per sweep)\n", e->n_prof,
+                1e6 * e->t_plan / e->n_prof, 1e6 * e->t_submit / e->n_prof, 1e6 * e->t_evalprep / e->n_prof, 1e6 * e->t_wait / e->n_prof);
     if (!e) return PF_OK;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
@@ -211,6 +222,8 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->h_eps.assign(e->Sl, 0.0);
     e->loc.assign(cfg->cap_indiv, -1);
     e->no_mailbox = getenv("PEDFAC_NO_MAILBOX") != nullptr;
+    e->host_prof = getenv("PF_HOST_PROF") != nullptr;
+    e->sweep_clocks = getenv("PF_SWEEP_CLOCKS") != nullptr;
     *out = e;
     return PF_OK;
 }
@@ -394,6 +407,11 @@ struct Plan {
     int n_levels = 1, n_out = 0;
     int target_tasks_per_group = 1 << 30;
     int scratch_rows = 0;
+    void reset()        // empties the plan but keeps the vectors' capacity (plans are built per call)
+    {
+        tasks.clear(); pool.clear(); emis.clear(); groups.clear(); row_ref_pos.clear();
+        n_levels = 1; n_out = 0; target_tasks_per_group = 1 << 30; scratch_rows = 0;
+    }
 
     // Whole components are appended to the open group; a new group starts once the open one has
     // reached the target size (components are never split: their tasks depend on each other).
@@ -416,6 +434,8 @@ struct ViewWork {           // scratch vectors reused across calls
     std::vector<int> up_i_row, up_m_row, dn_row, in_u_row, emis_idx;
     std::vector<int> bfs_m, queue, cnt_a, cnt_b, cnt_c, tmp_row;
     std::vector<char> vis_i, vis_m, label_seen, in_chunk;
+    std::vector<int> roots, comp_members_end, order_i, q;    // BFS order of individuals per component
+    std::vector<int> level_off, start;
     std::vector<int> it_off, it_cnt, it_type, it_first, it_n, it_kids, it_prow;   // sibship items per marriage (see item_factor)
 };
 
@@ -440,6 +460,9 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
     int rc = PF_OK;
     int registered = 0;
 
+    const bool hp_on = e->host_prof && e->n_prof_calls >= 100;
+    double hp_t = hp_on ? host_now() : 0.0;
+    auto hp_mark = [&](int ph) { if (hp_on) { const double t = host_now(); e->t_ph[ph] += t - hp_t; hp_t = t; } };
     // slot -> local index
     for (int i = 0; i < nI; i++) {
         const int slot = v->indiv[i];
@@ -482,9 +505,8 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         w.it_off.assign(nM, 0); w.it_cnt.assign(nM, 0); w.it_type.clear(); w.it_first.clear(); w.it_n.clear(); w.it_kids.clear(); w.it_prow.clear(); w.in_chunk.assign(nI, 0);
         w.up_i_row.assign(nI, -1); w.up_m_row.assign(nM, -1); w.in_u_row.assign(nM, -1); w.tmp_row.assign(nM, -1); w.dn_row.assign(nI, -1); w.emis_idx.assign(nI, -1);
         w.bfs_m.clear();
-        std::vector<int> roots, comp_members_end;   // BFS order of individuals per component
-        std::vector<int> order_i;
-        std::vector<int> q;
+        std::vector<int> &roots = w.roots, &comp_members_end = w.comp_members_end, &order_i = w.order_i, &q = w.q;
+        roots.clear(); comp_members_end.clear(); order_i.clear(); q.clear();
         const size_t no_m = (size_t)-1;
         // BFS over the bipartite tree from individual r: fills Ui / um / urole / depth_m, appends
         // the marriages to bfs_m, leaves the individuals in q. Returns an error code.
@@ -518,6 +540,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             w.bfs_m.resize(m_from);
         };
         (void)no_m;
+        hp_mark(0);
         for (int r0 = 0; r0 < nI; r0++) {
             if (w.vis_i[r0]) continue;
             const int label = v->indiv_cc[r0];
@@ -547,6 +570,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         }
         for (int m = 0; m < nM; m++)
             if (!w.vis_m[m]) { rc = fail(PF_EINVAL, "marriage %d not reachable", v->marr[m]); goto cleanup; }
+        hp_mark(1);
         // heights of the FAMILY_UP tasks, children first (reverse BFS order)
         int up_levels = 0;
         for (int b = (int)w.bfs_m.size() - 1; b >= 0; b--) {
@@ -563,6 +587,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         }
         max_up_levels = std::max(max_up_levels, up_levels);
 
+        hp_mark(2);
         // emit tasks component by component (BFS order keeps a component's marriages contiguous)
         std::vector<int> &pool = plan.pool;
         // transient row references are recorded so they can be tagged "in shared memory" once the
@@ -581,13 +606,6 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 push_row(w.up_m_row[m2]); n++;
             }
             pool[at] = n;
-        };
-        // height of the up message of individual x: 0 if nothing hangs below it
-        auto lvl_in = [&](int x, int except_m) {
-            int lv = 0;
-            for (int a = w.adj_off[x]; a < w.adj_off[x + 1]; a++)
-                if (w.adj_m[a] != except_m) lv = std::max(lv, w.lvlA[w.adj_m[a]] + 1);
-            return lv;
         };
         auto member = [&](int x, int role) { return role | (v->indiv_founder[x] ? 4 : 0) | (w.emis_idx[x] << 3); };
         size_t bfs_pos = 0;
@@ -722,6 +740,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 if (w.up_i_row[x] >= 0) push_row(w.up_i_row[x]);
                 else pool.push_back((int)(LEAF_REF_BIT | (unsigned)member(x, role)));
             };
+            hp_mark(3);
             auto add_task = [&](int level, int kind) { plan.tasks.push_back(PlanTask{gid, level, kind, (int)pool.size()}); G.task_end++; };
             // levels: >= 0 = up band; -1 = first level of the down band; -(2 + k) = down band level k
             const bool has_m = w.adj_off[r + 1] > w.adj_off[r];
@@ -828,6 +847,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 }
             }
             G.pool_len = (int)pool.size() - G.pool_begin;
+            hp_mark(4);
         }
     }
 cleanup:
@@ -842,7 +862,10 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     int rc = sync_tables(e);
     if (rc) return rc;
     const int n_tiles = (e->Sl + TILE_LOCI - 1) / TILE_LOCI;
-    Plan plan;
+    const double t_begin = e->host_prof ? host_now() : 0.0;
+    static thread_local Plan plan_storage;
+    Plan &plan = plan_storage;
+    plan.reset();
     // tasks = one ROOT per component + two per marriage: known before any traversal
     long long est_tasks = 0, est_comp = 0;
     for (int i = 0; i < n; i++) { est_tasks += (long long)std::max(views[i].n_cc, 0) + 2LL * std::max(views[i].n_marr, 0); est_comp += std::max(views[i].n_cc, 0); }
@@ -861,10 +884,10 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     bool throughput_shape = false;
     int n_levels = 1, G = 0, smem_bytes = 0, scratch_rows = 0, max_up = 0;
     bool all_staged = true;
-    std::vector<int> level_off, start;
+    std::vector<int> &level_off = g_work.level_off, &start = g_work.start;
     for (int pass = 0; pass < 2; pass++) {
         const SweepShape shape = throughput_shape ? SWEEP_THROUGHPUT : SWEEP_LATENCY;
-        plan = Plan();
+        plan.reset();
         plan.target_tasks_per_group = target_tasks;
         max_up = 0;
         int out_base = 0;
@@ -947,6 +970,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         }
     }
 
+    const double t_planned = e->host_prof ? host_now() : 0.0;
     const size_t bytes_tasks = plan.tasks.size() * sizeof(SweepTask);
     const size_t bytes_pool = plan.pool.size() * sizeof(int);
     const size_t bytes_loff = (size_t)G * (n_levels + 1) * sizeof(int);
@@ -996,7 +1020,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     }
     P.out = fused_reduce ? out_dev : nullptr;
     P.counter = static_cast<unsigned *>(e->sweep_counter.p);
-    if (getenv("PF_SWEEP_CLOCKS")) {
+    if (e->sweep_clocks) {
         // measurement aid: per-level clocks of the largest group, printed after the launch
         CU(e->clockbuf.reserve((size_t)(n_levels + 2) * sizeof(long long)));
         P.clocks = static_cast<long long *>(e->clockbuf.p);
@@ -1024,6 +1048,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         for (int l = 0; l < n_levels; l++) fprintf(stderr, " %d:%lld", lo[l + 1] - lo[l], hc[l + 1] - hc[l]);
         fprintf(stderr, "\n");
     }
+    if (e->host_prof && ++e->n_prof_calls > 100) { const double t = host_now(); e->t_plan += t_planned - t_begin; e->t_submit += t - t_planned; e->n_prof++; }   // the first 100 sweeps are warm-up
     if (plan.n_out > 0 && !fused_reduce) {
         ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_tiles, plan.n_out};
         e->prof_begin(2);
@@ -1058,6 +1083,7 @@ static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2
             launch_publish(static_cast<const double *>(e->result.p), reinterpret_cast<double *>(e->d_mail + 8), n, e->d_mail, seq, e->stream);
             e->launches++;
             CU(cudaGetLastError());
+            const double t_w0 = e->host_prof ? host_now() : 0.0;
             volatile unsigned long long *flag = e->h_mail;
             for (unsigned spins = 1; *flag != seq; spins++) {
                 __builtin_ia32_pause();
@@ -1068,6 +1094,7 @@ static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2
                 }
             }
             __atomic_thread_fence(__ATOMIC_ACQUIRE);
+            if (e->host_prof && e->n_prof_calls > 100) e->t_wait += host_now() - t_w0;
             const double *vals = reinterpret_cast<const double *>(e->h_mail + 8);
             if (n1 > 0) memcpy(host_out, vals, (size_t)n1 * sizeof(double));
             if (n2 > 0) memcpy(host_out2, vals + n1, (size_t)n2 * sizeof(double));
@@ -1291,6 +1318,7 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     CU(cudaSetDevice(e->cfg.device));
     const int n_props = prop_begin[n];
     if (n_props <= 0) return PF_OK;
+    const double t_e0 = e->host_prof ? host_now() : 0.0;
     int n_groups = 0;
     for (int i = 0; i < n; i++) {
         const int c = prop_begin[i + 1] - prop_begin[i];
@@ -1361,6 +1389,7 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     launch_eval(P, n_chunks, e->stream);
     e->prof_end();
     e->launches++;
+    if (e->host_prof && e->n_prof_calls > 100) e->t_evalprep += host_now() - t_e0;
     CU(cudaGetLastError());
     return PF_OK;
 }
