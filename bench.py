@@ -319,7 +319,7 @@ def main():
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "strong" if wl == "C" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak" if wl == "D" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{wl}: {desc}", "trace_steps": args.trace_steps,
                        "note": "ngthomas/pedFac ships pedigraph only as a macOS binary (no source): this arm times the C "
                                "restatement of its algorithm (oracle/pedfac_oracle.c) with the reference's own schedule"},

@@ -495,13 +495,15 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, MIN_BLOCKS) sweep_kernel(con
 void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, bool throughput_shape, cudaStream_t st)
 {
     constexpr SweepShape L = SWEEP_LATENCY, T = SWEEP_THROUGHPUT;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_set = 0;      // one bit per device: the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!(attr_set >> (dev & 63) & 1)) {
         cudaFuncSetAttribute(sweep_kernel<true, L.warps, L.blocks_per_sm>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_max);
         cudaFuncSetAttribute(sweep_kernel<false, L.warps, L.blocks_per_sm>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.smem_max);
         cudaFuncSetAttribute(sweep_kernel<true, T.warps, T.blocks_per_sm>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_max);
         cudaFuncSetAttribute(sweep_kernel<false, T.warps, T.blocks_per_sm>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_max);
-        attr_set = true;
+        attr_set |= 1ull << (dev & 63);
     }
     dim3 grid(n_tiles, P.n_groups);
     if (!throughput_shape) {
