@@ -115,7 +115,10 @@ constexpr int SMEM_ROW_BYTES = 3 * TILE_LOCI * 8;
 //                    used when there are more heavy blocks than SMs (10 000 loci, many chains)
 // The budgets keep the total under the 196 KB carve-out so that 32 KB of L1 remain.
 struct SweepShape { int warps, blocks_per_sm, smem_max, plan_smem_max, emis_smem_max, leaf_row_budget; };
-constexpr SweepShape SWEEP_LATENCY{16, 1, 195 * 1024, 56 * 1024, 72 * 1024, 160};
+#ifndef PF_LAT_WARPS
+#define PF_LAT_WARPS 16
+#endif
+constexpr SweepShape SWEEP_LATENCY{PF_LAT_WARPS, 1, 195 * 1024, 56 * 1024, 72 * 1024, 160};
 constexpr SweepShape SWEEP_THROUGHPUT{8, 2, 98 * 1024, 28 * 1024, 36 * 1024, 64};
 
 // staged bytes of one individual's 32-locus genotype tile
