@@ -332,3 +332,50 @@ def test_gpu_sweep_eval_equals_sweep_then_eval():
     ll4, l4 = g.sweep_eval(view, kid, [])
     np.testing.assert_array_equal(ll4, ll1)
     assert len(l4) == 0
+
+
+def test_gpu_throughput_shape_matches_oracle():
+    """Many locus tiles x heavy groups with small genotype tiles (hard calls) make the plan builder
+    pick the 8-warp / 2-blocks-per-SM sweep shape (98 KB of shared memory, more spilled rows): same
+    results as the oracle, and as the latency shape on a shard that is small enough for it."""
+    rng = np.random.default_rng(515)
+    sc = random_forest(rng, n_indiv=420, S=6000, max_kids=6, kinds=("hard", "none"), max_comp=200)
+    g = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    o = OracleEngine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(g); sc.upload(o)
+    labels, _ = sc.ped.components()
+    view, glob = sc.ped.view(labels)
+    ll = g.sweep(view)
+    st = g.plan_stats()
+    assert st["smem_bytes"] <= 98 * 1024 and st["tiles"] == 188, st
+    np.testing.assert_allclose(ll, o.sweep(view), rtol=1e-12, atol=1e-9)
+    for i in np.flatnonzero(sc.ped.active)[::17]:
+        np.testing.assert_allclose(g.get_stub(int(i)), o.get_stub(int(i)), rtol=1e-12, atol=0)
+    # a 1 000-locus shard of the same data runs the latency shape; its log-likelihoods are the partial sums
+    g2 = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr, locus_range=(0, 1000))
+    sc.upload(g2)
+    ll2 = g2.sweep(view)
+    assert g2.plan_stats()["smem_bytes"] > 98 * 1024 or g2.plan_stats()["rows"] == g2.plan_stats()["rows_smem"]
+    o2 = OracleEngine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr, locus_range=(0, 1000))
+    sc.upload(o2)
+    np.testing.assert_allclose(ll2, o2.sweep(view), rtol=1e-12, atol=1e-9)
+
+
+def test_gpu_results_without_the_mailbox_are_identical(monkeypatch):
+    """PEDFAC_NO_MAILBOX=1 delivers results by device-to-host copy + stream synchronise instead of
+    the mapped pinned mailbox: bit-identical values."""
+    rng = np.random.default_rng(616)
+    sc = random_forest(rng, n_indiv=90, S=130, max_kids=4, max_comp=30)
+    labels, _ = sc.ped.components()
+    view, _ = sc.ped.view(labels)
+    a = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    monkeypatch.setenv("PEDFAC_NO_MAILBOX", "1")
+    b = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    monkeypatch.delenv("PEDFAC_NO_MAILBOX")
+    sc.upload(a); sc.upload(b)
+    np.testing.assert_array_equal(a.sweep(view), b.sweep(view))
+    has_parents = {k for mm in sc.ped.marriages.values() for k in mm.kids}
+    kid = next(int(i) for i in np.flatnonzero(sc.ped.active) if int(i) not in has_parents)
+    others = [int(i) for i in np.flatnonzero(sc.ped.active) if labels[i] != labels[kid]]
+    props = [(PF_PROP_TRIO, c, -1, -1) for c in others[:20]]
+    np.testing.assert_array_equal(a.eval(kid, props), b.eval(kid, props))
