@@ -389,15 +389,19 @@ def main():
         eng.sweep_batch(chain_ids, [trace.final_view] * chains)
         return nbytes_in + chains * view_bytes(trace.final_view), nbytes_out + 8 * chains * trace.final_view.n_cc
 
+    # views of the output vector that each Gibbs step all-reduces (sliced once, outside the timed loop)
+    segs = [[d_out[c * tot + o: c * tot + o + view.n_cc + len(props)] for (view, kid, props), o in zip(trace.steps, offs)]
+            for c in range(chains)] if sharded else None
+
     def step_device():
         """T Gibbs-step passes, results stay on the device (plus the NCCL all-reduce when sharded)."""
         for c in range(chains):
             cb = c * tot
-            for (view, kid, props), o in zip(trace.steps, offs):
+            for t, ((view, kid, props), o) in enumerate(zip(trace.steps, offs)):
                 eng.sweep_dev(view, base_ptr + 8 * (cb + o), chain=c)
                 eng.eval_dev(kid, props, base_ptr + 8 * (cb + o + view.n_cc), chain=c)
                 if sharded:
-                    dist.all_reduce(d_out[cb + o: cb + o + view.n_cc + len(props)])
+                    dist.all_reduce(segs[c][t])
             eng.sweep_dev(trace.final_view, base_ptr + 8 * (cb + off_final), chain=c)
 
     h_pinned = torch.empty(max(tot, 1), dtype=torch.float64).pin_memory()
