@@ -90,6 +90,7 @@ struct SoftChunk { char *base; size_t cap, used; };
 
 struct pf_engine {
     // PF_HOST_PROF=1: seconds spent building sweep plans / staging+launching / waiting for results
+    int force_shape = 0;              // PF_SWEEP_SHAPE=latency|throughput overrides the per-launch choice (measurement aid)
     bool sweep_clocks = false;        // PF_SWEEP_CLOCKS=1: per-level clocks of the largest group after every sweep
     bool host_prof = false; double t_plan = 0, t_submit = 0, t_wait = 0, t_evalprep = 0; long n_prof = 0, n_prof_calls = 0; double t_ph[6] = {0, 0, 0, 0, 0, 0};
     bool no_mailbox = false;          // PEDFAC_NO_MAILBOX=1 or no mapped memory: results by copy + stream synchronise
@@ -224,6 +225,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->no_mailbox = getenv("PEDFAC_NO_MAILBOX") != nullptr;
     e->host_prof = getenv("PF_HOST_PROF") != nullptr;
     e->sweep_clocks = getenv("PF_SWEEP_CLOCKS") != nullptr;
+    if (const char *fs = getenv("PF_SWEEP_SHAPE")) e->force_shape = fs[0] == 't' ? 2 : fs[0] == 'l' ? 1 : 0;
     *out = e;
     return PF_OK;
 }
@@ -917,7 +919,8 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
             // with large genotype tiles (soft calls: 192+ B per individual) half the shared memory
             // leaves too few message rows: measured on config D the small shape LOSES 17 %, on
             // config C (hard calls, 8 B per individual) it wins 21 %
-            if ((long long)heavy * n_tiles > sm_count && emis_bytes <= 16 * 1024) { throughput_shape = true; continue; }
+            const bool want = e->force_shape == 2 || (e->force_shape == 0 && (long long)heavy * n_tiles > sm_count && emis_bytes <= 16 * 1024);
+            if (want) { throughput_shape = true; continue; }
         }
 
         // counting sort by (group, level); groups own contiguous task ranges in emission order already
