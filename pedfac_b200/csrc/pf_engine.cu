@@ -106,6 +106,7 @@ struct pf_engine {
     uint32_t *d_hard = nullptr;           // [cap_indiv][Sp/16]
     uint8_t *d_kind = nullptr; void **d_eptr = nullptr; uint32_t *d_denom = nullptr;
     std::vector<uint8_t> h_kind; std::vector<void *> h_eptr; std::vector<uint32_t> h_denom;
+    std::vector<double> h_rcp;            // 1 / h_denom per slot (the sweep plans carry it)
     std::vector<uint8_t> soft_kind_of_row;  // kind the slot's soft row was allocated for
     bool tables_dirty = true;
     std::vector<SoftChunk> soft_chunks;
@@ -219,6 +220,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->h_kind.assign(cfg->cap_indiv, EMIS_NONE);
     e->h_eptr.assign(cfg->cap_indiv, nullptr);
     e->h_denom.assign(cfg->cap_indiv, 1);
+    e->h_rcp.assign(cfg->cap_indiv, 1.0);
     e->soft_kind_of_row.assign(cfg->cap_indiv, EMIS_NONE);
     e->h_eps.assign(e->Sl, 0.0);
     e->loc.assign(cfg->cap_indiv, -1);
@@ -331,7 +333,7 @@ static int set_soft(pf_engine *e, int32_t slot, const T *lik, uint8_t kind, uint
         for (int g = 0; g < 3; g++) buf[(size_t)g * Sp + s] = lik[(size_t)(s0 + s) * 3 + g];
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemcpy(row, buf.data(), buf.size() * sizeof(T), cudaMemcpyHostToDevice));
-    e->h_kind[slot] = kind; e->h_eptr[slot] = row; e->h_denom[slot] = denom;
+    e->h_kind[slot] = kind; e->h_eptr[slot] = row; e->h_denom[slot] = denom; e->h_rcp[slot] = 1.0 / (double)denom;
     e->tables_dirty = true;
     return PF_OK;
 }
@@ -359,7 +361,7 @@ extern "C" int pf_set_genotypes_hard(pf_engine *e, int32_t slot, const uint8_t *
     uint32_t *row = e->d_hard + (size_t)slot * words;
     CU(cudaStreamSynchronize(e->stream));
     CU(cudaMemcpy(row, buf.data(), (size_t)words * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    e->h_kind[slot] = EMIS_HARD; e->h_eptr[slot] = row; e->h_denom[slot] = 1;
+    e->h_kind[slot] = EMIS_HARD; e->h_eptr[slot] = row; e->h_denom[slot] = 1; e->h_rcp[slot] = 1.0;
     e->soft_kind_of_row[slot] = EMIS_NONE;
     e->tables_dirty = true;
     return PF_OK;
@@ -405,13 +407,12 @@ struct Plan {
     std::vector<int> pool;
     std::vector<EmisEnt> emis;
     std::vector<SweepGroup> groups;
-    std::vector<int> row_ref_pos;        // pool positions holding transient row references
     int n_levels = 1, n_out = 0;
     int target_tasks_per_group = 1 << 30;
     int scratch_rows = 0;
     void reset()        // empties the plan but keeps the vectors' capacity (plans are built per call)
     {
-        tasks.clear(); pool.clear(); emis.clear(); groups.clear(); row_ref_pos.clear();
+        tasks.clear(); pool.clear(); emis.clear(); groups.clear();
         n_levels = 1; n_out = 0; target_tasks_per_group = 1 << 30; scratch_rows = 0;
     }
 
@@ -592,12 +593,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         hp_mark(2);
         // emit tasks component by component (BFS order keeps a component's marriages contiguous)
         std::vector<int> &pool = plan.pool;
-        // transient row references are recorded so they can be tagged "in shared memory" once the
-        // group's budget is known (see run_sweeps)
-        auto push_row = [&](int ref) {
-            if (ref & SCRATCH_BIT) plan.row_ref_pos.push_back((int)pool.size());
-            pool.push_back(ref);
-        };
+        auto push_row = [&](int ref) { pool.push_back(ref); };     // transient rows: the kernel tells shared from spilled by the row number
         auto below_rows = [&](int x, int except_m) {
             int n = 0;
             const size_t at = pool.size();
@@ -721,7 +717,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 // genotype entry
                 const int slot = v->indiv[i];
                 EmisEnt E{};
-                E.kind = e->h_kind[slot]; E.denom = e->h_denom[slot]; E.rcp = 1.0 / (double)e->h_denom[slot];
+                E.kind = e->h_kind[slot]; E.denom = e->h_denom[slot]; E.rcp = e->h_rcp[slot];
                 const unsigned long long pp = (unsigned long long)(uintptr_t)e->h_eptr[slot];
                 E.ptr_lo = (unsigned)(pp & 0xffffffffu); E.ptr_hi = (unsigned)(pp >> 32);
                 const int bytes = emis_tile_bytes(E.kind);
@@ -877,21 +873,52 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         const long long G = std::max<long long>(1, std::min<long long>(std::min<long long>(want_groups, est_comp), 65535));
         plan.target_tasks_per_group = (int)std::max<long long>(1, (est_tasks + G - 1) / G);
     }
-    // Build the plan for the latency shape first; if the launch then has more heavy blocks than
-    // the GPU has SMs (a block of a large component runs ~100 us whatever the number of tiles),
-    // rebuild it for the throughput shape, which overlaps two blocks per SM (see SweepShape).
+    // Shape of the launch (see SweepShape), decided from the views before any traversal: a component
+    // is heavy when it has at least 40 individuals and a quarter of the largest one's; a block of a
+    // heavy component runs ~100 us whatever the number of tiles, so with more heavy blocks than SMs the
+    // throughput shape overlaps two per SM — unless the genotype tiles are large (soft calls:
+    // 192+ B per individual): then half the shared memory leaves too few message rows (measured on
+    // config D the small shape loses, on config C, hard calls at 8 B per individual, it wins 21 %).
     int sm_count = e->sm_count;
     if (sm_count <= 0) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device); e->sm_count = sm_count = sm_count > 0 ? sm_count : 148; }
-    const int target_tasks = plan.target_tasks_per_group;
-    bool throughput_shape = false;
+    bool throughput_shape = e->force_shape == 2;
+    if (e->force_shape == 0) {
+        std::vector<int> &cnt = g_work.cnt_a, &bytes = g_work.cnt_b;
+        int heavy = 0, biggest = 0, emis_bytes = 0;
+        for (int pass = 0; pass < 2; pass++)
+            for (int i = 0; i < n; i++) {
+                const pf_graph_view &v = views[i];
+                if (v.n_cc <= 0 || v.n_indiv <= 0 || !v.indiv || !v.indiv_cc) continue;
+                if (pass == 0) {
+                    cnt.assign(v.n_cc, 0); bytes.assign(v.n_cc, 0);
+                    for (int k = 0; k < v.n_indiv; k++) {
+                        const int c = v.indiv_cc[k], slot = v.indiv[k];
+                        if (c < 0 || c >= v.n_cc || slot < 0 || slot >= e->cfg.cap_indiv) continue;    // reported by plan_add_view
+                        cnt[c]++; bytes[c] += emis_tile_bytes(e->h_kind[slot]);
+                    }
+                    for (int c = 0; c < v.n_cc; c++) biggest = std::max(biggest, cnt[c]);
+                    if (n > 1) continue;        // several views: second pass recounts (rare: batched chains)
+                }
+                if (pass == 1 && n > 1) {
+                    cnt.assign(v.n_cc, 0); bytes.assign(v.n_cc, 0);
+                    for (int k = 0; k < v.n_indiv; k++) {
+                        const int c = v.indiv_cc[k], slot = v.indiv[k];
+                        if (c < 0 || c >= v.n_cc || slot < 0 || slot >= e->cfg.cap_indiv) continue;
+                        cnt[c]++; bytes[c] += emis_tile_bytes(e->h_kind[slot]);
+                    }
+                }
+                if (pass == 1 || n == 1)
+                    for (int c = 0; c < v.n_cc; c++)
+                        if (cnt[c] >= 40 && 4 * cnt[c] >= biggest) { heavy++; emis_bytes = std::max(emis_bytes, bytes[c]); }
+                if (n == 1) break;
+            }
+        throughput_shape = (long long)heavy * n_tiles > sm_count && emis_bytes <= 16 * 1024;
+    }
+    const SweepShape shape = throughput_shape ? SWEEP_THROUGHPUT : SWEEP_LATENCY;
     int n_levels = 1, G = 0, smem_bytes = 0, scratch_rows = 0, max_up = 0;
     bool all_staged = true;
     std::vector<int> &level_off = g_work.level_off, &start = g_work.start;
-    for (int pass = 0; pass < 2; pass++) {
-        const SweepShape shape = throughput_shape ? SWEEP_THROUGHPUT : SWEEP_LATENCY;
-        plan.reset();
-        plan.target_tasks_per_group = target_tasks;
-        max_up = 0;
+    {
         int out_base = 0;
         for (int i = 0; i < n; i++) {
             rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up, up_only, shape);
@@ -912,16 +939,6 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         plan.n_levels = n_levels;
         G = (int)plan.groups.size();
         if (G > 65535) return fail(PF_EINVAL, "too many task groups (%d)", G);
-        if (pass == 0) {
-            int heavy = 0, biggest = 0, emis_bytes = 0;
-            for (auto &sg : plan.groups) { biggest = std::max(biggest, sg.task_end); emis_bytes = std::max(emis_bytes, sg.emis_bytes); }   // task_end counts the group's tasks here
-            for (auto &sg : plan.groups) if (sg.task_end >= 48 && 4 * sg.task_end >= biggest) heavy++;
-            // with large genotype tiles (soft calls: 192+ B per individual) half the shared memory
-            // leaves too few message rows: measured on config D the small shape LOSES 17 %, on
-            // config C (hard calls, 8 B per individual) it wins 21 %
-            const bool want = e->force_shape == 2 || (e->force_shape == 0 && (long long)heavy * n_tiles > sm_count && emis_bytes <= 16 * 1024);
-            if (want) { throughput_shape = true; continue; }
-        }
 
         // counting sort by (group, level); groups own contiguous task ranges in emission order already
         level_off.assign((size_t)G * (n_levels + 1) + 1, 0);
@@ -957,22 +974,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
             scratch_rows += sg.n_rows;
             smem_bytes = std::max(smem_bytes, sweep_smem_layout(sg, n_levels).total);
         }
-        break;
     }
-    // tag the transient rows that live in shared memory (row_ref_pos is sorted; groups own
-    // consecutive pool slices)
-    {
-        size_t rp = 0;
-        for (int g = 0; g < G; g++) {
-            const SweepGroup &sg = plan.groups[g];
-            const int pend = sg.pool_begin + sg.pool_len;
-            for (; rp < plan.row_ref_pos.size() && plan.row_ref_pos[rp] < pend; rp++) {
-                int &ref = plan.pool[plan.row_ref_pos[rp]];
-                if ((ref & ~SCRATCH_BIT) < sg.n_rows_smem) ref |= SMEM_ROW_BIT;
-            }
-        }
-    }
-
     const double t_planned = e->host_prof ? host_now() : 0.0;
     const size_t bytes_tasks = plan.tasks.size() * sizeof(SweepTask);
     const size_t bytes_pool = plan.pool.size() * sizeof(int);

@@ -28,7 +28,7 @@ struct SweepCtx {
 __device__ __forceinline__ Tri ld_row(const SweepCtx &C, int ref)
 {
     const int idx = ref & (SMEM_ROW_BIT - 1);
-    if (ref & SMEM_ROW_BIT) {
+    if ((ref & SCRATCH_BIT) && idx < C.n_rows_smem) {
         const double *p = C.smem_lane + idx * (3 * TILE_LOCI);
         return Tri{p[0], p[TILE_LOCI], p[2 * TILE_LOCI]};
     }
@@ -38,7 +38,7 @@ __device__ __forceinline__ Tri ld_row(const SweepCtx &C, int ref)
 __device__ __forceinline__ void st_row(const SweepCtx &C, int ref, Tri v)
 {
     const int idx = ref & (SMEM_ROW_BIT - 1);
-    if (ref & SMEM_ROW_BIT) {
+    if ((ref & SCRATCH_BIT) && idx < C.n_rows_smem) {
         double *p = C.smem_lane + idx * (3 * TILE_LOCI);
         p[0] = v.x; p[TILE_LOCI] = v.y; p[2 * TILE_LOCI] = v.z;
         return;
@@ -58,7 +58,7 @@ __device__ __forceinline__ void st_persist(const SweepCtx &C, int row, Tri v)
 __device__ __forceinline__ Tri ld_t(const SweepCtx &C, int ref)
 {
     const int idx = ref & (SMEM_ROW_BIT - 1);
-    if (ref & SMEM_ROW_BIT) {
+    if (idx < C.n_rows_smem) {
         const double *p = C.smem_lane + idx * (3 * TILE_LOCI);
         return Tri{p[0], p[TILE_LOCI], p[2 * TILE_LOCI]};
     }
@@ -68,7 +68,7 @@ __device__ __forceinline__ Tri ld_t(const SweepCtx &C, int ref)
 __device__ __forceinline__ void st_t(const SweepCtx &C, int ref, Tri v)
 {
     const int idx = ref & (SMEM_ROW_BIT - 1);
-    if (ref & SMEM_ROW_BIT) {
+    if (idx < C.n_rows_smem) {
         double *p = C.smem_lane + idx * (3 * TILE_LOCI);
         p[0] = v.x; p[TILE_LOCI] = v.y; p[2 * TILE_LOCI] = v.z;
         return;
