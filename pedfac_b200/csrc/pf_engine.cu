@@ -678,7 +678,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                     w.tmp_row[m] = -1;
                     // sibships of more than one single kid park a, b and one row pair per item; the rows
                     // are written at level l and read at l + 1: two banks by the parity of l
-                    if (has_tmp(m)) { w.tmp_row[m] = cnt_t[l]; cnt_t[l] += 2 + 2 * w.it_cnt[m]; bank_t = std::max(bank_t, cnt_t[l]); }
+                    if (has_tmp(m)) { w.tmp_row[m] = cnt_t[l]; cnt_t[l] += 4 + 2 * w.it_cnt[m]; bank_t = std::max(bank_t, cnt_t[l]); }
                     for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
                         const int x = w.mem_i[k];
                         if (x == w.um[m] || w.adj_off[x + 1] - w.adj_off[x] <= 1) continue;
@@ -829,12 +829,19 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                     }
                     continue;
                 }
+                // beside FAM_DOWN, on another warp: the product of the other items' factors, per item
+                if (w.it_cnt[m] >= 2) {
+                    add_task(-(2 + w.depth_m[m]), TASK_FAM_EXCL);
+                    pool.push_back(w.it_cnt[m]);
+                    pool.push_back(w.tmp_row[m] + 4);
+                    push_item_list(m);
+                }
                 // one KID_CHUNK task per item on the next level
                 for (int it = w.it_off[m], i = 0; it < w.it_off[m] + w.it_cnt[m]; it++, i++) {
                     add_task(-(2 + w.depth_m[m] + 1), TASK_KID_CHUNK);
                     pool.push_back(flags);
                     pool.push_back(w.tmp_row[m]);
-                    pool.push_back(w.tmp_row[m] + 2 + 2 * i);
+                    pool.push_back(w.it_cnt[m] >= 2 ? w.tmp_row[m] + 4 + 2 * i : -1);
                     pool.push_back(w.it_n[it]);
                     for (int j = 0; j < w.it_n[it]; j++) {
                         const int x = w.mem_i[w.it_kids[w.it_first[it] + j]];

@@ -283,8 +283,10 @@ __device__ __forceinline__ void put_down(const SweepCtx &C, const int *ent, Tri 
 //           pa{ref, stub_row, dn_row}, ma{ref, stub_row, dn_row}, n_items, tmp_row, item[n_items]
 //           (+ stub_row, dn_row of the kid when the sibship is one single kid: tmp_row = -1)
 //   pa.ref / ma.ref = NO_REF when that parent is the up individual (or selfing mother);
-//   tmp_row = first of 2 + 2 * n_items bank rows: a, b, then per item the product of everything
-//   OUTSIDE that item, which the item's KID_CHUNK task on the next level turns into messages
+//   tmp_row = first of 4 + 2 * n_items bank rows: a, b, Pu (the factor of the up individual when it
+//   is a kid of the marriage, else ones; 2 rows), then per item the product of the OTHER items'
+//   factors, which a FAM_EXCL task computes on another warp at the same level; the items'
+//   KID_CHUNK tasks on the next level turn them into messages
 __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
 {
     const int flags = t[0], selfing = flags & 1, urole = flags >> 1, nSib = t[4];
@@ -300,33 +302,41 @@ __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
     Sym3 Pu = sym_ones();
     if (urole == 2) sym_mul(Pu, kid_matrix(in_u));
 
+    Sym3 Pall = Pu;
     if (tmp < 0) {
         // no down kid, or one single kid: finished here
-        Sym3 Pall = Pu;
         Tri kmsg = one;
         if (n_items) { kmsg = up_msg(C, item[1]); sym_mul(Pall, kid_matrix(kmsg)); }
-        st_persist(C, t[1], fam_to_kid(Pall, a, b, selfing));                 // prong
-        if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(Pall, b, selfing));
-        if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(Pall, a, 0));
         if (n_items) put_down(C, item + 1, kmsg, fam_to_kid(Pu, a, b, selfing));   // item + 1 = {ref, stub_row, dn_row}
-        return;
+    } else {
+        st_i(C, tmp, a);
+        st_i(C, tmp + 1, b);
+        st_i(C, tmp + 2, Tri{Pu.a00, Pu.a01, Pu.a02});
+        st_i(C, tmp + 3, Tri{Pu.a11, Pu.a12, Pu.a22});
+        for (int i = 0; i < n_items; i++) sym_mul(Pall, item_factor(C, item + 2 * i));
     }
-    // park a, b and, per item, the product of all factors outside it (exclusive prefix x suffix)
-    st_i(C, tmp, a);
-    st_i(C, tmp + 1, b);
-    Sym3 run = Pu;
+    st_persist(C, t[1], fam_to_kid(Pall, a, b, selfing));                     // prong
+    if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(Pall, b, selfing));
+    if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(Pall, a, 0));
+}
+
+// FAM_EXCL: n_items (>= 2), out_row, item[n_items] — for every item the product of the factors of
+//   all OTHER items (exclusive prefix x exclusive suffix), left in rows out_row + 2 i, + 2 i + 1.
+//   Independent of the messages from above, so it runs beside FAM_DOWN instead of inside it.
+__device__ __forceinline__ void task_fam_excl(const SweepCtx &C, const int *t)
+{
+    const int n_items = t[0], out = t[1];
+    const int *item = t + 2;
+    Sym3 run = sym_ones();
     for (int i = 0; i < n_items; i++) {
-        const int r = tmp + 2 + 2 * i;
+        const int r = out + 2 * i;
         st_i(C, r, Tri{run.a00, run.a01, run.a02});
         st_i(C, r + 1, Tri{run.a11, run.a12, run.a22});
-        sym_mul(run, item_factor(C, item + 2 * i));
+        if (i + 1 < n_items) sym_mul(run, item_factor(C, item + 2 * i));
     }
-    st_persist(C, t[1], fam_to_kid(run, a, b, selfing));                      // prong: run = all kids now
-    if (urole != 0 && pa[0] != NO_REF) put_down(C, pa, a, fam_to_pa(run, b, selfing));
-    if (urole != 1 && ma[0] != NO_REF) put_down(C, ma, b, fam_to_pa(run, a, 0));
-    Sym3 suf = sym_ones();
-    for (int i = n_items - 1; i >= 0; i--) {
-        const int r = tmp + 2 + 2 * i;
+    Sym3 suf = item_factor(C, item + 2 * (n_items - 1));
+    for (int i = n_items - 2; i >= 0; i--) {
+        const int r = out + 2 * i;
         const Tri p0 = ld_i(C, r), p1 = ld_i(C, r + 1);
         st_i(C, r, Tri{p0.x * suf.a00, p0.y * suf.a01, p0.z * suf.a02});
         st_i(C, r + 1, Tri{p1.x * suf.a11, p1.y * suf.a12, p1.z * suf.a22});
@@ -334,15 +344,19 @@ __device__ __forceinline__ void task_fam_down(const SweepCtx &C, const int *t)
     }
 }
 
-// KID_CHUNK: flags, ab_row (a at ab_row, b at ab_row + 1), out_row (outside product, 2 rows), n,
-//            { up_ref, stub_row, dn_row (-1 = not needed) } * n            (n <= FAM_CHUNK kids)
+// KID_CHUNK: flags, ab_row (a, b, Pu at ab_row .. ab_row + 3), out_row (product of the other items, 2 rows;
+//            -1 = the only item), n, { up_ref, stub_row, dn_row (-1 = not needed) } * n   (n <= FAM_CHUNK kids)
 __device__ __forceinline__ void task_kid_chunk(const SweepCtx &C, const int *t)
 {
     const int selfing = t[0] & 1, n = t[3];
     const int ab = t[1], orow = t[2];
     const Tri a = ld_i(C, ab), b = ld_i(C, ab + 1);
-    const Tri p0 = ld_i(C, orow), p1 = ld_i(C, orow + 1);
-    const Sym3 Pout{p0.x, p0.y, p0.z, p1.x, p1.y, p1.z};
+    const Tri u0 = ld_i(C, ab + 2), u1 = ld_i(C, ab + 3);
+    Sym3 Pout{u0.x, u0.y, u0.z, u1.x, u1.y, u1.z};
+    if (orow >= 0) {
+        const Tri p0 = ld_i(C, orow), p1 = ld_i(C, orow + 1);
+        sym_mul(Pout, Sym3{p0.x, p0.y, p0.z, p1.x, p1.y, p1.z});
+    }
     const int *mem = t + 4;
     Tri km[FAM_CHUNK];
 #pragma unroll
@@ -458,6 +472,7 @@ __global__ void __launch_bounds__(SWEEP_WARPS * 32, MIN_BLOCKS) sweep_kernel(con
             case TASK_FAM_UP: task_fam_up(C, t); break;
             case TASK_FAM_DOWN: task_fam_down(C, t); break;
             case TASK_KID_CHUNK: task_kid_chunk(C, t); break;
+            case TASK_FAM_EXCL: task_fam_excl(C, t); break;
             default: task_kfold(C, t); break;
             }
         }

@@ -46,7 +46,7 @@ namespace pf {
 // member = role | founder << 2 | (group-local genotype entry index) << 3; roles: 0 father,
 // 1 mother, 2 kid. flags = selfing | (role of u(m) in m) << 1.
 //   KID_CHUNK (large sibships; next level): flags, ab_row, outside_row, n, { up_ref, stub_row, dn_row } * n
-enum TaskKind : int { TASK_ROOT = 0, TASK_LEAF_IN = 1, TASK_FAM_UP = 2, TASK_FAM_DOWN = 3, TASK_KID_CHUNK = 4, TASK_KFOLD = 5 };
+enum TaskKind : int { TASK_ROOT = 0, TASK_LEAF_IN = 1, TASK_FAM_UP = 2, TASK_FAM_DOWN = 3, TASK_KID_CHUNK = 4, TASK_KFOLD = 5, TASK_FAM_EXCL = 6 };
 constexpr int NO_REF = 0x1fffffff;
 #ifndef PF_FAM_CHUNK
 #define PF_FAM_CHUNK 3
