@@ -400,7 +400,7 @@ static DevView dev_view(pf_engine *e)
 
 namespace {
 
-struct PlanTask { int group, level, kind, off; };
+struct PlanTask { int group, level, kind, off, cost; };     // cost: rough instruction count, orders the tasks of a crowded level
 
 struct Plan {
     std::vector<PlanTask> tasks;
@@ -438,7 +438,8 @@ struct ViewWork {           // scratch vectors reused across calls
     std::vector<int> bfs_m, queue, cnt_a, cnt_b, cnt_c, tmp_row;
     std::vector<char> vis_i, vis_m, label_seen, in_chunk;
     std::vector<int> roots, comp_members_end, order_i, q;    // BFS order of individuals per component
-    std::vector<int> level_off, start;
+    std::vector<int> level_off, start, cost_of;
+    std::vector<std::pair<int, SweepTask>> sort_tmp;
     std::vector<int> it_off, it_cnt, it_type, it_first, it_n, it_kids, it_prow;   // sibship items per marriage (see item_factor)
 };
 
@@ -739,10 +740,10 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 else pool.push_back((int)(LEAF_REF_BIT | (unsigned)member(x, role)));
             };
             hp_mark(3);
-            auto add_task = [&](int level, int kind) { plan.tasks.push_back(PlanTask{gid, level, kind, (int)pool.size()}); G.task_end++; };
+            auto add_task = [&](int level, int kind, int cost) { plan.tasks.push_back(PlanTask{gid, level, kind, (int)pool.size(), cost}); G.task_end++; };
             // levels: >= 0 = up band; -1 = first level of the down band; -(2 + k) = down band level k
             const bool has_m = w.adj_off[r + 1] > w.adj_off[r];
-            add_task(has_m ? -1 : 0, TASK_ROOT);
+            add_task(has_m ? -1 : 0, TASK_ROOT, 8);
             pool.push_back(member(r, 0));
             if (up_only) push_row(SCRATCH_BIT | G.n_rows++);        // nothing persisted: the root's belief goes to a transient row
             else pool.push_back(e->stub_row(chain, v->indiv[r]));
@@ -753,7 +754,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 const int i = order_i[oi];
                 const bool leaf = w.adj_off[i + 1] - w.adj_off[i] <= 1;
                 if (!leaf || w.up_i_row[i] < 0) continue;
-                add_task(0, TASK_LEAF_IN);
+                add_task(0, TASK_LEAF_IN, 5);
                 pool.push_back(member(i, 0)); push_row(w.up_i_row[i]);
             }
             // chunk products, also at level 0
@@ -761,7 +762,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 const int m = w.bfs_m[b];
                 for (int it = w.it_off[m]; it < w.it_off[m] + w.it_cnt[m]; it++) {
                     if (w.it_type[it] != 1) continue;
-                    add_task(0, TASK_KFOLD);
+                    add_task(0, TASK_KFOLD, 4 + 6 * w.it_n[it]);
                     pool.push_back(w.it_prow[it]); pool.push_back(w.it_n[it]);
                     for (int j = 0; j < w.it_n[it]; j++) push_up_i(w.mem_i[w.it_kids[w.it_first[it] + j]], 2);
                 }
@@ -780,7 +781,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 const int u = w.um[m];
                 int nd = 0;
                 for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) if (w.mem_i[k] != u) nd++;
-                add_task(1 + w.lvlA[m], TASK_FAM_UP);
+                add_task(1 + w.lvlA[m], TASK_FAM_UP, 10 + 4 * nd + 3 * w.it_cnt[m]);
                 pool.push_back(flags); push_row(w.up_m_row[m]);
                 {
                     const size_t nc_at = pool.size(); pool.push_back(0);
@@ -805,7 +806,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 pool.push_back(w.it_cnt[m]);
                 push_item_list(m);
                 if (up_only) continue;                              // log Z only: no down band
-                add_task(-(2 + w.depth_m[m]), TASK_FAM_DOWN);
+                add_task(-(2 + w.depth_m[m]), TASK_FAM_DOWN, 24 + 3 * w.it_cnt[m]);
                 pool.push_back(flags); pool.push_back(e->prong_row(chain, v->marr[m]));
                 pool.push_back(member(u, w.urole[m]));
                 if (w.Ui[u] < 0) pool.push_back(-1); else push_row(w.dn_row[u]);
@@ -831,14 +832,14 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
                 }
                 // beside FAM_DOWN, on another warp: the product of the other items' factors, per item
                 if (w.it_cnt[m] >= 2) {
-                    add_task(-(2 + w.depth_m[m]), TASK_FAM_EXCL);
+                    add_task(-(2 + w.depth_m[m]), TASK_FAM_EXCL, 4 + 8 * w.it_cnt[m]);
                     pool.push_back(w.it_cnt[m]);
                     pool.push_back(w.tmp_row[m] + 4);
                     push_item_list(m);
                 }
                 // one KID_CHUNK task per item on the next level
                 for (int it = w.it_off[m], i = 0; it < w.it_off[m] + w.it_cnt[m]; it++, i++) {
-                    add_task(-(2 + w.depth_m[m] + 1), TASK_KID_CHUNK);
+                    add_task(-(2 + w.depth_m[m] + 1), TASK_KID_CHUNK, 6 + 12 * w.it_n[it]);
                     pool.push_back(flags);
                     pool.push_back(w.tmp_row[m]);
                     pool.push_back(w.it_cnt[m] >= 2 ? w.tmp_row[m] + 4 + 2 * i : -1);
@@ -997,9 +998,25 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     void *hp = nullptr; int slot = 0;
     CU(e->staging.get(blob, &hp, &slot));
     SweepTask *ht = static_cast<SweepTask *>(hp);
-    for (auto &t : plan.tasks) {
-        const int pos = start[(size_t)t.group * n_levels + t.level]++;
-        ht[pos].kind = t.kind; ht[pos].off = t.off;
+    {
+        std::vector<int> &cost = g_work.cost_of;
+        cost.resize(plan.tasks.size());
+        for (auto &t : plan.tasks) {
+            const int pos = start[(size_t)t.group * n_levels + t.level]++;
+            ht[pos].kind = t.kind; ht[pos].off = t.off; cost[pos] = t.cost;
+        }
+        // a level with more tasks than warps runs in rounds (warp w takes tasks w, w + warps, ...):
+        // longest first, so that the last round holds the short ones
+        std::vector<std::pair<int, SweepTask>> &tmp = g_work.sort_tmp;
+        for (int g = 0; g < G; g++)
+            for (int l = 0; l < n_levels; l++) {
+                const int b0 = level_off[(size_t)g * (n_levels + 1) + l], b1 = level_off[(size_t)g * (n_levels + 1) + l + 1];
+                if (b1 - b0 <= shape.warps) continue;
+                tmp.clear();
+                for (int k = b0; k < b1; k++) tmp.push_back({cost[k], ht[k]});
+                std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, SweepTask> &x, const std::pair<int, SweepTask> &y) { return x.first > y.first; });
+                for (int k = b0; k < b1; k++) ht[k] = tmp[k - b0].second;
+            }
     }
     memcpy(static_cast<char *>(hp) + off_pool, plan.pool.data(), bytes_pool);
     memcpy(static_cast<char *>(hp) + off_loff, level_off.data(), bytes_loff);
