@@ -36,7 +36,6 @@ int main(int argc, char **argv)
     }
     e->host_prof = true; e->n_prof_calls = 1000;
     for (int r = 0; r < 100; r++) for (auto &x : vs) { plan.reset(); plan.target_tasks_per_group = 256; int mu = 0; plan_add_view(e, &x.v, 0, 0, plan, mu, false, SWEEP_LATENCY); }
-    printf("sub: items %.1f dn/tmp rows %.1f up_i+emis %.1f rest(3) %.1f\n", 1e6*e->t_ph[5]/(100*vs.size()), 1e6*e->t_ph[6]/(100*vs.size()), 1e6*e->t_ph[7]/(100*vs.size()), 1e6*e->t_ph[3]/(100*vs.size()));
     printf("phases us: adjacency %.1f traversals %.1f heights %.1f rows+items+emis %.1f emission %.1f\n", 1e6*e->t_ph[0]/(100*vs.size()), 1e6*e->t_ph[1]/(100*vs.size()), 1e6*e->t_ph[2]/(100*vs.size()), 1e6*e->t_ph[3]/(100*vs.size()), 1e6*e->t_ph[4]/(100*vs.size()));
     printf("plan_add_view: %.1f us per view (best of %d), last plan: %zu tasks %zu pool ints %zu emis\n", best, reps, plan.tasks.size(), plan.pool.size(), plan.emis.size());
     return 0;
