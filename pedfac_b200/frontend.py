@@ -11,10 +11,12 @@ from .synth import SynthData
 
 
 def write_run_dir(data: SynthData, run_dir, *, max_unobs: int = 1, min_age: float = 1.0, max_age: float = 1.0,
-                  observe_frac: float = 0.8, max_gen: int = 0, seeds=(2590, 7579545), loci=None):
+                  observe_frac: float = 0.8, max_gen: int = 0, seeds=(2590, 7579545), loci=None, seed_marriages: bool = False):
     """Writes run_dir/{geno.txt, prior.txt, rand}. Only observed individuals are listed (ids 1..n
     in slot order); `gen` is the generation index (0 = youngest), founders are the oldest observed
-    generation when max_gen == 0 (R/renderGeno.R:84-86)."""
+    generation when max_gen == 0 (R/renderGeno.R:84-86). With `seed_marriages` the optional
+    marriage.txt (`kid pa ma` rows by user id; `nMar` = number of couples) seeds the chain with the
+    true trios whose three members are all observed."""
     run = Path(run_dir)
     run.mkdir(parents=True, exist_ok=True)
     sl = slice(None) if loci is None else slice(0, loci)
@@ -37,10 +39,17 @@ def write_run_dir(data: SynthData, run_dir, *, max_unobs: int = 1, min_age: floa
             else:
                 toks = tbl[data.codes[i, sl]]
             f.write(f"{rank + 1} 1 {int(data.sex[i])} {int(data.gen[i])} {founder} " + " ".join(toks.tolist()) + "\n")
+    n_mar = 0
+    if seed_marriages:
+        uid = {int(i): k + 1 for k, i in enumerate(order)}
+        rows = [(uid[int(i)], uid[int(data.pa[i])], uid[int(data.ma[i])]) for i in order
+                if data.pa[i] >= 0 and int(data.pa[i]) in uid and int(data.ma[i]) in uid]
+        n_mar = len({(p_, m_) for _, p_, m_ in rows})
+        (run / "marriage.txt").write_text("".join(f"{k} {p_} {m_}\n" for k, p_, m_ in rows))
     obs_frac = np.zeros(n_gen)
     obs_frac[np.unique(data.gen[obs])] = observe_frac
     with open(run / "prior.txt", "w") as f:
-        f.write(f"nIndiv {len(order)}\nnObsIndiv {len(order)}\nnGen {n_gen}\nnSNP {S}\nnMar 0\nmaxID {len(order) + 1}\n")
+        f.write(f"nIndiv {len(order)}\nnObsIndiv {len(order)}\nnGen {n_gen}\nnSNP {S}\nnMar {n_mar}\nmaxID {len(order) + 1}\n")
         f.write("aFreq " + " ".join(f"{a:g}" for a in data.afreq[sl]) + "\n")
         f.write("epsilon " + " ".join(f"{e:g}" for e in data.eps[sl]) + "\n")
         f.write("obsFrac " + " ".join(f"{x:g}" for x in np.round(obs_frac, 3)) + "\n")

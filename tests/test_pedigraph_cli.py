@@ -33,9 +33,9 @@ def swap_counts(stderr):
     return prop, pick
 
 
-def make_run(tmp_path, name, n=80, S=60, soft=False, seed=46, seeds=(2590, 7579545)):
+def make_run(tmp_path, name, n=80, S=60, soft=False, seed=46, seeds=(2590, 7579545), seed_marriages=False):
     d = synth.simulate(n, S, soft=soft, seed=seed)
-    order = frontend.write_run_dir(d, tmp_path / name, seeds=seeds)
+    order = frontend.write_run_dir(d, tmp_path / name, seeds=seeds, seed_marriages=seed_marriages)
     return d, order, tmp_path / name
 
 
@@ -120,6 +120,43 @@ def test_swap_moves_are_scored_consistently_and_can_be_disabled(tmp_path):
     assert swap_counts(r2.stderr) == (0, 0)
     assert len((rd2 / "out" / "ped.txt").read_text().splitlines()) == len((rd2 / "out" / "ll.txt").read_text().splitlines())
     assert (rd / "out" / "ped.txt").read_text() != (rd2 / "out" / "ped.txt").read_text()
+
+
+def test_marriage_file_seeds_the_chain(tmp_path):
+    """Optional marriage.txt (`kid pa ma` rows by user id, nMar couples in prior.txt;
+    _ReadPedfile@0x10000b7b0): the chain starts from that pedigree instead of all singletons."""
+    d, order, rd = make_run(tmp_path, "m1", n=200, S=120, seed_marriages=True)
+    _, _, rd0 = make_run(tmp_path, "m0", n=200, S=120)
+    assert (rd / "marriage.txt").exists() and not (rd0 / "marriage.txt").exists()
+    env = {"PEDFAC_STATS": "1", "PEDFAC_CHECK": "1"}
+    r, r0 = run(REF, rd, n_iter=2, env=env), run(REF, rd0, n_iter=2, env=env)
+    assert r.returncode == 0 and r0.returncode == 0, r.stderr[-1000:]
+    assert "optional marriage.txt is not found" in r0.stdout and "optional marriage.txt is not found" not in r.stdout
+    # the seeded start has families already: another initial log-likelihood (kids without parents carry
+    # no prior at all, so it is lower) and swap proposals from iteration 0 on
+    prior = lambda out: float(re.search(r"prior: (-?[\d.]+)", out).group(1))
+    assert prior(r.stdout) < prior(r0.stdout)
+    first = lambda err: dict(zip(*[iter(err.splitlines()[[l.startswith("pedigraph-stats") for l in err.splitlines()].index(True)].split()[1:])] * 2))
+    assert int(first(r.stderr)["swaps"]) > 0 and int(first(r0.stderr)["swaps"]) == 0
+    bad = tmp_path / "mbad"
+    frontend.write_run_dir(d, bad, seed_marriages=True)
+    (bad / "prior.txt").write_text((bad / "prior.txt").read_text().replace("nMar ", "nMar 1"))
+    rb = run(REF, bad, n_iter=1)
+    assert rb.returncode != 0 and "doesn't match up with nMar" in rb.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("soft", [False, True])
+def test_gpu_sampler_reproduces_the_cpu_trace_from_a_seeded_pedigree(tmp_path, soft):
+    d, order, rd = make_run(tmp_path, "gm", n=220, S=150, soft=soft, seed_marriages=True)
+    _, _, rd2 = make_run(tmp_path, "hm", n=220, S=150, soft=soft, seed_marriages=True)
+    env = {"PEDFAC_STATS": "1", "PEDFAC_CHECK": "1"}
+    rg, rc = run(GPU, rd, n_iter=3, env=env), run(REF, rd2, n_iter=3, env=env)
+    assert rg.returncode == 0, rg.stderr
+    assert rc.returncode == 0, rc.stderr
+    assert (rd / "out" / "ped.txt").read_text() == (rd2 / "out" / "ped.txt").read_text()
+    a = np.loadtxt(rd / "out" / "ll.txt"); b = np.loadtxt(rd2 / "out" / "ll.txt")
+    np.testing.assert_allclose(a[:, 2], b[:, 2], rtol=1e-9, atol=2e-6)
 
 
 @pytest.mark.gpu
