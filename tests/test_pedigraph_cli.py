@@ -177,3 +177,29 @@ def test_gpu_sampler_reproduces_the_cpu_trace(tmp_path, soft):
     np.testing.assert_allclose(a[:, 2], b[:, 2], rtol=1e-9, atol=2e-6)
     pg = float(re.search(r"prior: (-?[\d.]+)", rg.stdout).group(1)); pc = float(re.search(r"prior: (-?[\d.]+)", rc.stdout).group(1))
     assert abs(pg - pc) <= 1e-9 * abs(pc) + 2e-6
+
+
+@pytest.mark.gpu
+def test_gpu_sampler_trace_parity_with_other_priors(tmp_path):
+    """Two unobserved layers, a two-generation age window and a lower observed fraction: more
+    unobserved parents are created and trimmed, more candidates per step."""
+    d = synth.simulate(240, 140, soft=True, seed=9, observe_frac=0.6)
+    outs = []
+    for name, binary in (("g", GPU), ("c", REF)):
+        rd = tmp_path / name
+        frontend.write_run_dir(d, rd, seeds=(31, 77), max_unobs=2, min_age=1.0, max_age=2.0, observe_frac=0.5)
+        r = run(binary, rd, n_iter=3, env={"PEDFAC_STATS": "1", "PEDFAC_CHECK": "1"})
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(((rd / "out" / "ped.txt").read_text(), np.loadtxt(rd / "out" / "ll.txt")))
+    assert outs[0][0] == outs[1][0]
+    np.testing.assert_allclose(outs[0][1][:, 2], outs[1][1][:, 2], rtol=1e-9, atol=2e-6)
+
+
+def test_other_priors_run_consistently_on_the_cpu(tmp_path):
+    d = synth.simulate(160, 90, soft=False, seed=9, observe_frac=0.6)
+    rd = tmp_path / "p"
+    frontend.write_run_dir(d, rd, seeds=(31, 77), max_unobs=2, min_age=1.0, max_age=2.0, observe_frac=0.5)
+    r = run(REF, rd, n_iter=3, env={"PEDFAC_STATS": "1", "PEDFAC_CHECK": "1"})
+    assert r.returncode == 0, r.stderr[-1500:]
+    rows = np.loadtxt(rd / "out" / "ped.txt", dtype=int)
+    assert (rows[:, 1] > len(np.flatnonzero(d.observed))).any()        # unobserved individuals get sampled too
