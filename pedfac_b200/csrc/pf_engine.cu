@@ -13,6 +13,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace pf;
@@ -452,8 +453,9 @@ static thread_local ViewWork g_work;
 // The band offset is fixed up by the caller once every view has been added. While a group is
 // being filled, SweepGroup::task_end counts its tasks and n_rows / emis_count its transient rows
 // and genotype entries.
-static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only, const SweepShape &shape)
+static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only, const SweepShape &shape, int *loc = nullptr)
 {
+    if (!loc) loc = e->loc.data();
     if (!v) return fail(PF_EINVAL, "null view");
     const int nI = v->n_indiv, nM = v->n_marr;
     if (nI < 0 || nM < 0 || v->n_cc < 0) return fail(PF_EINVAL, "negative count in view");
@@ -470,9 +472,9 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
     // slot -> local index
     for (int i = 0; i < nI; i++) {
         const int slot = v->indiv[i];
-        if (slot < 0 || slot >= e->cfg.cap_indiv || e->loc[slot] != -1) { rc = fail(PF_EINVAL, "bad or duplicate individual slot %d in view", slot); goto cleanup; }
+        if (slot < 0 || slot >= e->cfg.cap_indiv || loc[slot] != -1) { rc = fail(PF_EINVAL, "bad or duplicate individual slot %d in view", slot); goto cleanup; }
         if (v->indiv_cc[i] < 0 || v->indiv_cc[i] >= v->n_cc) { rc = fail(PF_EINVAL, "component label %d of slot %d outside [0,%d)", v->indiv_cc[i], slot, v->n_cc); goto cleanup; }
-        e->loc[slot] = i;
+        loc[slot] = i;
         registered = i + 1;
     }
     {
@@ -487,10 +489,10 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             for (int ed = 0; ed < ne; ed++) {
                 if (ed == 1 && v->marr_selfing[j]) continue;
                 const int slot = ed == 0 ? v->marr_pa[j] : ed == 1 ? v->marr_ma[j] : v->marr_kids[kb + ed - 2];
-                if (slot < 0 || slot >= e->cfg.cap_indiv || e->loc[slot] < 0) { rc = fail(PF_EINVAL, "view not closed: marriage %d references unlisted individual %d", v->marr[j], slot); goto cleanup; }
-                w.mem_i.push_back(e->loc[slot]);
+                if (slot < 0 || slot >= e->cfg.cap_indiv || loc[slot] < 0) { rc = fail(PF_EINVAL, "view not closed: marriage %d references unlisted individual %d", v->marr[j], slot); goto cleanup; }
+                w.mem_i.push_back(loc[slot]);
                 w.mem_role.push_back(ed < 2 ? ed : 2);
-                w.adj_off[e->loc[slot] + 1]++;
+                w.adj_off[loc[slot] + 1]++;
             }
             w.mem_off[j + 1] = (int)w.mem_i.size();
         }
@@ -857,7 +859,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         }
     }
 cleanup:
-    for (int i = 0; i < registered; i++) e->loc[v->indiv[i]] = -1;
+    for (int i = 0; i < registered; i++) loc[v->indiv[i]] = -1;
     return rc;
 }
 
@@ -928,10 +930,47 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     std::vector<int> &level_off = g_work.level_off, &start = g_work.start;
     {
         int out_base = 0;
-        for (int i = 0; i < n; i++) {
-            rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up, up_only, shape);
-            if (rc) return rc;
-            out_base += views[i].n_cc;
+        if (n >= 16) {
+            // a batch of chains: the views are planned by a few threads (each with its own work
+            // buffers and slot map) and the partial plans are concatenated; 64 plans of ~50 us each
+            // built one after the other made the batched sweeps host-bound
+            const int T = (int)std::min<unsigned>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), (unsigned)n / 4u);
+            std::vector<int> bases(n + 1, 0);
+            for (int i = 0; i < n; i++) bases[i + 1] = bases[i] + std::max(views[i].n_cc, 0);
+            struct Part { Plan plan; int max_up = 0, rc = PF_OK; std::string err; };
+            std::vector<Part> parts(T);
+            std::vector<std::thread> th;
+            const int target = plan.target_tasks_per_group;
+            for (int t = 0; t < T; t++)
+                th.emplace_back([&, t]() {
+                    static thread_local std::vector<int> tl_loc;
+                    if ((int)tl_loc.size() < e->cfg.cap_indiv) tl_loc.assign(e->cfg.cap_indiv, -1);
+                    Part &P = parts[t];
+                    P.plan.target_tasks_per_group = target;
+                    const int i0 = (int)((long long)n * t / T), i1 = (int)((long long)n * (t + 1) / T);
+                    for (int i = i0; i < i1 && P.rc == PF_OK; i++) {
+                        P.rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, bases[i], P.plan, P.max_up, up_only, shape, tl_loc.data());
+                        if (P.rc) P.err = g_err;
+                    }
+                });
+            for (auto &x : th) x.join();
+            for (int t = 0; t < T; t++) {
+                Part &P = parts[t];
+                if (P.rc) return fail(P.rc, "%s", P.err.c_str());
+                const int gb = (int)plan.groups.size(), pb = (int)plan.pool.size(), eb = (int)plan.emis.size();
+                for (auto &tk : P.plan.tasks) plan.tasks.push_back(PlanTask{tk.group + gb, tk.level, tk.kind, tk.off + pb, tk.cost});
+                for (auto &sg : P.plan.groups) { SweepGroup g2 = sg; g2.pool_begin += pb; g2.emis_begin += eb; plan.groups.push_back(g2); }
+                plan.pool.insert(plan.pool.end(), P.plan.pool.begin(), P.plan.pool.end());
+                plan.emis.insert(plan.emis.end(), P.plan.emis.begin(), P.plan.emis.end());
+                max_up = std::max(max_up, P.max_up);
+            }
+            out_base = bases[n];
+        } else {
+            for (int i = 0; i < n; i++) {
+                rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, plan, max_up, up_only, shape);
+                if (rc) return rc;
+                out_base += views[i].n_cc;
+            }
         }
         plan.n_out = out_base;
         *n_out_total = out_base;

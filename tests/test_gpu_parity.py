@@ -379,3 +379,31 @@ def test_gpu_results_without_the_mailbox_are_identical(monkeypatch):
     others = [int(i) for i in np.flatnonzero(sc.ped.active) if labels[i] != labels[kid]]
     props = [(PF_PROP_TRIO, c, -1, -1) for c in others[:20]]
     np.testing.assert_array_equal(a.eval(kid, props), b.eval(kid, props))
+
+
+def test_gpu_large_chain_batch_is_planned_in_parallel_and_matches_the_oracle():
+    """24 chains with different graphs in one sweep_batch call: the views are planned by several
+    host threads and the partial plans concatenated; every chain must match its own oracle, and a
+    bad view anywhere in the batch must still be reported."""
+    n_ch = 24
+    scs = [random_forest(np.random.default_rng(700 + c), n_indiv=40, S=70, max_kids=4) for c in range(n_ch)]
+    base = scs[0]
+    cap_i = max(s.ped.cap_indiv for s in scs); cap_m = max(s.ped.cap_marr for s in scs)
+    g = Engine(base.S, cap_i, cap_m, n_chains=n_ch)
+    base.upload(g)
+    o = OracleEngine(base.S, cap_i, cap_m)
+    base.upload(o)
+    views = [sc.ped.view()[0] for sc in scs]
+    got = g.sweep_batch(list(range(n_ch)), views)
+    want = np.concatenate([o.sweep(v) for v in views])
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-11)
+    for c in (0, 11, 23):
+        o.sweep(views[c])
+        for i in np.flatnonzero(scs[c].ped.active)[::5]:
+            np.testing.assert_allclose(g.get_stub(int(i), chain=c), o.get_stub(int(i)), rtol=1e-12)
+    bad = scs[17].ped.copy()
+    m0 = next(iter(bad.marriages)); mm = bad.marriages[m0]
+    bad.add_marriage(max(bad.marriages) + 1, mm.pa, mm.ma, [mm.kids[0]])      # a second marriage through the same three: a loop
+    views[17] = bad.view()[0]
+    with pytest.raises(PedfacError):
+        g.sweep_batch(list(range(n_ch)), views)
