@@ -204,6 +204,18 @@ int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kid
                  const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
                  const double *cand_bias, int32_t top_k, int32_t *out_slot, double *out_score);
 
+/* pf_prefilter in two halves for engines that hold a locus shard: every shard writes
+ * its dense partial scores [n_kids][n_cands] (sum over its loci; cand_bias is added as given — pass it
+ * on one shard only, NULL on the others) to device memory on the engine's stream, the caller sums
+ * them over the shards (NCCL all-reduce), and any shard ranks the sums. scores_dev is overwritten by
+ * the ranking. */
+int pf_prefilter_scores_dev(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                            const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
+                            const double *cand_bias, double *scores_dev);
+int pf_prefilter_topk_dev(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                          int32_t n_cands, const int32_t *cands, double *scores_dev, int32_t top_k,
+                          int32_t *out_slot, double *out_score);
+
 /* Read-back of persisted per-locus results (tests, debugging): out[s][3] for this engine's loci. */
 int pf_get_stub(pf_engine *e, int32_t chain, int32_t slot, double *out);
 int pf_get_prong(pf_engine *e, int32_t chain, int32_t marr, double *out);

@@ -812,6 +812,47 @@ int pfo_prefilter(pfo_engine *e, int32_t chain, int32_t n_kids, const int32_t *k
     return PF_OK;
 }
 
+/* the two halves of pfo_prefilter for locus shards: dense partial scores (host memory here), then
+ * the ranking of the summed scores with the same tie rule (earlier candidate first; the kid itself
+ * is never a candidate) */
+int pfo_prefilter_scores_dev(pfo_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                             const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
+                             const double *cand_bias, double *scores)
+{
+    if (!e || (n_kids > 0 && (!kids || !as_father)) || (n_cands > 0 && !cands) || (n_kids > 0 && n_cands > 0 && !scores)) FAIL(PF_EINVAL, "bad argument");
+    for (int k = 0; k < n_kids; k++)
+        for (int c = 0; c < n_cands; c++) {
+            pf_proposal pr = { PF_PROP_TRIO, -1, -1, -1 };
+            if (as_father[k]) pr.pa = cands[c]; else pr.ma = cands[c];
+            double v = 0.0;
+            if (cands[c] != kids[k]) { int rc = pfo_eval(e, chain, kids[k], 1, &pr, &v); if (rc) return rc; }
+            scores[(size_t)k * n_cands + c] = cand_bias ? v + cand_bias[c] : v;
+        }
+    return PF_OK;
+}
+
+int pfo_prefilter_topk_dev(pfo_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                           int32_t n_cands, const int32_t *cands, double *scores, int32_t top_k,
+                           int32_t *out_slot, double *out_score)
+{
+    (void)chain;
+    if (!e || (n_kids > 0 && (!kids || !out_slot || !out_score)) || (n_cands > 0 && (!cands || !scores)) || top_k <= 0) FAIL(PF_EINVAL, "bad argument");
+    for (int k = 0; k < n_kids; k++) {
+        for (int t = 0; t < top_k; t++) { out_slot[k * top_k + t] = -1; out_score[k * top_k + t] = -INFINITY; }
+        for (int c = 0; c < n_cands; c++) {
+            if (cands[c] == kids[k]) continue;
+            const double v = scores[(size_t)k * n_cands + c];
+            int pos = top_k;
+            while (pos > 0 && (out_slot[k * top_k + pos - 1] == -1 || v > out_score[k * top_k + pos - 1])) pos--;
+            if (pos < top_k) {
+                for (int t = top_k - 1; t > pos; t--) { out_slot[k * top_k + t] = out_slot[k * top_k + t - 1]; out_score[k * top_k + t] = out_score[k * top_k + t - 1]; }
+                out_slot[k * top_k + pos] = cands[c]; out_score[k * top_k + pos] = v;
+            }
+        }
+    }
+    return PF_OK;
+}
+
 int pfo_get_stub(pfo_engine *e, int32_t chain, int32_t slot, double *out)
 {
     (void)chain;

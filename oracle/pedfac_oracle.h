@@ -47,6 +47,13 @@ int pfo_eval_swaps(pfo_engine *e, int32_t chain, const pf_graph_view *view, int3
 int pfo_prefilter(pfo_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
                   const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
                   const double *cand_bias, int32_t top_k, int32_t *out_slot, double *out_score);
+/* the oracle has no device: the *_dev pointers are host pointers here */
+int pfo_prefilter_scores_dev(pfo_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                             const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
+                             const double *cand_bias, double *scores);
+int pfo_prefilter_topk_dev(pfo_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                           int32_t n_cands, const int32_t *cands, double *scores, int32_t top_k,
+                           int32_t *out_slot, double *out_score);
 int pfo_get_stub(pfo_engine *e, int32_t chain, int32_t slot, double *out);
 int pfo_get_prong(pfo_engine *e, int32_t chain, int32_t marr, double *out);
 

@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
+    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -93,6 +93,8 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("eval_swaps_dev", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), C.c_int32, vp, vp)
     sig("prefilter", C.c_int, vp, C.c_int32, C.c_int32, _i32p, _u8p, C.c_int32, _i32p, _f64p,
         C.c_int32, _i32p, _f64p)
+    sig("prefilter_scores_dev", C.c_int, vp, C.c_int32, C.c_int32, _i32p, _u8p, C.c_int32, _i32p, _f64p, vp)
+    sig("prefilter_topk_dev", C.c_int, vp, C.c_int32, C.c_int32, _i32p, C.c_int32, _i32p, vp, C.c_int32, _i32p, _f64p)
     sig("get_stub", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
     sig("get_prong", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
     sig("launch_count", C.c_int64, vp)
@@ -317,6 +319,25 @@ class CEngine:
         return out_slot, out_score
 
     # -- read-back -----------------------------------------------------------------------------
+    def prefilter_scores_dev(self, kids, as_father, cands, cand_bias, scores_ptr: int, chain: int = 0):
+        """Dense partial scores [n_kids][n_cands] of this engine's loci into the buffer at `scores_ptr`
+        (device memory for the CUDA engine)."""
+        kids, cands = as_i32(kids), as_i32(cands)
+        role = np.ascontiguousarray(as_father, dtype=np.uint8)
+        bias = None if cand_bias is None else np.ascontiguousarray(cand_bias, dtype=np.float64)
+        self._check(self._fn("prefilter_scores_dev")(self._h, chain, len(kids), ptr(kids, _i32p), ptr(role, _u8p), len(cands),
+                                                     ptr(cands, _i32p), None if bias is None else ptr(bias, _f64p),
+                                                     C.c_void_p(scores_ptr)))
+
+    def prefilter_topk_dev(self, kids, cands, scores_ptr: int, top_k: int = 15, chain: int = 0):
+        """Ranks dense (summed) scores in place; returns (slot[n_kids][top_k], score[n_kids][top_k])."""
+        kids, cands = as_i32(kids), as_i32(cands)
+        slot = np.full((len(kids), top_k), -1, dtype=np.int32)
+        score = np.full((len(kids), top_k), -np.inf, dtype=np.float64)
+        self._check(self._fn("prefilter_topk_dev")(self._h, chain, len(kids), ptr(kids, _i32p), len(cands), ptr(cands, _i32p),
+                                                   C.c_void_p(scores_ptr), top_k, ptr(slot, _i32p), ptr(score, _f64p)))
+        return slot, score
+
     def get_stub(self, slot: int, chain: int = 0) -> np.ndarray:
         out = np.empty((self.n_local, 3), dtype=np.float64)
         self._check(self._fn("get_stub")(self._h, chain, slot, ptr(out, _f64p)))

@@ -1499,25 +1499,18 @@ extern "C" int pf_eval_dev(pf_engine *e, int32_t chain, int32_t kid, int32_t n, 
 // ---------------------------------------------------------------------------------------------
 // Prefilter (_RefineParentOffPair@0x100014d20)
 
-extern "C" int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
-                            const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
-                            const double *cand_bias, int32_t top_k, int32_t *out_slot, double *out_score)
+// stage the kid / candidate row tables and the bias, fill the kernel parameters
+static int prefilter_setup(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids, int32_t n_cands, const int32_t *cands,
+                           const double *cand_bias, PrefilterParams &P)
 {
-    if (!e || n_kids < 0 || n_cands < 0 || !kids || !as_father || !out_slot || !out_score) return fail(PF_EINVAL, "null argument");
-    if (n_cands > 0 && !cands) return fail(PF_EINVAL, "null candidates");
-    if (top_k <= 0 || top_k > PREF_MAX_TOPK) return fail(PF_EINVAL, "top_k must be in [1, %d]", PREF_MAX_TOPK);
     if (chain < 0 || chain >= e->cfg.n_chains) return fail(PF_EINVAL, "chain %d out of range", chain);
-    if (e->Sl != e->cfg.n_loci) return fail(PF_EINVAL, "pf_prefilter needs an unsharded engine (ranking requires all loci)");
     CU(cudaSetDevice(e->cfg.device));
-    if (n_kids == 0) return PF_OK;
     for (int k = 0; k < n_kids; k++)
         if (kids[k] < 0 || kids[k] >= e->cfg.cap_indiv) return fail(PF_EINVAL, "kid slot %d out of range", kids[k]);
     for (int j = 0; j < n_cands; j++)
         if (cands[j] < 0 || cands[j] >= e->cfg.cap_indiv) return fail(PF_EINVAL, "candidate slot %d out of range", cands[j]);
     int rc = sync_tables(e);
     if (rc) return rc;
-
-    // device inputs: kid rows, candidate rows, bias
     const size_t b_kid = (size_t)n_kids * sizeof(int), b_cand = (size_t)n_cands * sizeof(int);
     const size_t o_cand = (b_kid + 15) & ~(size_t)15, o_bias = (o_cand + b_cand + 15) & ~(size_t)15;
     const size_t blob = o_bias + (size_t)n_cands * sizeof(double);
@@ -1531,25 +1524,29 @@ extern "C" int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const i
     CU(e->plan.reserve(blob));
     CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
     CU(e->staging.mark(slot, e->stream));
-
-    const size_t out_bytes = (size_t)n_kids * top_k * (sizeof(double) + sizeof(int));
-    CU(e->result.reserve(out_bytes));
-    CU(e->partial.reserve(std::max<size_t>((size_t)n_kids * n_cands, 1) * sizeof(double)));
-    PrefilterParams P;
     P.D = dev_view(e);
     char *d = static_cast<char *>(e->plan.p);
     P.kid_rows = reinterpret_cast<const int *>(d);
     P.cand_rows = reinterpret_cast<const int *>(d + o_cand);
     P.cand_bias = reinterpret_cast<const double *>(d + o_bias);
-    P.n_kids = n_kids; P.n_cands = n_cands; P.top_k = top_k;
-    P.scores = static_cast<double *>(e->partial.p);
+    P.n_kids = n_kids; P.n_cands = n_cands; P.top_k = 0;
+    P.scores = nullptr; P.out_score = nullptr; P.out_idx = nullptr;
+    return PF_OK;
+}
+
+// rank the dense scores on the device and bring the top_k per kid back to the host
+static int prefilter_rank(pf_engine *e, PrefilterParams &P, const int32_t *cands, int32_t top_k, int32_t *out_slot, double *out_score)
+{
+    const int n_kids = P.n_kids;
+    const size_t out_bytes = (size_t)n_kids * top_k * (sizeof(double) + sizeof(int));
+    CU(e->result.reserve(out_bytes));
+    P.top_k = top_k;
     P.out_score = static_cast<double *>(e->result.p);
     P.out_idx = reinterpret_cast<int *>(static_cast<char *>(e->result.p) + (size_t)n_kids * top_k * sizeof(double));
     e->prof_begin(3);
-    e->launches += launch_prefilter(P, e->stream);
+    e->launches += launch_prefilter_topk(P, e->stream);
     e->prof_end();
     CU(cudaGetLastError());
-
     std::vector<char> hout(out_bytes);
     CU(cudaMemcpyAsync(hout.data(), e->result.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
@@ -1562,6 +1559,60 @@ extern "C" int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const i
             out_score[(size_t)k * top_k + t] = j < 0 ? -INFINITY : sc[(size_t)k * top_k + t];
         }
     return PF_OK;
+}
+
+extern "C" int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                            const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
+                            const double *cand_bias, int32_t top_k, int32_t *out_slot, double *out_score)
+{
+    if (!e || n_kids < 0 || n_cands < 0 || !kids || !as_father || !out_slot || !out_score) return fail(PF_EINVAL, "null argument");
+    if (n_cands > 0 && !cands) return fail(PF_EINVAL, "null candidates");
+    if (top_k <= 0 || top_k > PREF_MAX_TOPK) return fail(PF_EINVAL, "top_k must be in [1, %d]", PREF_MAX_TOPK);
+    if (e->Sl != e->cfg.n_loci) return fail(PF_EINVAL, "pf_prefilter needs an unsharded engine (ranking requires all loci): use pf_prefilter_scores_dev + an all-reduce + pf_prefilter_topk_dev");
+    if (n_kids == 0) return PF_OK;
+    PrefilterParams P;
+    int rc = prefilter_setup(e, chain, n_kids, kids, n_cands, cands, cand_bias, P);
+    if (rc) return rc;
+    CU(e->partial.reserve(std::max<size_t>((size_t)n_kids * n_cands, 1) * sizeof(double)));
+    P.scores = static_cast<double *>(e->partial.p);
+    e->prof_begin(3);
+    e->launches += launch_prefilter_scores(P, e->stream);
+    e->prof_end();
+    CU(cudaGetLastError());
+    return prefilter_rank(e, P, cands, top_k, out_slot, out_score);
+}
+
+// The two halves of pf_prefilter for engines that hold a locus shard: dense partial scores first,
+// the ranking after the caller has summed them over the shards (NCCL all-reduce on this stream).
+extern "C" int pf_prefilter_scores_dev(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
+                                       const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
+                                       const double *cand_bias, double *scores_dev)
+{
+    if (!e || n_kids < 0 || n_cands < 0 || (n_kids > 0 && (!kids || !as_father)) || (n_cands > 0 && !cands)) return fail(PF_EINVAL, "null argument");
+    if (n_kids == 0 || n_cands == 0) return PF_OK;
+    if (!scores_dev) return fail(PF_EINVAL, "null output");
+    PrefilterParams P;
+    int rc = prefilter_setup(e, chain, n_kids, kids, n_cands, cands, cand_bias, P);
+    if (rc) return rc;
+    P.scores = scores_dev;
+    e->prof_begin(3);
+    e->launches += launch_prefilter_scores(P, e->stream);
+    e->prof_end();
+    CU(cudaGetLastError());
+    return PF_OK;
+}
+
+extern "C" int pf_prefilter_topk_dev(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids, int32_t n_cands,
+                                     const int32_t *cands, double *scores_dev, int32_t top_k, int32_t *out_slot, double *out_score)
+{
+    if (!e || n_kids < 0 || n_cands < 0 || (n_kids > 0 && (!kids || !out_slot || !out_score)) || (n_cands > 0 && (!cands || !scores_dev))) return fail(PF_EINVAL, "null argument");
+    if (top_k <= 0 || top_k > PREF_MAX_TOPK) return fail(PF_EINVAL, "top_k must be in [1, %d]", PREF_MAX_TOPK);
+    if (n_kids == 0) return PF_OK;
+    PrefilterParams P;
+    int rc = prefilter_setup(e, chain, n_kids, kids, n_cands, cands, nullptr, P);
+    if (rc) return rc;
+    P.scores = scores_dev;
+    return prefilter_rank(e, P, cands, top_k, out_slot, out_score);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -116,15 +116,19 @@ __global__ void __launch_bounds__(128) prefilter_topk_kernel(const __grid_consta
     }
 }
 
-int launch_prefilter(const PrefilterParams &P, cudaStream_t st)
+int launch_prefilter_scores(const PrefilterParams &P, cudaStream_t st)
+{
+    if (P.n_kids <= 0 || P.n_cands <= 0) return 0;
+    dim3 grid((P.n_cands + PF_CT - 1) / PF_CT, (P.n_kids + PF_KT - 1) / PF_KT);
+    prefilter_scores_kernel<<<grid, 256, 0, st>>>(P);
+    return 1;
+}
+
+int launch_prefilter_topk(const PrefilterParams &P, cudaStream_t st)
 {
     if (P.n_kids <= 0) return 0;
-    if (P.n_cands > 0) {
-        dim3 grid((P.n_cands + PF_CT - 1) / PF_CT, (P.n_kids + PF_KT - 1) / PF_KT);
-        prefilter_scores_kernel<<<grid, 256, 0, st>>>(P);
-    }
     prefilter_topk_kernel<<<(P.n_kids * 32 + 127) / 128, 128, 0, st>>>(P);
-    return P.n_cands > 0 ? 2 : 1;
+    return 1;
 }
 
 } // namespace pf

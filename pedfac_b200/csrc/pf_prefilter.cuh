@@ -17,7 +17,8 @@ struct PrefilterParams {
     int *out_idx;             // [n_kids][top_k] index into cand_rows or -1
 };
 
-// returns the number of kernels launched
-int launch_prefilter(const PrefilterParams &P, cudaStream_t st);
+// each returns the number of kernels launched
+int launch_prefilter_scores(const PrefilterParams &P, cudaStream_t st);
+int launch_prefilter_topk(const PrefilterParams &P, cudaStream_t st);
 
 } // namespace pf

@@ -65,3 +65,17 @@ class ShardedEngine:
                 self.dist.all_reduce(seg, op=self.dist.ReduceOp.SUM, group=self.group)
             return seg.cpu().numpy()
         return self._reduce_host(self.engine.sweep(view, chain=chain))
+
+    def prefilter(self, kids, as_father, cands, cand_bias=None, top_k: int = 15, chain: int = 0):
+        """`pf_prefilter` over locus shards: every rank computes its dense partial scores, one
+        all-reduce sums them, then they are ranked (same result on every rank). The bias is added
+        on rank 0 only."""
+        torch, dist = self.torch, self.dist
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
+        rank0 = (not multi) or dist.get_rank(self.group) == 0
+        n = len(kids) * len(cands)
+        buf = torch.zeros(max(n, 1), dtype=torch.float64, device="cuda" if self.device_buffers else "cpu")
+        self.engine.prefilter_scores_dev(kids, as_father, cands, cand_bias if rank0 else None, buf.data_ptr(), chain=chain)
+        if multi:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group)
+        return self.engine.prefilter_topk_dev(kids, cands, buf.data_ptr(), top_k=top_k, chain=chain)

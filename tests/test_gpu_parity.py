@@ -407,3 +407,34 @@ def test_gpu_large_chain_batch_is_planned_in_parallel_and_matches_the_oracle():
     views[17] = bad.view()[0]
     with pytest.raises(PedfacError):
         g.sweep_batch(list(range(n_ch)), views)
+
+
+def test_gpu_prefilter_in_two_halves_over_locus_shards():
+    """pf_prefilter_scores_dev on three locus shards, summed, then pf_prefilter_topk_dev = pf_prefilter
+    on the unsharded engine (same slots; scores to 1e-12)."""
+    import torch
+    rng = np.random.default_rng(808)
+    sc = random_forest(rng, n_indiv=70, S=300, max_kids=3, kinds=("hard", "dec16", "none"))
+    full = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(full)
+    view, _ = sc.ped.view()
+    full.sweep(view)
+    kids = np.arange(0, 40, dtype=np.int32); cands = np.arange(10, 70, dtype=np.int32)
+    role = (kids % 2).astype(np.uint8); bias = rng.normal(size=len(cands))
+    want_slot, want_score = full.prefilter(kids, role, cands, bias, top_k=15)
+    total = torch.zeros(len(kids) * len(cands), dtype=torch.float64, device="cuda")
+    shards = []
+    for k, (a, b) in enumerate([(0, 100), (100, 150), (150, 300)]):
+        e = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr, locus_range=(a, b))
+        sc.upload(e); e.sweep(view)
+        part = torch.zeros_like(total)
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        e.prefilter_scores_dev(kids, role, cands, bias if k == 0 else None, part.data_ptr())
+        torch.cuda.synchronize()
+        total += part
+        shards.append(e)
+    got_slot, got_score = shards[1].prefilter_topk_dev(kids, cands, total.data_ptr(), top_k=15)
+    np.testing.assert_array_equal(got_slot, want_slot)
+    np.testing.assert_allclose(got_score, want_score, rtol=1e-12, atol=1e-10)
+    with pytest.raises(PedfacError):
+        shards[0].prefilter(kids, role, cands, bias, top_k=15)        # the one-call form needs all loci

@@ -35,7 +35,11 @@ def _worker(rank, world, port, q):
     view, _ = sc.ped.view()
     props = make_proposals([(PF_PROP_TRIO, 1, 2, -1), (PF_PROP_TRIO, -1, 7, -1), (PF_PROP_SELFING, 5, -1, -1)])
     ll_cc, lsum = sh.step(view, 0, props)
-    q.put((rank, (s0, s1), ll_cc.copy(), lsum.copy(), sh.sweep(view).copy()))
+    kids, cands = np.arange(0, 12, dtype=np.int32), np.arange(5, 40, dtype=np.int32)
+    role = (kids % 2).astype(np.uint8)
+    bias = -np.linspace(0.0, 3.0, len(cands))
+    pslot, pscore = sh.prefilter(kids, role, cands, bias, top_k=6)
+    q.put((rank, (s0, s1), ll_cc.copy(), lsum.copy(), sh.sweep(view).copy(), pslot.copy(), pscore.copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -60,7 +64,13 @@ def test_two_rank_locus_sharding_matches_unsharded():
     view, _ = sc.ped.view()
     want_cc = full.sweep(view)
     want = full.eval(0, [(PF_PROP_TRIO, 1, 2, -1), (PF_PROP_TRIO, -1, 7, -1), (PF_PROP_SELFING, 5, -1, -1)])
-    for rank, _, ll_cc, lsum, sw in res:
+    kids, cands = np.arange(0, 12, dtype=np.int32), np.arange(5, 40, dtype=np.int32)
+    want_slot, want_score = full.prefilter(kids, (kids % 2).astype(np.uint8), cands, -np.linspace(0.0, 3.0, len(cands)), top_k=6)
+    for r_ in res:
+        np.testing.assert_array_equal(r_[5], want_slot)                    # sharded prefilter ranks like the unsharded one
+        np.testing.assert_allclose(r_[6], want_score, rtol=1e-12)
+    np.testing.assert_array_equal(res[0][6], res[1][6])
+    for rank, _, ll_cc, lsum, sw, _ps, _pc in res:
         np.testing.assert_allclose(ll_cc, want_cc, rtol=1e-13, atol=1e-12)
         np.testing.assert_allclose(sw, want_cc, rtol=1e-13, atol=1e-12)
         np.testing.assert_allclose(lsum, want, rtol=1e-13)
