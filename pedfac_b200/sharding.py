@@ -66,6 +66,19 @@ class ShardedEngine:
             return seg.cpu().numpy()
         return self._reduce_host(self.engine.sweep(view, chain=chain))
 
+    def eval_swaps(self, view, swaps, chain: int = 0) -> np.ndarray:
+        """`pf_eval_swaps` over locus shards: per-shard partial log-sums, one all-reduce."""
+        from .abi import make_swaps
+        swaps = make_swaps(swaps)
+        if self.device_buffers:
+            buf = self._dev_buf(len(swaps))
+            self.engine.eval_swaps_dev(view, swaps, buf.data_ptr(), chain=chain)
+            seg = buf[: len(swaps)]
+            if self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1:
+                self.dist.all_reduce(seg, op=self.dist.ReduceOp.SUM, group=self.group)
+            return seg.cpu().numpy()
+        return self._reduce_host(self.engine.eval_swaps(view, swaps, chain=chain))
+
     def prefilter(self, kids, as_father, cands, cand_bias=None, top_k: int = 15, chain: int = 0):
         """`pf_prefilter` over locus shards: every rank computes its dense partial scores, one
         all-reduce sums them, then they are ranked (same result on every rank). The bias is added

@@ -39,7 +39,17 @@ def _worker(rank, world, port, q):
     role = (kids % 2).astype(np.uint8)
     bias = -np.linspace(0.0, 3.0, len(cands))
     pslot, pscore = sh.prefilter(kids, role, cands, bias, top_k=6)
-    q.put((rank, (s0, s1), ll_cc.copy(), lsum.copy(), sh.sweep(view).copy(), pslot.copy(), pscore.copy()))
+    # a swap proposal on a pruned copy of the pedigree (sharded: partial sums + all-reduce)
+    site = sc.ped.swap_sites()[0]
+    x, z, mx, mz, m_of_x = site
+    ped2 = sc.ped.copy()
+    pa, ma, prev = ped2.detach_kid(x)
+    ped2.founder[x] = False
+    labels2, _ = ped2.components()
+    sh.sweep(ped2.view(labels2)[0])
+    view3, _ = ped2.view(labels2, only={int(labels2[x]), int(labels2[pa]), int(labels2[ma])})
+    sw = sh.eval_swaps(view3, [(1, 0, x, z, mz, mx, pa, ma, -1 if prev is None else prev), (3, 1, x, z, mz, mx, pa, ma, -1 if prev is None else prev)])
+    q.put((rank, (s0, s1), ll_cc.copy(), lsum.copy(), sh.sweep(view).copy(), pslot.copy(), pscore.copy(), sw.copy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -70,7 +80,18 @@ def test_two_rank_locus_sharding_matches_unsharded():
         np.testing.assert_array_equal(r_[5], want_slot)                    # sharded prefilter ranks like the unsharded one
         np.testing.assert_allclose(r_[6], want_score, rtol=1e-12)
     np.testing.assert_array_equal(res[0][6], res[1][6])
-    for rank, _, ll_cc, lsum, sw, _ps, _pc in res:
+    x, z, mx, mz, m_of_x = sc.ped.swap_sites()[0]
+    ped2 = sc.ped.copy()
+    pa, ma, prev = ped2.detach_kid(x)
+    ped2.founder[x] = False
+    labels2, _ = ped2.components()
+    full.sweep(ped2.view(labels2)[0])
+    view3, _ = ped2.view(labels2, only={int(labels2[x]), int(labels2[pa]), int(labels2[ma])})
+    want_sw = full.eval_swaps(view3, [(1, 0, x, z, mz, mx, pa, ma, -1 if prev is None else prev), (3, 1, x, z, mz, mx, pa, ma, -1 if prev is None else prev)])
+    for r_ in res:
+        np.testing.assert_allclose(r_[7], want_sw, rtol=1e-12)
+    full.sweep(view)
+    for rank, _, ll_cc, lsum, sw, _ps, _pc, _sw in res:
         np.testing.assert_allclose(ll_cc, want_cc, rtol=1e-13, atol=1e-12)
         np.testing.assert_allclose(sw, want_cc, rtol=1e-13, atol=1e-12)
         np.testing.assert_allclose(lsum, want, rtol=1e-13)
