@@ -438,3 +438,27 @@ def test_gpu_prefilter_in_two_halves_over_locus_shards():
     np.testing.assert_allclose(got_score, want_score, rtol=1e-12, atol=1e-10)
     with pytest.raises(PedfacError):
         shards[0].prefilter(kids, role, cands, bias, top_k=15)        # the one-call form needs all loci
+
+
+def test_gpu_repeated_sweeps_are_bitwise_identical():
+    """The sweep's transient rows are reused by level parity and its tasks run on whichever warp
+    takes them: a hazard between tasks would show up as run-to-run differences. 40 repetitions of
+    a deep, wide view (and of its swap evaluations) must agree to the bit."""
+    rng = np.random.default_rng(919)
+    sc = random_forest(rng, n_indiv=600, S=100, max_kids=8, kinds=("hard", "dec16", "none"), max_comp=400)
+    g = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(g)
+    labels, _ = sc.ped.components()
+    view, _ = sc.ped.view(labels)
+    ref_ll = g.sweep(view)
+    probe = [int(i) for i in np.flatnonzero(sc.ped.active)[::7]]
+    ref_stubs = [g.get_stub(i) for i in probe]
+    marrs = sorted(sc.ped.marriages)[::5]
+    ref_prongs = [g.get_prong(m) for m in marrs]
+    assert g.plan_stats()["levels"] >= 8
+    for _ in range(40):
+        np.testing.assert_array_equal(g.sweep(view), ref_ll)
+    for i, s in zip(probe, ref_stubs):
+        np.testing.assert_array_equal(g.get_stub(i), s)
+    for m, s in zip(marrs, ref_prongs):
+        np.testing.assert_array_equal(g.get_prong(m), s)
