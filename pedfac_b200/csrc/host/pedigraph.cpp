@@ -1099,18 +1099,63 @@ static bool parse_dec4(const char *s, unsigned &num)
     return true;
 }
 
+// geno.txt is the one big input (tens of MB: one token per individual and locus): its lines are read
+// with getline() and tokenised in place; the generic read_line()/split() pair above allocates a
+// string per token and took most of the sampler's start-up time.
+struct LineReader {
+    FILE *f; char *buf = nullptr; size_t cap = 0; size_t len = 0;
+    explicit LineReader(FILE *f_) : f(f_) {}
+    ~LineReader() { free(buf); }
+    bool next()                                 // like read_line: drops the newline and every '\r'
+    {
+        const ssize_t n = getline(&buf, &cap, f);
+        if (n < 0) return false;
+        size_t w = 0;
+        for (ssize_t i = 0; i < n; i++) if (buf[i] != '\n' && buf[i] != '\r') buf[w++] = buf[i];
+        buf[w] = 0; len = w;
+        return true;
+    }
+};
+// next run of non-blank characters at or after c; returns false at the end of the line
+static bool next_token(const char *&c, const char *&b, const char *&e)
+{
+    while (*c == ' ') c++;
+    if (!*c) return false;
+    b = c;
+    while (*c && *c != ' ') c++;
+    e = c;
+    return true;
+}
+static double tok_strtod(const char *b, const char *e)
+{
+    char tmp[64];
+    const size_t n = std::min<size_t>((size_t)(e - b), sizeof tmp - 1);
+    memcpy(tmp, b, n); tmp[n] = 0;
+    return strtod(tmp, nullptr);
+}
+static bool parse_dec4(const char *b, const char *e, unsigned &num)
+{
+    char tmp[32];
+    if ((size_t)(e - b) >= sizeof tmp) return false;
+    memcpy(tmp, b, (size_t)(e - b)); tmp[e - b] = 0;
+    return parse_dec4(tmp, num);
+}
+
 static void ReadGeno(Ped &p, const std::string &path)
 {
     // pass 1 (_CalculateMaxSize): observed individuals per generation -> capacities
     FILE *f = fopen(path.c_str(), "r");
     if (!f) { fprintf(stderr, "Failed to open geno.txt for reading\n"); exit(-1); }
-    std::string line;
+    LineReader lr(f);
     std::vector<int> nPerGen(p.nGen, 0);
-    while (read_line(f, line)) {
-        if (line.empty() || line[0] == '#') continue;
-        auto tok = split(line, ' ');
-        if (tok.size() < 4 || atoi(tok[1].c_str()) == 0) continue;
-        const int g = atoi(tok[3].c_str());
+    while (lr.next()) {
+        if (lr.len == 0 || lr.buf[0] == '#') continue;
+        const char *c = lr.buf, *b, *e;
+        const char *tb[4], *te[4];
+        int nt = 0;
+        while (nt < 4 && next_token(c, b, e)) { tb[nt] = b; te[nt] = e; nt++; }
+        if (nt < 4 || (int)tok_strtod(tb[1], te[1]) == 0) continue;      // atoi semantics for plain integers
+        const int g = (int)tok_strtod(tb[3], te[3]);
         if (g >= 0 && g < p.nGen) nPerGen[g]++;
     }
     p.capIndiv = 0; p.capMarr = 0;
@@ -1141,11 +1186,15 @@ static void ReadGeno(Ped &p, const std::string &path)
     std::vector<uint8_t> codes(p.S);
     std::vector<double> lik((size_t)p.S * 3);
     std::vector<uint16_t> num((size_t)p.S * 3);
-    while (read_line(f, line)) {
-        if (line.empty() || line[0] == '#') continue;
-        auto tok = split(line, ' ');
-        if (tok.size() < 5) continue;
-        const bool obs = atoi(tok[1].c_str()) != 0;
+    while (lr.next()) {
+        if (lr.len == 0 || lr.buf[0] == '#') continue;
+        const char *c = lr.buf, *b, *e;
+        const char *tb[5], *te[5];
+        int nt = 0;
+        while (nt < 5 && next_token(c, b, e)) { tb[nt] = b; te[nt] = e; nt++; }
+        if (nt < 5) continue;
+        auto tok_int = [&](int k) { char tmp[32]; const size_t n = std::min<size_t>((size_t)(te[k] - tb[k]), sizeof tmp - 1); memcpy(tmp, tb[k], n); tmp[n] = 0; return atoi(tmp); };
+        const bool obs = tok_int(1) != 0;
         int slot;
         if (obs) {
             if (nextObs >= p.nObs) { fprintf(stderr, "There are more observed individuals in your genoInfo.txt than what you have declared\n"); exit(-1); }
@@ -1155,45 +1204,60 @@ static void ReadGeno(Ped &p, const std::string &path)
             slot = nextUnobs++;
         }
         Indiv &x = p.indiv[slot];
-        x.userID = atoi(tok[0].c_str());
+        x.userID = tok_int(0);
         x.observed = obs;
-        x.sex = atoi(tok[2].c_str()); x.sexWasUnknown = x.sex == 0;
-        x.genTime = atof(tok[3].c_str());
+        x.sex = tok_int(2); x.sexWasUnknown = x.sex == 0;
+        x.genTime = tok_strtod(tb[3], te[3]);
         x.gen = (int)(x.genTime / p.minAge);
         if (x.gen >= p.nGen || x.gen < 0) {
             fprintf(stderr, "In genoInfo.txt, the assigned generation level of %d-th individual is %d, beyond nGen\n", row, x.gen); exit(0);
         }
         p.nIndivPerGen[x.gen]++;
         if (obs) p.nObsPerGen[x.gen]++;
-        x.founder = atoi(tok[4].c_str()) != 0;
+        x.founder = tok_int(4) != 0;
         p.indivActive[slot] = 1;
         if (obs) {
-            if ((int)tok.size() - 5 < p.S) {
-                fprintf(stderr, "error on geno.txt: Individual %d has fewer SNPs than reported. \nnum of SNP - obs: %d , exp: %d", row, (int)tok.size() - 5, p.S); exit(-1);
-            }
             bool soft = false, dec_ok = true;
-            for (int s = 0; s < p.S; s++) {
-                const std::string &t = tok[5 + s];
-                if (t.find(',') != std::string::npos) {
+            int s = 0;
+            for (; s < p.S && next_token(c, b, e); s++) {
+                const char *comma = (const char *)memchr(b, ',', (size_t)(e - b));
+                if (comma) {
                     soft = true;
-                    auto parts = split(t, ',');
-                    if (parts.size() != 3) { fprintf(stderr, "Expect three genotype posterior prob on the geno.txt\n"); exit(1); }
+                    // three non-empty parts separated by commas (empty parts are skipped, as split() does)
+                    const char *pb[3], *pe[3];
+                    int np = 0;
+                    const char *q = b;
+                    while (q < e) {
+                        const char *r = (const char *)memchr(q, ',', (size_t)(e - q));
+                        if (!r) r = e;
+                        if (r > q) { if (np < 3) { pb[np] = q; pe[np] = r; } np++; }
+                        q = r + 1;
+                    }
+                    if (np != 3) { fprintf(stderr, "Expect three genotype posterior prob on the geno.txt\n"); exit(1); }
                     for (int g = 0; g < 3; g++) {
-                        lik[(size_t)s * 3 + g] = strtod(parts[g].c_str(), nullptr);
                         unsigned nn = 0;
-                        if (dec_ok && parse_dec4(parts[g].c_str(), nn)) num[(size_t)s * 3 + g] = (uint16_t)nn; else dec_ok = false;
+                        if (parse_dec4(pb[g], pe[g], nn)) {
+                            lik[(size_t)s * 3 + g] = (double)nn / 10000.0;        // = strtod of the token: both are the correctly rounded value
+                            if (dec_ok) num[(size_t)s * 3 + g] = (uint16_t)nn;
+                        } else {
+                            lik[(size_t)s * 3 + g] = tok_strtod(pb[g], pe[g]);
+                            dec_ok = false;
+                        }
                     }
                     codes[s] = 3;
                 } else {
-                    const int c = (int)strtod(t.c_str(), nullptr);
-                    if (c < 0 || c > 3) {
+                    const int cde = (e - b == 1 && *b >= '0' && *b <= '9') ? *b - '0' : (int)tok_strtod(b, e);
+                    if (cde < 0 || cde > 3) {
                         fprintf(stderr, "Acceptable genotype values are 0, 1, 2, or 3.\nIf you are uncertain about the genotype value, you can replace that value with 3.\n"); exit(-1);
                     }
-                    codes[s] = (uint8_t)c;
-                    const double e = p.eps[s];
-                    for (int g = 0; g < 3; g++) lik[(size_t)s * 3 + g] = c == 3 ? 1.0 : (g == c ? 1.0 - e : e / 2.0);
+                    codes[s] = (uint8_t)cde;
+                    const double ee = p.eps[s];
+                    for (int g = 0; g < 3; g++) lik[(size_t)s * 3 + g] = cde == 3 ? 1.0 : (g == cde ? 1.0 - ee : ee / 2.0);
                     dec_ok = false;
                 }
+            }
+            if (s < p.S) {
+                fprintf(stderr, "error on geno.txt: Individual %d has fewer SNPs than reported. \nnum of SNP - obs: %d , exp: %d", row, s, p.S); exit(-1);
             }
             int rc;
             if (!soft) rc = PFN(set_genotypes_hard)(p.eng, slot, codes.data());

@@ -203,3 +203,37 @@ def test_other_priors_run_consistently_on_the_cpu(tmp_path):
     assert r.returncode == 0, r.stderr[-1500:]
     rows = np.loadtxt(rd / "out" / "ped.txt", dtype=int)
     assert (rows[:, 1] > len(np.flatnonzero(d.observed))).any()        # unobserved individuals get sampled too
+
+
+def test_geno_parser_accepts_equivalent_spellings(tmp_path):
+    """CRLF line ends, repeated blanks, trailing zeros and short decimals spell the same data; five
+    significant decimals force the exact-double path. Same chain in every case."""
+    d, order, rd = make_run(tmp_path, "f0", n=70, S=50, soft=True)
+    base = (rd / "geno.txt").read_text()
+    variants = {
+        "crlf": base.replace("\n", "\r\n"),
+        "blanks": base.replace(" ", "  "),
+        "zeros": re.sub(r"(\d\.\d{4})(?=[, \n])", r"\g<1>00", base),
+    }
+    want = None
+    for name, text in {"plain": base, **variants}.items():
+        vd = tmp_path / name
+        frontend.write_run_dir(d, vd)
+        (vd / "geno.txt").write_text(text)
+        r = run(REF, vd, n_iter=2)
+        assert r.returncode == 0, (name, r.stderr[-500:])
+        got = (vd / "out" / "ped.txt").read_text(), (vd / "out" / "ll.txt").read_text()
+        want = want or got
+        assert got == want, name
+    # a fifth significant decimal cannot be a 16-bit numerator: the row goes through the f64 path and still runs
+    odd = tmp_path / "odd"
+    frontend.write_run_dir(d, odd)
+    (odd / "geno.txt").write_text(re.sub(r"0\.(\d{4}),", r"0.\g<1>1,", base, count=3))
+    assert run(REF, odd, n_iter=1).returncode == 0
+    short = tmp_path / "short"
+    frontend.write_run_dir(d, short)
+    lines = base.splitlines()
+    lines[3] = " ".join(lines[3].split(" ")[:-2])
+    (short / "geno.txt").write_text("\n".join(lines) + "\n")
+    r = run(REF, short, n_iter=1)
+    assert r.returncode != 0 and "fewer SNPs than reported" in r.stderr and "obs: 48 , exp: 50" in r.stderr
