@@ -15,7 +15,9 @@
 //   * -c 1 (throttle) and -l (loopy BP) are rejected;
 //   * the sweep that ends _PickAndUpdate is merged with the one that follows the next
 //     _PruneIndiv (nothing reads messages in between), so a Gibbs step costs one sweep;
-//   * mnode kid arrays grow (the reference overflows a malloc(8) block).
+//   * mnode kid arrays grow (the reference overflows a malloc(8) block);
+//   * a chosen parent (or marriage) that the trimming of the previous parents deletes in the same step is
+//     replaced by a new unobserved parent (the reference links the kid to the freed slot).
 //
 // The engine entry points are reached through PFN(name); the default binds libpedfac_cuda
 // (pf_*). The test infrastructure builds the same file against its CPU checker by defining
@@ -928,6 +930,17 @@ static void PickAndUpdate(Ped &p, int kid)
             TrimPed(p, p.prev[1]); UpdateConComp(p, p.prev[1]); RevertSex(p, p.prev[0]);   // sic: prev.pa
         }
     }
+    // The trimming above can delete what was just chosen: an unobserved ancestor of a trimmed
+    // ex-parent (only the ex-parents themselves are hidden from the enumeration), or the marriage of
+    // such ancestors. The reference then links the kid to a freed slot (_PickAndUpdate@0x100016cf5 uses
+    // new[] unchecked) and carries an inactive individual inside an active marriage from there on.
+    // Such an ancestor carries no information (its stub is the founder prior), so the choice means
+    // "a new unobserved parent": that is what is created here instead.
+    if (!swap) {
+        if (p.neu[2] != -1 && !p.marrActive[p.neu[2]]) p.neu[2] = -1;
+        if (p.neu[0] >= 0 && !p.indivActive[p.neu[0]]) p.neu[0] = -1;
+        if (p.neu[1] >= 0 && !p.indivActive[p.neu[1]]) p.neu[1] = p.neu[3] == 1 ? p.neu[0] : -1;
+    }
     const int sel_pa = p.neu[0], sel_ma = p.neu[1];            // v54 / v58 of the swap rewiring below
     int m = p.neu[2], pa = p.neu[0], ma = p.neu[1];
     Indiv &k = p.indiv[kid];
@@ -988,6 +1001,41 @@ static void PickAndUpdate(Ped &p, int kid)
     // start of the next Gibbs step instead (see the header of this file)
 }
 
+// PEDFAC_CHECK: structural invariants of the pedigree state (every member of an active marriage is
+// active, carries the marriage in its own list with the right edge index and shares its component)
+static void CheckInvariants(Ped &p, const char *where, int id)
+{
+    auto bad = [&](const char *what, int a, int b) {
+        fprintf(stderr, "PEDFAC_CHECK: %s after %s of %d (iter %d): %d %d\n", what, where, id, p.iter, a, b);
+        exit(4);
+    };
+    for (int m = 0; m < p.nMarrUsed; m++) {
+        if (!p.marrActive[m]) continue;
+        const Marr &mm = p.marr[m];
+        const int ne = mm.nEdges();
+        for (int ed = 0; ed < ne; ed++) {
+            if (ed == 1 && mm.selfing) continue;
+            const int x = ed == 0 ? mm.pa : ed == 1 ? mm.ma : mm.kids[ed - 2];
+            if (x < 0 || x >= p.nIndivUsed || !p.indivActive[x]) bad("inactive member of marriage", m, x);
+            if (p.cc[x] != p.cc[mm.pa]) bad("member in another component than the father of marriage", m, x);
+            bool found = false;
+            for (size_t k = 0; k < p.indiv[x].M.size(); k++) if (p.indiv[x].M[k] == m && p.indiv[x].edge[k] == ed) found = true;
+            if (!found) bad("marriage missing from its member's list", m, x);
+        }
+    }
+    for (int i = 0; i < p.nIndivUsed; i++) {
+        if (!p.indivActive[i]) continue;
+        if (p.cc[i] < 0 || p.cc[i] >= p.nCC) bad("component label out of range", i, p.cc[i]);
+        for (size_t k = 0; k < p.indiv[i].M.size(); k++) {
+            const int m = p.indiv[i].M[k], ed = p.indiv[i].edge[k];
+            if (m < 0 || m >= p.nMarrUsed || !p.marrActive[m]) bad("individual lists an inactive marriage", i, m);
+            const Marr &mm = p.marr[m];
+            const int x = ed == 0 ? mm.pa : ed == 1 ? mm.ma : (ed - 2 < (int)mm.kids.size() ? mm.kids[ed - 2] : -1);
+            if (x != i) bad("edge index does not point back", i, m);
+        }
+    }
+}
+
 // _MCMC_sampling@0x100019ec0
 static void MCMC_sampling(Ped &p, const Opts &o, int id)
 {
@@ -996,11 +1044,15 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
     p.t++;
     p.n_steps++;
     PruneIndiv(p, id);
+    if (p.check) CheckInvariants(p, "PruneIndiv", id);
     EvalMoves(p, o, id);                                       // runs the pending sweep together with its first batch
     p.t++;
     if (p.check) p.chll_data = p.chll;
     AddObsFracPrior(p, id);
+    const int dbg_prev[3] = {p.prev[0], p.prev[1], p.prev[2]};
     PickAndUpdate(p, id);
+    if (getenv("PEDFAC_DEBUG")) fprintf(stderr, "step iter %d kid %d prev %d %d %d -> new %d %d %d self %d picked %d kind %d\n", p.iter, id, dbg_prev[0], dbg_prev[1], dbg_prev[2], p.neu[0], p.neu[1], p.neu[2], p.neu[3], p.picked, p.picked >= 0 ? p.ch[p.picked].kind : -1);
+    if (p.check) CheckInvariants(p, "PickAndUpdate", id);
     if (p.check && p.picked >= 0 && !p.ch.empty()) {
         // the log-likelihood a proposal was scored with is the total the pedigree has once the move
         // is made: re-propagate now and compare (every move kind, swaps included)

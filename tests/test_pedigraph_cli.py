@@ -237,3 +237,15 @@ def test_geno_parser_accepts_equivalent_spellings(tmp_path):
     (short / "geno.txt").write_text("\n".join(lines) + "\n")
     r = run(REF, short, n_iter=1)
     assert r.returncode != 0 and "fewer SNPs than reported" in r.stderr and "obs: 48 , exp: 50" in r.stderr
+
+
+def test_choice_deleted_by_the_same_steps_trimming(tmp_path):
+    """Found by tools/trace_soak.py: with two unobserved layers a kid can pick an unobserved ancestor
+    of its own ex-parent; trimming the ex-parent then deletes that ancestor (and its marriage) in
+    the same step. The reference links the kid to the freed slot; here a new unobserved parent is
+    created instead, and PEDFAC_CHECK (structure + likelihood) must hold through the run."""
+    d = synth.simulate(245, 58, soft=False, seed=500392788, observe_frac=0.8)
+    rd = tmp_path / "t"
+    frontend.write_run_dir(d, rd, seeds=(614661122, 956123187), max_unobs=2, max_age=2.0, observe_frac=0.8)
+    r = run(REF, rd, n_iter=3, extra=("-s",), env={"PEDFAC_CHECK": "1", "PEDFAC_STATS": "1"})
+    assert r.returncode == 0, r.stderr[-800:]
