@@ -1,7 +1,7 @@
 """Trace-parity soak (measurement aid): random data sets and option mixes, the CUDA sampler against the
 oracle-backed sampler (same source, same seed); ped.txt must be identical and ll.txt equal to its
 printed 6 decimals (allowing the last digit)."""
-import os, subprocess, sys, time
+import os, shutil, subprocess, sys, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -9,7 +9,7 @@ import numpy as np
 from pedfac_b200 import synth, frontend
 GPU, REF = ROOT / "pedfac_b200/bin/pedigraph", ROOT / "oracle/pedigraph_ref"
 n_cases = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-rng = np.random.default_rng(2026)
+rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 2026)
 bad = 0
 for case in range(n_cases):
     n = int(rng.integers(80, 420)); S = int(rng.integers(40, 260)); soft = bool(rng.integers(2))
@@ -20,6 +20,7 @@ for case in range(n_cases):
     outs = []
     for tag, b in (("gpu", GPU), ("ref", REF)):
         rd = Path(f"/tmp/soak_{case}_{tag}")
+        shutil.rmtree(rd, ignore_errors=True)
         frontend.write_run_dir(d, rd, seeds=seeds, max_unobs=unobs, max_age=max_age, observe_frac=obs_frac, seed_marriages=seeded)
         t = time.time()
         r = subprocess.run([str(b), "-d", str(rd), "-n", str(iters), "-r", str(rd / "rand")] + (["-s"] if selfing else []),
