@@ -18,7 +18,7 @@ for case in range(n_cases):
     d = synth.simulate(n, S, soft=soft, seed=int(rng.integers(1 << 30)), observe_frac=float(rng.choice([0.6, 0.8, 0.95])))
     seeds = (int(rng.integers(1, 1 << 30)), int(rng.integers(1, 1 << 30)))
     outs = []
-    for tag, b in (("gpu", GPU), ("ref", REF)):
+    for tag, b in ((("ref", REF), ("ref", REF)) if os.environ.get("SOAK_REF_ONLY") else (("gpu", GPU), ("ref", REF))):
         rd = Path(f"/tmp/soak_{case}_{tag}")
         shutil.rmtree(rd, ignore_errors=True)
         frontend.write_run_dir(d, rd, seeds=seeds, max_unobs=unobs, max_age=max_age, observe_frac=obs_frac, seed_marriages=seeded)
