@@ -36,6 +36,9 @@ static int fail(int code, const char *fmt, ...)
             return fail(PF_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
+#ifndef PF_EVAL_MIN_CHUNK
+#define PF_EVAL_MIN_CHUNK 128
+#endif
 namespace {
 
 // grow-only device buffer
@@ -1427,7 +1430,7 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     // least 4 lane-iterations per chunk, at most 128 (the running mantissa product needs
     // renormalising only every 512 factors)
     const int group_blocks = (n_groups + EVAL_WARPS - 1) / EVAL_WARPS;
-    const int max_chunks = std::max(1, (e->Sl + 127) / 128);
+    const int max_chunks = std::max(1, (e->Sl + PF_EVAL_MIN_CHUNK - 1) / PF_EVAL_MIN_CHUNK);
     if (e->eval_capacity <= 0) e->eval_capacity = eval_resident_blocks();
     const int waves = (group_blocks + e->eval_capacity - 1) / e->eval_capacity;    // > 1 only for huge proposal lists
     int n_chunks = std::max(1, std::min(max_chunks, waves * e->eval_capacity / group_blocks));
