@@ -989,6 +989,23 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         plan.n_levels = n_levels;
         G = (int)plan.groups.size();
         if (G > 65535) return fail(PF_EINVAL, "too many task groups (%d)", G);
+        // heaviest groups first: blockIdx.y is the group, and when the grid is larger than the GPU the
+        // blocks of the last groups only start once earlier ones have finished — the long-running
+        // blocks must not be the ones that wait
+        if (G > 1 && (long long)G * n_tiles > sm_count) {
+            std::vector<int> &perm = g_work.cost_of, &inv = g_work.start;
+            perm.resize(G); inv.resize(G);
+            for (int g = 0; g < G; g++) perm[g] = g;
+            std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return plan.groups[a].task_end > plan.groups[b].task_end; });   // task_end still counts the group's tasks
+            bool moved = false;
+            for (int k = 0; k < G; k++) { inv[perm[k]] = k; moved = moved || perm[k] != k; }
+            if (moved) {
+                std::vector<SweepGroup> sorted(G);
+                for (int k = 0; k < G; k++) sorted[k] = plan.groups[perm[k]];
+                plan.groups.swap(sorted);
+                for (auto &t : plan.tasks) t.group = inv[t.group];
+            }
+        }
 
         // counting sort by (group, level); groups own contiguous task ranges in emission order already
         level_off.assign((size_t)G * (n_levels + 1) + 1, 0);
