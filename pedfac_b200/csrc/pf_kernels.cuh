@@ -118,7 +118,10 @@ struct SweepShape { int warps, blocks_per_sm, smem_max, plan_smem_max, emis_smem
 #ifndef PF_LAT_WARPS
 #define PF_LAT_WARPS 16
 #endif
-constexpr SweepShape SWEEP_LATENCY{PF_LAT_WARPS, 1, 195 * 1024, 56 * 1024, 72 * 1024, 160};
+#ifndef PF_LEAF_BUDGET
+#define PF_LEAF_BUDGET 400
+#endif
+constexpr SweepShape SWEEP_LATENCY{PF_LAT_WARPS, 1, 195 * 1024, 56 * 1024, 72 * 1024, PF_LEAF_BUDGET};
 constexpr SweepShape SWEEP_THROUGHPUT{8, 2, 98 * 1024, 28 * 1024, 36 * 1024, 64};
 
 // staged bytes of one individual's 32-locus genotype tile
