@@ -122,7 +122,10 @@ struct SweepShape { int warps, blocks_per_sm, smem_max, plan_smem_max, emis_smem
 #define PF_LEAF_BUDGET 400
 #endif
 constexpr SweepShape SWEEP_LATENCY{PF_LAT_WARPS, 1, 195 * 1024, 56 * 1024, 72 * 1024, PF_LEAF_BUDGET};
-constexpr SweepShape SWEEP_THROUGHPUT{8, 2, 98 * 1024, 28 * 1024, 36 * 1024, 64};
+#ifndef PF_T_LEAF
+#define PF_T_LEAF 64
+#endif
+constexpr SweepShape SWEEP_THROUGHPUT{8, 2, 98 * 1024, 28 * 1024, 36 * 1024, PF_T_LEAF};
 
 // staged bytes of one individual's 32-locus genotype tile
 __host__ __device__ inline int emis_tile_bytes(unsigned kind)
