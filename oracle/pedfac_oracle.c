@@ -639,9 +639,10 @@ static int directpass_if2iv(const swap_ctx *c, double *holder, double *tmp, int 
     if (v->marr_pa[j] == src) src_ed = 0;
     else if (v->marr_ma[j] == src) src_ed = 1;
     else for (int k = 2; k < ne; k++) if (view_edge_slot(v, j, k) == src) { src_ed = k; break; }
-    if (src_ed < 0 || ne > 64) return -1;
+    if (src_ed < 0) return -1;
     memcpy(tmp, holder, sizeof(double) * T3);
-    const double *in[64];
+    const double **in = malloc(sizeof(double *) * (size_t)ne);
+    if (!in) return -1;
     for (int k = 0; k < ne; k++) in[k] = k == src_ed ? tmp : e->m_in[M] + k * T3;
     for (int s = 0; s < e->Sl; s++)
         for (int go = 0; go < 3; go++) {
@@ -703,6 +704,7 @@ static int directpass_if2iv(const swap_ctx *c, double *holder, double *tmp, int 
             }
             holder[s * 3 + go] = acc;
         }
+    free((void *)in);
     return 0;
 }
 

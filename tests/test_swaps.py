@@ -28,7 +28,7 @@ SWAP_KINDS = [(1, 0), (1, 1), (2, 0), (2, 1), (3, 1)]
 def tiny_scenario(rng, S=4, sibs_x=1, sibs_z=1, extra_kid=True, only_child=False):
     """P,Q -> x (+ sibs); paz,maz -> z (+ sibs); x,z -> k (+ a second marriage of z)."""
     n = 0
-    ped = Pedigree(24, 12)
+    ped = Pedigree(24 + sibs_x + sibs_z, 12)
     ids = {}
     for name, founder in [("P", True), ("Q", True), ("paz", True), ("maz", False), ("x", False), ("z", False), ("k", False)]:
         ids[name] = n; ped.add_individual(n, founder); n += 1
@@ -120,6 +120,14 @@ def test_oracle_swaps_match_rewired_sweep(seed):
     assert check_swaps_vs_rewired(eng, sc) >= 5
 
 
+def test_swaps_with_very_large_sibships():
+    """70 siblings next to z and 66 next to x: no fixed per-marriage edge limit anywhere."""
+    rng = np.random.default_rng(31)
+    sc, _ = tiny_scenario(rng, S=3, sibs_x=66, sibs_z=70)
+    eng = make_oracle(sc.S, sc.ped.cap_indiv + 160, sc.ped.cap_marr)
+    assert check_swaps_vs_rewired(eng, sc, rtol=1e-9) >= 5
+
+
 def test_swap_argument_errors():
     rng = np.random.default_rng(5)
     sc, ids = tiny_scenario(rng)
@@ -173,3 +181,19 @@ def test_gpu_swaps_match_oracle_on_forests(seed):
         if n > 60:
             break
     assert n >= 5
+
+
+@pytest.mark.gpu
+def test_gpu_swaps_with_very_large_sibships():
+    rng = np.random.default_rng(31)
+    sc, _ = tiny_scenario(rng, S=40, sibs_x=66, sibs_z=70)
+    gpu = make_gpu(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    ora = make_oracle(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    for psc, swaps, only, labels in pruned_cases(sc):
+        for e in (gpu, ora):
+            psc.upload(e)
+            e.sweep(psc.ped.view(labels)[0])
+        view3, _ = psc.ped.view(labels, only=only)
+        np.testing.assert_allclose(gpu.eval_swaps(view3, swaps), ora.eval_swaps(view3, swaps), rtol=1e-11, atol=1e-9)
+        for i in np.flatnonzero(psc.ped.active)[::9]:
+            np.testing.assert_allclose(gpu.get_stub(int(i)), ora.get_stub(int(i)), rtol=1e-12)
