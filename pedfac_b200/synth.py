@@ -103,7 +103,16 @@ def simulate(n_total: int, n_loci: int, *, soft: bool, seed: int = 46, n_gen: in
                     union(int(m_), int(f_))
                     break
         if not couples:
-            couples = [(int(males[0]), int(females[0]))]
+            # nothing fits the component budget: take any couple from two different components; if the
+            # whole generation is one component already, its kids stay parentless (never close a loop)
+            for m_ in males:
+                f_ok = [int(f_) for f_ in females if find(int(f_)) != find(int(m_))]
+                if f_ok:
+                    couples = [(int(m_), f_ok[0])]
+                    union(int(m_), f_ok[0])
+                    break
+        if not couples:
+            continue
         couple_of_kid = np.sort(rng.integers(0, len(couples), size=len(kids)))
         carr = np.array(couples, dtype=np.int32)
         pa[kids], ma[kids] = carr[couple_of_kid, 0], carr[couple_of_kid, 1]

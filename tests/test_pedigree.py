@@ -35,3 +35,17 @@ def test_synthetic_data_shapes_and_frequencies():
     ped = synth.truth_pedigree(d, d.n_total + 8, d.n_total)
     labels, n = ped.components()
     assert n >= 1 and (labels[: d.n_total] >= 0).all()
+
+
+def test_synthetic_truth_is_a_forest_for_any_depth():
+    """The sampler's model is acyclic (loops abort: _CheckPed), so the synthetic truth must be a forest
+    whatever the number of generations — small deep pedigrees once got a loop-closing fallback couple."""
+    from pedfac_b200 import synth
+    for n_gen in (2, 3, 4, 5, 6):
+        for seed in range(6):
+            d = synth.simulate(120, 8, soft=False, seed=seed, n_gen=n_gen)
+            ped = synth.truth_pedigree(d, 4000, 4000)
+            _, n_cc = ped.components()
+            nodes = int(ped.active.sum()) + len(ped.marriages)
+            edges = sum(2 + len(m.kids) for m in ped.marriages.values())
+            assert edges == nodes - n_cc, (n_gen, seed)
