@@ -191,6 +191,7 @@ struct Ped {
     std::vector<Choice> ch;
     std::vector<double> chll;
     int prev[3] = {-1, -1, -1}, neu[4] = {-1, -1, -1, 0}, picked = -1, t = 0;
+    int keep[3] = {-1, -1, -1};                                // chosen pa, ma, marriage: not trimmed (see PickAndUpdate)
     // candidate lists by sex (0 unknown, 1 male, 2 female)
     std::vector<std::pair<int, double>> cand[3];
     PF_ENGINE_T *eng = nullptr;
@@ -403,6 +404,7 @@ static void TrimPed(Ped &p, int x)
 {
     Indiv &ix = p.indiv[x];
     if (ix.observed) return;
+    if (x == p.keep[0] || x == p.keep[1]) return;
     if (ix.M.size() > 1) return;
     if (ix.M.size() == 1 && ix.edge[0] < 2) return;
     p.indivActive[x] = 0;
@@ -414,7 +416,7 @@ static void TrimPed(Ped &p, int x)
     const int m = ix.M[0];
     hist_edge(p, 0, m, x);
     Marr &mm = p.marr[m];
-    if (mm.nEdges() == 3) {
+    if (mm.nEdges() == 3 && m != p.keep[2]) {
         p.marrActive[m] = 0;
         p.freeMarr.push_back(m);
         hist_edge(p, 0, m, mm.pa);
@@ -937,23 +939,19 @@ static void PickAndUpdate(Ped &p, int kid)
     fprintf(p.fLL, "%d %d %f\n", p.iter, kid, p.picked >= 0 ? p.chll[p.picked] : 0.0);
     const bool swap = p.picked >= 0 && p.ch[p.picked].kind == 3;
     if (!swap) {                                               // @0x100016be2: a swap keeps the previous parents
+        // Trimming an ex-parent cascades to its unobserved ancestors, and only the ex-parents themselves
+        // are hidden from the enumeration: the choice can be such an ancestor (or the marriage of two).
+        // The reference trims first and then links the kid to the freed slot (_PickAndUpdate@0x100016cf5
+        // uses new[] unchecked). Here the chosen individuals and marriage survive the trimming, with
+        // their own ancestors, so the pedigree after the step is the one that was scored.
+        p.keep[0] = p.neu[0]; p.keep[1] = p.neu[1]; p.keep[2] = p.neu[2];
         if (p.neu[0] != p.prev[0] && p.prev[0] > -1) {
             TrimPed(p, p.prev[0]); UpdateConComp(p, p.prev[0]); RevertSex(p, p.prev[0]);
         }
         if (p.prev[0] != p.prev[1] && p.neu[1] != p.prev[1] && p.prev[1] > -1) {
             TrimPed(p, p.prev[1]); UpdateConComp(p, p.prev[1]); RevertSex(p, p.prev[0]);   // sic: prev.pa
         }
-    }
-    // The trimming above can delete what was just chosen: an unobserved ancestor of a trimmed
-    // ex-parent (only the ex-parents themselves are hidden from the enumeration), or the marriage of
-    // such ancestors. The reference then links the kid to a freed slot (_PickAndUpdate@0x100016cf5 uses
-    // new[] unchecked) and carries an inactive individual inside an active marriage from there on.
-    // Such an ancestor carries no information (its stub is the founder prior), so the choice means
-    // "a new unobserved parent": that is what is created here instead.
-    if (!swap) {
-        if (p.neu[2] != -1 && !p.marrActive[p.neu[2]]) p.neu[2] = -1;
-        if (p.neu[0] >= 0 && !p.indivActive[p.neu[0]]) p.neu[0] = -1;
-        if (p.neu[1] >= 0 && !p.indivActive[p.neu[1]]) p.neu[1] = p.neu[3] == 1 ? p.neu[0] : -1;
+        p.keep[0] = p.keep[1] = p.keep[2] = -1;
     }
     const int sel_pa = p.neu[0], sel_ma = p.neu[1];            // v54 / v58 of the swap rewiring below
     int m = p.neu[2], pa = p.neu[0], ma = p.neu[1];
@@ -1080,6 +1078,7 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
     EvalMoves(p, o, id);                                       // runs the pending sweep together with its first batch
     p.t++;
     if (p.check) p.chll_data = p.chll;
+    if (getenv("PEDFAC_DUMP_PRE") && getenv("PEDFAC_DUMP_KID") && atoi(getenv("PEDFAC_DUMP_KID")) == id) DumpState(p, getenv("PEDFAC_DUMP_PRE"));   // last visit wins
     AddObsFracPrior(p, id);
     const int dbg_prev[3] = {p.prev[0], p.prev[1], p.prev[2]};
     PickAndUpdate(p, id);

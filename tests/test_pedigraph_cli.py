@@ -239,13 +239,25 @@ def test_geno_parser_accepts_equivalent_spellings(tmp_path):
     assert r.returncode != 0 and "fewer SNPs than reported" in r.stderr and "obs: 48 , exp: 50" in r.stderr
 
 
-def test_choice_deleted_by_the_same_steps_trimming(tmp_path):
-    """Found by tools/trace_soak.py: with two unobserved layers a kid can pick an unobserved ancestor
-    of its own ex-parent; trimming the ex-parent then deletes that ancestor (and its marriage) in
-    the same step. The reference links the kid to the freed slot; here a new unobserved parent is
-    created instead, and PEDFAC_CHECK (structure + likelihood) must hold through the run."""
-    d = synth.simulate(245, 58, soft=False, seed=500392788, observe_frac=0.8)
+TRIM_CASES = [
+    # n, S, soft, data seed, rng seeds, max_unobs, observe_frac (prior), iterations, generations
+    (245, 58, False, 500392788, (614661122, 956123187), 2, 0.8, 3, 3),
+    # the chosen ancestor descends from a selfing: its stub is not the founder prior, so replacing it
+    # with a new unobserved parent (an earlier fix) left a pedigree 1.07 log units off the scored one
+    (362, 60, True, 138171697, (594499943, 43070780), 1, 0.5, 2, 5),
+]
+
+
+@pytest.mark.parametrize("case", TRIM_CASES, ids=["two-layers", "selfed-ancestor"])
+def test_choice_survives_the_same_steps_trimming(tmp_path, case):
+    """Found by tools/trace_soak.py: a kid can pick an unobserved ancestor of its own ex-parent (or
+    the marriage of two); trimming the ex-parent then cascades to that ancestor in the same step.
+    The reference links the kid to the freed slot; here the chosen individuals and marriage are
+    kept through the trimming, and PEDFAC_CHECK (structure + scored == resulting likelihood) must
+    hold through the run."""
+    n, S, soft, dseed, seeds, unobs, ofrac, iters, gens = case
+    d = synth.simulate(n, S, soft=soft, seed=dseed, observe_frac=0.8, n_gen=gens)
     rd = tmp_path / "t"
-    frontend.write_run_dir(d, rd, seeds=(614661122, 956123187), max_unobs=2, max_age=2.0, observe_frac=0.8)
-    r = run(REF, rd, n_iter=3, extra=("-s",), env={"PEDFAC_CHECK": "1", "PEDFAC_STATS": "1"})
+    frontend.write_run_dir(d, rd, seeds=seeds, max_unobs=unobs, max_age=2.0, observe_frac=ofrac)
+    r = run(REF, rd, n_iter=iters, extra=("-s",), env={"PEDFAC_CHECK": "1", "PEDFAC_STATS": "1"})
     assert r.returncode == 0, r.stderr[-800:]

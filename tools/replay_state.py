@@ -6,7 +6,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path[:0] = [str(ROOT)]
 import numpy as np
 from oracle.binding import OracleEngine
-from pedfac_b200 import Pedigree, PF_PROP_PRONG, PF_PROP_TRIO
+from pedfac_b200 import Pedigree, PF_PROP_PRONG, PF_PROP_SELFING, PF_PROP_TRIO
 
 run, state = Path(sys.argv[1]), Path(sys.argv[2])
 prior = {l.split()[0]: l.split()[1:] for l in (run / "prior.txt").read_text().splitlines() if l.strip()}
@@ -47,6 +47,7 @@ if len(sys.argv) > 3:
     mm = ped.marriages[m]
     print("kid", kid, "is in marriage", m, "pa", mm.pa, "ma", mm.ma, "kids", mm.kids, "founder flag", bool(ped.founder[kid]))
     after = float(np.sum(ll))
+    was_selfing = mm.selfing
     pa, ma, prev = ped.detach_kid(kid)
     labels2, n2 = ped.components()
     view2, glob2 = ped.view(labels2)
@@ -55,6 +56,9 @@ if len(sys.argv) > 3:
     g = {int(x): j for j, x in enumerate(glob2)}
     if prev is not None:
         ls = e.eval(kid, [(PF_PROP_PRONG, -1, -1, prev)])[0]
+        scored = before + ls - ll2[g[int(labels2[kid])]] - ll2[g[int(labels2[pa])]]
+    elif was_selfing:
+        ls = e.eval(kid, [(PF_PROP_SELFING, pa, -1, -1)])[0]
         scored = before + ls - ll2[g[int(labels2[kid])]] - ll2[g[int(labels2[pa])]]
     else:
         ls = e.eval(kid, [(PF_PROP_TRIO, pa, ma, -1)])[0]
