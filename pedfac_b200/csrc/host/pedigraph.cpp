@@ -486,6 +486,8 @@ static void dirty_view(Ped &p, ViewBuf &b)
     build_view(p, want, b);
 }
 
+static const double kUnderflowMeanPerLocus = -354.0;          // half of log(DBL_MIN)
+
 // store the component log-likelihoods a sweep returned and recompute the total
 // (_UpdateProb@0x10001dd0c-0x10001dd65)
 static void store_sweep(Ped &p, const ViewBuf &b, const std::vector<double> &ll)
@@ -494,13 +496,15 @@ static void store_sweep(Ped &p, const ViewBuf &b, const std::vector<double> &ll)
     for (size_t j = 0; j < b.labels.size(); j++) {
         p.LLcc[b.labels[j]] = ll[j];
         // Messages are unnormalised products (as in the reference): once a component's partition value
-        // per locus approaches the smallest normal double, its messages lose precision and then vanish.
-        if (ll[j] < -640.0 * p.S) {
+        // at a locus approaches the smallest normal double (log = -708), its messages lose precision and
+        // then vanish. Only the sum over loci comes back, and the loci spread widely around their mean
+        // (a sibship of 700 unrelated individuals: mean -449, minimum -737), hence half the range.
+        if (ll[j] < kUnderflowMeanPerLocus * p.S) {
             p.underflow_steps++;
             if (!p.underflow_warned) {
                 p.underflow_warned = true;
-                fprintf(stderr, "warning: a component's log-likelihood is %.1f over %d loci (%.0f per locus): its unnormalised messages are at the "
-                                "edge of the double range (the limit of the reference's arithmetic as well); scores involving it are unreliable\n",
+                fprintf(stderr, "warning: a component's log-likelihood is %.1f over %d loci (%.0f per locus): its unnormalised messages can leave "
+                                "the double range at some loci (the limit of the reference's arithmetic as well); scores involving it are unreliable\n",
                         ll[j], p.S, ll[j] / p.S);
             }
         }
@@ -1090,7 +1094,7 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
         Propagating_msg(p);
         const double want = p.chll_data[p.picked], got = p.LLtot;
         bool in_range = true;                                  // components beyond the double range cannot be checked
-        for (int c = 0; c < p.nCC; c++) in_range = in_range && !(p.LLcc[c] < -600.0 * p.S);
+        for (int c = 0; c < p.nCC; c++) in_range = in_range && !(p.LLcc[c] < kUnderflowMeanPerLocus * p.S);
         if (in_range && !(fabs(want - got) <= 1e-9 * std::max(1.0, fabs(got)))) {
             if (getenv("PEDFAC_DUMP")) DumpState(p, getenv("PEDFAC_DUMP"));
             fprintf(stderr, "PEDFAC_CHECK: iter %d kid %d choice %d (kind %d swap %d/%d): scored %.12f, pedigree has %.12f\n",

@@ -1190,8 +1190,7 @@ static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2
         }
     }
     if ((size_t)n * sizeof(double) > e->h_result_cap) {
-        if (e->h_result) cudaFreeHost(e->h_result);
-    if (e->h_mail) cudaFreeHost(e->h_mail);
+        if (e->h_result) CU(cudaFreeHost(e->h_result));
         e->h_result = nullptr; e->h_result_cap = 0;
         const size_t want = (size_t)n * sizeof(double) * 2 + 4096;
         CU(cudaMallocHost(&e->h_result, want));

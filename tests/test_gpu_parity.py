@@ -381,6 +381,33 @@ def test_gpu_results_without_the_mailbox_are_identical(monkeypatch):
     np.testing.assert_array_equal(a.eval(kid, props), b.eval(kid, props))
 
 
+def test_gpu_small_results_after_growing_large_ones():
+    """Results beyond the mailbox size (4096 doubles) go through a pinned buffer that grows on
+    demand. A stray free of the mailbox in that growth path once left later small results reading
+    freed memory, and a second growth failed with "invalid argument" (found by
+    tools/gpu_chain_soak.py in a degenerate chain state with huge proposal lists)."""
+    rng = np.random.default_rng(4097)
+    sc = random_forest(rng, n_indiv=90, S=70, max_kids=4, max_comp=30)
+    labels, _ = sc.ped.components()
+    view, _ = sc.ped.view(labels)
+    g = Engine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    o = OracleEngine(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr)
+    sc.upload(g); sc.upload(o)
+    np.testing.assert_allclose(g.sweep(view), o.sweep(view), rtol=1e-12, atol=1e-9)
+    has_parents = {k for mm in sc.ped.marriages.values() for k in mm.kids}
+    kid = next(int(i) for i in np.flatnonzero(sc.ped.active) if int(i) not in has_parents)
+    others = [int(i) for i in np.flatnonzero(sc.ped.active) if labels[i] != labels[kid]]
+    small = [(PF_PROP_TRIO, c, -1, -1) for c in others[:20]]
+    want_small = o.eval(kid, small)
+    for n_big in (5000, 12000, 30000):
+        big = [(PF_PROP_TRIO, others[j % len(others)], -1, -1) for j in range(n_big)]
+        got = g.eval(kid, big)
+        np.testing.assert_allclose(got[:len(others)], o.eval(kid, big[:len(others)]), rtol=1e-12, atol=1e-9)
+        np.testing.assert_array_equal(got[len(others):2 * len(others)], got[:len(others)])
+        np.testing.assert_allclose(g.eval(kid, small), want_small, rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(g.sweep(view), o.sweep(view), rtol=1e-12, atol=1e-9)
+
+
 def test_gpu_large_chain_batch_is_planned_in_parallel_and_matches_the_oracle():
     """24 chains with different graphs in one sweep_batch call: the views are planned by several
     host threads and the partial plans concatenated; every chain must match its own oracle, and a
