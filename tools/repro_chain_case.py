@@ -1,5 +1,5 @@
 """Debug aid: re-run one case of tools/gpu_chain_soak.py (same RNG stream) with PEDFAC_CHECK and state dumps.
-python tools/repro_chain_case.py SOAK_SEED CASE [binary]  ->  gpurun_out/case_{pre,post,err}.txt"""
+CASE_ITERS=4 python tools/repro_chain_case.py SOAK_SEED CASE [binary]  ->  gpurun_out/case_{pre,post,err}.txt"""
 import os, shutil, subprocess, sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
@@ -21,7 +21,7 @@ rd = Path(os.environ.get("CASE_DIR", "/tmp/chain_case")); shutil.rmtree(rd, igno
 frontend.write_run_dir(d, rd, seeds=seeds, max_unobs=unobs, max_age=max_age, seed_marriages=seeded)
 if os.environ.get("CASE_ONLY_WRITE"): sys.exit(0)
 out = ROOT / "gpurun_out"; out.mkdir(exist_ok=True)
-args = [binary, "-d", str(rd), "-n", "1", "-r", str(rd / "rand")] + (["-s"] if selfing else [])
+args = [binary, "-d", str(rd), "-n", os.environ.get("CASE_ITERS", "1"), "-r", str(rd / "rand")] + (["-s"] if selfing else [])
 env = dict(os.environ, PEDFAC_CHECK="1", PEDFAC_DEBUG="1", PEDFAC_DUMP=str(out / "case_post.txt"))
 r = subprocess.run(args, capture_output=True, text=True, env=env)
 (out / "case_err.txt").write_text(r.stderr[-30000:])
