@@ -1,0 +1,275 @@
+/* macho_run — runs the reference's own `exec/pedigraph` (a macOS Mach-O x86_64 executable, the only
+ * implementation of the hot path that ngthomas/pedFac ships) as a user-space image on x86-64 Linux.
+ *
+ * TEST INFRASTRUCTURE (oracle/): only tests/, __graft_entry__.smoke() and bench.py's reference /
+ * cpu_baseline legs may execute what this builds. Nothing under pedfac_b200/ may.
+ *
+ * Why this works: macOS x86-64 and Linux x86-64 share the System V calling convention (varargs
+ * included), and the binary imports nothing but 47 plain libc/libm functions plus
+ * ___stack_chk_guard, ___stderrp and dyld_stub_binder (see its LC_DYSYMTAB indirect symbol table).
+ * The loader
+ *   1. takes the Mach-O bytes embedded at build time (.incbin of /root/reference/exec/pedigraph —
+ *      the recipe reads the file where it lies; the output goes to oracle/_ref/, git-ignored),
+ *   2. maps every LC_SEGMENT_64 at its own vmaddr (0x100000000…, so no rebasing is needed),
+ *   3. fills the S_NON_LAZY_SYMBOL_POINTERS (__got) and S_LAZY_SYMBOL_POINTERS (__la_symbol_ptr)
+ *      slots named by the indirect symbol table with the glibc function of the same name
+ *      (leading underscore stripped) or with one of the few shims below,
+ *   4. calls LC_MAIN's entry with (argc, argv, envp, apple).
+ * The code that runs is the reference's machine code, byte for byte; what differs from a Mac is
+ * the C library underneath (glibc's qsort / log / exp / pow / strtod / printf instead of
+ * libSystem's). Ties in qsort and last-ulp libm differences are therefore glibc's.
+ *
+ * One deliberate accommodation: `_AllocIndiv@0x100008ac1` allocates every
+ * marriage's kid array as malloc(8) and nothing ever grows it, while `_PickAndUpdate@0x100016d9c`
+ * appends kids without bound. On a Mac the overflow scribbles over the neighbouring tiny block;
+ * here the malloc issued from that one call site (return address 0x100008ac6) is padded to
+ * PEDFAC_REF_KIDCAP pointers (default 4096) so that the binary's *intended* semantics (the array
+ * holds all kids) are what is observed. PEDFAC_REF_KIDCAP=1 gives the literal malloc(8).
+ */
+#define _GNU_SOURCE
+#include <ctype.h>
+#include <dlfcn.h>
+#include <errno.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/time.h>
+#include <time.h>
+#include <unistd.h>
+#include <signal.h>
+#include <ucontext.h>
+
+#ifndef REF_MACHO_PATH
+#error "build with -DREF_MACHO_PATH=\"/root/reference/exec/pedigraph\" (see oracle/Makefile)"
+#endif
+__asm__(".section .rodata\n.balign 4096\n.globl ref_macho_begin\nref_macho_begin:\n.incbin \"" REF_MACHO_PATH
+        "\"\n.globl ref_macho_end\nref_macho_end:\n.byte 0\n.text\n");
+extern const unsigned char ref_macho_begin[], ref_macho_end[];
+
+/* ---- the Mach-O structures that are needed (restated from the public <mach-o/loader.h> layout) */
+struct mach_header_64 { uint32_t magic; int32_t cputype, cpusubtype; uint32_t filetype, ncmds, sizeofcmds, flags, reserved; };
+struct load_command { uint32_t cmd, cmdsize; };
+struct segment_command_64 { uint32_t cmd, cmdsize; char segname[16]; uint64_t vmaddr, vmsize, fileoff, filesize; int32_t maxprot, initprot; uint32_t nsects, flags; };
+struct section_64 { char sectname[16], segname[16]; uint64_t addr, size; uint32_t offset, align, reloff, nreloc, flags, reserved1, reserved2, reserved3; };
+struct symtab_command { uint32_t cmd, cmdsize, symoff, nsyms, stroff, strsize; };
+struct dysymtab_command { uint32_t cmd, cmdsize, ilocalsym, nlocalsym, iextdefsym, nextdefsym, iundefsym, nundefsym, tocoff, ntoc,
+                          modtaboff, nmodtab, extrefsymoff, nextrefsyms, indirectsymoff, nindirectsyms, extreloff, nextrel, locreloff, nlocrel; };
+struct entry_point_command { uint32_t cmd, cmdsize; uint64_t entryoff, stacksize; };
+struct nlist_64 { uint32_t n_strx; uint8_t n_type, n_sect; uint16_t n_desc; uint64_t n_value; };
+enum { LC_SEGMENT_64 = 0x19, LC_SYMTAB = 0x2, LC_DYSYMTAB = 0xb, LC_MAIN = 0x80000028u,
+       S_NON_LAZY_SYMBOL_POINTERS = 6, S_LAZY_SYMBOL_POINTERS = 7,
+       INDIRECT_SYMBOL_LOCAL = (int)0x80000000u, INDIRECT_SYMBOL_ABS = 0x40000000 };
+
+/* ---- shims */
+static uint64_t shim_stack_guard = 0x5eedfacec0ffee00ull;
+static long kid_cap = 4096;
+static int trace_calls = 0;
+
+/* ____chkstk_darwin: stack probe, called with the size in rax and required to preserve every
+ * register. Linux grows the main stack on demand, so there is nothing to do. */
+__asm__(".text\n.globl shim_chkstk\n.type shim_chkstk,@function\nshim_chkstk:\n ret\n");
+extern void shim_chkstk(void);
+
+static void shim_stack_chk_fail(void) { fprintf(stderr, "macho_run: stack check failed inside the reference\n"); abort(); }
+static void shim_stub_binder(void) { fprintf(stderr, "macho_run: dyld_stub_binder reached (unbound import)\n"); abort(); }
+static int *shim_error(void) { return &errno; }
+
+static void *shim_malloc(size_t n) {
+    uintptr_t ra = (uintptr_t)__builtin_return_address(0);
+    if (ra == 0x100008ac6ull && n == 8 && kid_cap > 1) n = 8 * (size_t)kid_cap;     /* App. D.1, see header */
+    return malloc(n);
+}
+
+/* macOS struct timeval is {long tv_sec; int tv_usec;} (16 bytes with padding): glibc's 8-byte
+ * tv_usec write stays inside it, but keep the layouts explicit. */
+struct darwin_timeval { long tv_sec; int tv_usec; int pad; };
+static int shim_gettimeofday(struct darwin_timeval *tv, void *tz) {
+    (void)tz; struct timeval t; int r = gettimeofday(&t, 0);
+    if (tv) { tv->tv_sec = t.tv_sec; tv->tv_usec = (int)t.tv_usec; }
+    return r;
+}
+static int shim_mkdir(const char *p, unsigned mode) { return mkdir(p, (mode_t)(mode & 07777)); }
+static void shim_exit(int c) { fflush(0); exit(c); }
+
+static const struct { const char *name; void *fn; } shims[] = {
+    {"____chkstk_darwin", (void *)shim_chkstk}, {"___error", (void *)shim_error},
+    {"___stack_chk_fail", (void *)shim_stack_chk_fail}, {"___stack_chk_guard", (void *)&shim_stack_guard},
+    {"___stderrp", (void *)&stderr}, {"___stdoutp", (void *)&stdout}, {"___stdinp", (void *)&stdin},
+    {"dyld_stub_binder", (void *)shim_stub_binder}, {"_malloc", (void *)shim_malloc},
+    {"_gettimeofday", (void *)shim_gettimeofday}, {"_mkdir", (void *)shim_mkdir}, {"_exit", (void *)shim_exit},
+    /* libm by address, so that the link keeps libm whatever --as-needed says */
+    {"_exp", (void *)(double (*)(double))exp}, {"_log", (void *)(double (*)(double))log},
+    {"_pow", (void *)(double (*)(double, double))pow},
+    /* fortified libc entry points: same signatures in glibc (minus one underscore) */
+    {"___memset_chk", 0}, {"___snprintf_chk", 0}, {"___sprintf_chk", 0}, {"___strncpy_chk", 0},
+};
+
+static void *resolve(const char *name) {
+    for (size_t i = 0; i < sizeof shims / sizeof *shims; ++i)
+        if (!strcmp(shims[i].name, name) && shims[i].fn) return shims[i].fn;
+    void *p = dlsym(RTLD_DEFAULT, name + 1);                 /* "_log" -> "log", "___x_chk" -> "__x_chk" */
+    if (!p) { fprintf(stderr, "macho_run: no Linux counterpart for import %s\n", name); exit(120); }
+    return p;
+}
+
+/* A fault inside the reference: print where (Mach-O VM addresses; the binary is -O0 with frame
+ * pointers, so the rbp chain is a usable backtrace) and exit like a crash would. */
+static void on_fault(int sig, siginfo_t *si, void *uc_) {
+    ucontext_t *uc = uc_;
+    uintptr_t rip = (uintptr_t)uc->uc_mcontext.gregs[REG_RIP], rbp = (uintptr_t)uc->uc_mcontext.gregs[REG_RBP];
+    fprintf(stderr, "macho_run: signal %d in the reference at rip=0x%lx, fault address %p\n  frames:", sig, (unsigned long)rip, si->si_addr);
+    for (int k = 0; k < 12 && rbp > 0x1000 && (rbp & 7) == 0; ++k) {
+        uintptr_t ret = ((uintptr_t *)rbp)[1], next = ((uintptr_t *)rbp)[0];
+        fprintf(stderr, " 0x%lx", (unsigned long)ret);
+        if (next <= rbp) break;
+        rbp = next;
+    }
+    fprintf(stderr, "\n");
+    fflush(0);
+    _exit(128 + sig);
+}
+
+/* PEDFAC_REF_TRACE_FN=0x100019ec0,0x...: a call trace of the named reference functions (debug aid).
+ * Every function of the -O0 binary starts with `push rbp` (0x55); the byte is replaced by int3 and
+ * the SIGTRAP handler prints the integer argument registers, then performs the push itself. */
+/* PEDFAC_REF_DUMP=1 additionally prints the reference's pedigree state (layout: SURVEY.md App. B)
+ * whenever the traced function is `_MCMC_sampling@0x100019ec0` (rdi = ped, esi = focal slot), in the
+ * format of the product sampler's PEDFAC_DEBUG_STATE lines so the two can be diffed. */
+#define RD(T, p, off) (*(T *)((char *)(p) + (off)))
+static void dump_ref_state(FILE *f, char *ped, int id) {
+    int nI = *RD(int *, ped, 0x10), nM = *RD(int *, ped, 0x38);
+    char **indiv = RD(char **, ped, 0x40), **mnode = RD(char **, ped, 0x58);
+    unsigned char *iact = RD(unsigned char *, ped, 0xe0), *mact = RD(unsigned char *, ped, 0xe8);
+    int *cc = RD(int *, ped, 0xc0);
+    fprintf(f, "state before %d nCC %d\n", id, *RD(int *, ped, 0xb8));
+    for (int i = 0; i < nI; ++i) {
+        if (!(iact[i] & 1)) continue;
+        char *x = indiv[i];
+        fprintf(f, "I %d gen %d sex %d deg %d founder %d red %d queued %d cc %d :", i, *RD(int *, x, 0x10), RD(int, x, 0x18),
+                *RD(int *, x, 0x48), *RD(unsigned char *, x, 0x40) & 1, RD(unsigned char *, x, 0xa0)[0] & 1, RD(unsigned char *, x, 0xa0)[1] & 1, cc[i]);
+        int nm = *RD(int *, x, 0x50);
+        for (int k = 0; k < nm; ++k) fprintf(f, " %d/%d", *RD(int *, RD(char **, x, 0x60)[k], 0x48), RD(int *, x, 0x58)[k]);
+        fprintf(f, "\n");
+    }
+    for (int m = 0; m < nM; ++m) {
+        if (!(mact[m] & 1)) continue;
+        char *y = mnode[m];
+        int ne = *RD(int *, y, 0x20), self = *RD(unsigned char *, y, 0x50) & 1;
+        char *pa = *RD(char **, y, 0x00), *ma = *RD(char **, y, 0x08);
+        fprintf(f, "M %d pa %d ma %d self %d kids", m, pa ? *RD(int *, pa, 0x28) : -1, (ma && !self) ? *RD(int *, ma, 0x28) : -1, self);
+        for (int k = 0; k < ne - 2; ++k) fprintf(f, " %d", *RD(int *, RD(char **, y, 0x10)[k], 0x28));
+        fprintf(f, "\n");
+    }
+}
+
+static void on_trap(int sig, siginfo_t *si, void *uc_) {
+    (void)sig; (void)si;
+    ucontext_t *uc = uc_;
+    greg_t *g = uc->uc_mcontext.gregs;
+    if ((unsigned long)g[REG_RIP] - 1 == 0x100019ec0ul && getenv("PEDFAC_REF_DUMP")) dump_ref_state(stderr, (char *)g[REG_RDI], (int)g[REG_RSI]);
+    fprintf(stderr, "ref-call 0x%lx rdi=%ld rsi=%ld rdx=%ld rcx=%ld r8=%ld\n", (unsigned long)g[REG_RIP] - 1,
+            (long)g[REG_RDI], (long)g[REG_RSI], (long)g[REG_RDX], (long)g[REG_RCX], (long)g[REG_R8]);
+    g[REG_RSP] -= 8;
+    *(uint64_t *)g[REG_RSP] = (uint64_t)g[REG_RBP];
+}
+
+static void die(const char *what) { fprintf(stderr, "macho_run: %s\n", what); exit(121); }
+
+int main(int argc, char **argv, char **envp) {
+    const unsigned char *img = ref_macho_begin;
+    size_t img_size = (size_t)(ref_macho_end - ref_macho_begin);
+    const struct mach_header_64 *mh = (const void *)img;
+    if (img_size < sizeof *mh || mh->magic != 0xfeedfacfu || mh->cputype != 0x01000007 || mh->filetype != 2)
+        die("embedded file is not an x86_64 Mach-O executable");
+    if (getenv("PEDFAC_REF_KIDCAP")) kid_cap = atol(getenv("PEDFAC_REF_KIDCAP"));
+    trace_calls = getenv("PEDFAC_REF_TRACE") != 0;
+
+    const struct symtab_command *st = 0; const struct dysymtab_command *dst = 0; const struct entry_point_command *ep = 0;
+    const unsigned char *lc = img + sizeof *mh;
+    uint64_t text_vm = 0;
+    /* pass 1: map the segments */
+    for (uint32_t i = 0; i < mh->ncmds; ++i) {
+        const struct load_command *c = (const void *)lc;
+        if (c->cmd == LC_SEGMENT_64) {
+            const struct segment_command_64 *s = (const void *)lc;
+            if (s->initprot != 0 && s->vmsize) {                    /* skips __PAGEZERO */
+                size_t len = (s->vmsize + 4095) & ~4095ull;
+                void *want = (void *)s->vmaddr;
+                void *got = mmap(want, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_FIXED_NOREPLACE, -1, 0);
+                if (got != want) die("cannot map a segment at its preferred address");
+                if (s->fileoff + s->filesize > img_size) die("segment beyond the end of the file");
+                memcpy(want, img + s->fileoff, s->filesize);
+                if (!strcmp(s->segname, "__TEXT")) text_vm = s->vmaddr;
+            }
+        } else if (c->cmd == LC_SYMTAB) st = (const void *)lc;
+        else if (c->cmd == LC_DYSYMTAB) dst = (const void *)lc;
+        else if (c->cmd == LC_MAIN) ep = (const void *)lc;
+        lc += c->cmdsize;
+    }
+    if (!st || !dst || !ep || !text_vm) die("missing LC_SYMTAB / LC_DYSYMTAB / LC_MAIN / __TEXT");
+    const struct nlist_64 *syms = (const void *)(img + st->symoff);
+    const char *strtab = (const char *)(img + st->stroff);
+    const uint32_t *indirect = (const void *)(img + dst->indirectsymoff);
+
+    /* pass 2: bind the symbol-pointer sections, then apply the segments' protections */
+    lc = img + sizeof *mh;
+    for (uint32_t i = 0; i < mh->ncmds; ++i) {
+        const struct load_command *c = (const void *)lc;
+        if (c->cmd == LC_SEGMENT_64) {
+            const struct segment_command_64 *s = (const void *)lc;
+            const struct section_64 *sec = (const void *)(lc + sizeof *s);
+            for (uint32_t k = 0; k < s->nsects; ++k, ++sec) {
+                uint32_t type = sec->flags & 0xff;
+                if (type != S_NON_LAZY_SYMBOL_POINTERS && type != S_LAZY_SYMBOL_POINTERS) continue;
+                uint64_t n = sec->size / 8;
+                for (uint64_t j = 0; j < n; ++j) {
+                    uint32_t is = indirect[sec->reserved1 + j];
+                    if (is & ((uint32_t)INDIRECT_SYMBOL_LOCAL | INDIRECT_SYMBOL_ABS)) continue;
+                    if (is >= st->nsyms) die("indirect symbol out of range");
+                    const char *name = strtab + syms[is].n_strx;
+                    void *p = resolve(name);
+                    if (trace_calls) fprintf(stderr, "macho_run: bind %s.%s[%lu] %s -> %p\n", sec->segname, sec->sectname, (unsigned long)j, name, p);
+                    ((void **)sec->addr)[j] = p;
+                }
+            }
+        }
+        lc += c->cmdsize;
+    }
+    if (getenv("PEDFAC_REF_TRACE_FN")) {
+        char *list = strdup(getenv("PEDFAC_REF_TRACE_FN"));
+        for (char *t = strtok(list, ","); t; t = strtok(0, ",")) {
+            unsigned char *fn = (unsigned char *)(uintptr_t)strtoull(t, 0, 16);
+            if (*fn != 0x55) die("PEDFAC_REF_TRACE_FN: address does not start with push rbp");
+            *fn = 0xcc;
+        }
+        struct sigaction st_; memset(&st_, 0, sizeof st_);
+        st_.sa_sigaction = on_trap; st_.sa_flags = SA_SIGINFO;
+        sigaction(SIGTRAP, &st_, 0);
+    }
+    lc = img + sizeof *mh;
+    for (uint32_t i = 0; i < mh->ncmds; ++i) {
+        const struct load_command *c = (const void *)lc;
+        if (c->cmd == LC_SEGMENT_64) {
+            const struct segment_command_64 *s = (const void *)lc;
+            if (s->initprot != 0 && s->vmsize) {
+                int prot = ((s->initprot & 1) ? PROT_READ : 0) | ((s->initprot & 2) ? PROT_WRITE : 0) | ((s->initprot & 4) ? PROT_EXEC : 0);
+                if (mprotect((void *)s->vmaddr, (s->vmsize + 4095) & ~4095ull, prot)) die("mprotect failed");
+            }
+        }
+        lc += c->cmdsize;
+    }
+
+    struct sigaction sa; memset(&sa, 0, sizeof sa);
+    sa.sa_sigaction = on_fault; sa.sa_flags = SA_SIGINFO;
+    sigaction(SIGSEGV, &sa, 0); sigaction(SIGBUS, &sa, 0); sigaction(SIGFPE, &sa, 0); sigaction(SIGILL, &sa, 0);
+    static char *apple[] = {(char *)"executable_path=pedigraph", 0};
+    typedef int (*macho_main)(int, char **, char **, char **);
+    macho_main entry = (macho_main)(uintptr_t)(text_vm + ep->entryoff);
+    int rc = entry(argc, argv, envp, apple);
+    fflush(0);
+    return rc;
+}

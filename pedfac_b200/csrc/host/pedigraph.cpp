@@ -581,6 +581,8 @@ static void sweep_and_flush(Ped &p, int kid, Batch &b)
 static int add_choice(Ped &p, Batch &b, int kind, int pa, int ma, int marr)
 {
     pf_proposal q{kind, pa, ma, marr};
+    static const bool dbg = getenv("PEDFAC_DEBUG_CHOICES") != nullptr;
+    if (dbg) fprintf(stderr, "choice kind %d pa %d ma %d marr %d\n", kind, pa, ma, marr);
     Choice c;
     if (kind == PF_PROP_PRONG) c = Choice{marr, p.marr[marr].pa, p.marr[marr].ma, p.marr[marr].selfing ? 1 : 0, 0};
     else if (kind == PF_PROP_SELFING) c = Choice{-1, pa, pa, 1, 0};
@@ -814,7 +816,14 @@ static int GetEmptyMarrIndx(Ped &p)
 static void AttachUnobsIndiv(Ped &p, int slot, int kid, int m, int edge)
 {
     Indiv &x = p.indiv[slot];
+    // the reference re-initialises only sex, gen, genTime, founder, observed, ids and the marriage
+    // list of a recycled slot (@0x100012c15-0x100012d67): the previous occupant's unobsDegree,
+    // `reductive` flag and sexWasUnknown stay (a fresh slot has 0 / false from _AllocIndiv), and the
+    // degree of the spouse created just before is what UpdateUnobsDegree then reads
+    const int staleDegree = x.unobsDegree, staleSexUnknown = x.sexWasUnknown;
+    const bool staleReductive = x.reductive, staleQueued = x.queued;
     x = Indiv();
+    x.unobsDegree = staleDegree; x.sexWasUnknown = staleSexUnknown; x.reductive = staleReductive; x.queued = staleQueued;
     x.sex = edge + 1;
     x.gen = p.indiv[kid].gen + 1;
     x.genTime = p.indiv[kid].genTime + p.minAge;
@@ -1073,6 +1082,24 @@ static void CheckInvariants(Ped &p, const char *where, int id)
 // _MCMC_sampling@0x100019ec0
 static void MCMC_sampling(Ped &p, const Opts &o, int id)
 {
+    static const bool dbg_calls = getenv("PEDFAC_DEBUG_CALLS") != nullptr;
+    if (dbg_calls) fprintf(stderr, "call %d gen %d deg %d\n", id, p.indiv[id].gen, p.indiv[id].unobsDegree);
+    if (getenv("PEDFAC_DEBUG_STATE")) {                       // same format as oracle/macho_run.c's PEDFAC_REF_DUMP
+        fprintf(stderr, "state before %d nCC %d\n", id, p.nCC);
+        for (int i = 0; i < p.nIndivUsed; i++) {
+            if (!p.indivActive[i]) continue;
+            const Indiv &x = p.indiv[i];
+            fprintf(stderr, "I %d gen %d sex %d deg %d founder %d red %d queued %d cc %d :", i, x.gen, x.sex, x.unobsDegree, x.founder ? 1 : 0, x.reductive ? 1 : 0, x.queued ? 1 : 0, p.cc[i]);
+            for (size_t k = 0; k < x.M.size(); k++) fprintf(stderr, " %d/%d", x.M[k], x.edge[k]);
+            fprintf(stderr, "\n");
+        }
+        for (int m = 0; m < p.nMarrUsed; m++) {
+            if (!p.marrActive[m]) continue;
+            fprintf(stderr, "M %d pa %d ma %d self %d kids", m, p.marr[m].pa, p.marr[m].selfing ? -1 : p.marr[m].ma, p.marr[m].selfing ? 1 : 0);
+            for (int k : p.marr[m].kids) fprintf(stderr, " %d", k);
+            fprintf(stderr, "\n");
+        }
+    }
     if (!(p.indiv[id].gen < p.nGen - 1)) return;
     if (!(p.indiv[id].unobsDegree <= p.maxUnobsLayer)) return;
     p.t++;
@@ -1437,18 +1464,35 @@ static void RefineParentOffPair(Ped &p)
             cands.push_back(j); bias.push_back(-p.LLcc[p.cc[j]]);
         }
         if (!cands.empty()) {
-            std::vector<uint8_t> role(kids.size());
-            for (size_t k = 0; k < kids.size(); k++) role[k] = p.indiv[kids[k]].sex == 1 ? 1 : 0;
+            // _CalculateLLByStubs@0x10001eef0 subtracts LLcc[cc(candidate)] only when the candidate is
+            // not in the kid's own component. From the all-singletons start that is every pair, and the
+            // whole generation goes down in one call with a per-candidate bias; a kid that shares its
+            // component with a candidate (possible only with a seeded marriage.txt) gets a call of
+            // its own with that candidate's bias cleared.
             const int K = 15;
-            std::vector<int> slot(kids.size() * K);
-            std::vector<double> score(kids.size() * K);
-            if (PFN(prefilter)(p.eng, 0, (int)kids.size(), kids.data(), role.data(), (int)cands.size(), cands.data(),
-                               bias.data(), K, slot.data(), score.data()) != PF_OK) die("prefilter failed");
-            for (size_t k = 0; k < kids.size(); k++) {
-                auto &pc = p.parentCand[kids[k]];
-                pc.clear();
-                for (int t = 0; t < K; t++) if (slot[k * K + t] >= 0) pc.push_back(slot[k * K + t]);
+            auto run = [&](const std::vector<int> &ks, const std::vector<double> &bs) {
+                std::vector<uint8_t> role(ks.size());
+                for (size_t k = 0; k < ks.size(); k++) role[k] = p.indiv[ks[k]].sex == 1 ? 1 : 0;
+                std::vector<int> slot(ks.size() * K);
+                std::vector<double> score(ks.size() * K);
+                if (PFN(prefilter)(p.eng, 0, (int)ks.size(), ks.data(), role.data(), (int)cands.size(), cands.data(),
+                                   bs.data(), K, slot.data(), score.data()) != PF_OK) die("prefilter failed");
+                for (size_t k = 0; k < ks.size(); k++) {
+                    auto &pc = p.parentCand[ks[k]];
+                    pc.clear();
+                    for (int t = 0; t < K; t++) if (slot[k * K + t] >= 0) pc.push_back(slot[k * K + t]);
+                }
+            };
+            std::vector<int> plain;
+            for (int kd : kids) {
+                bool shares = false;
+                for (int j : cands) shares = shares || p.cc[j] == p.cc[kd];
+                if (!shares) { plain.push_back(kd); continue; }
+                std::vector<double> own(bias);
+                for (size_t c = 0; c < cands.size(); c++) if (p.cc[cands[c]] == p.cc[kd]) own[c] = 0.0;
+                run({kd}, own);
             }
+            if (!plain.empty()) run(plain, bias);
         }
         i0 = i1;
     }
@@ -1559,6 +1603,7 @@ int main(int argc, char **argv)
             if (!last && !(p.indiv[id].gen < p.indiv[p.observedSorted[k + 1]].gen)) continue;
             const int gap = last ? p.nGen - p.indiv[id].gen : p.indiv[p.observedSorted[k + 1]].gen - p.indiv[id].gen;
             for (int g = 1; g <= gap; g++) {
+                if (getenv("PEDFAC_DEBUG_CALLS")) fprintf(stderr, "pass g %d of %d window %d..%d queue %zu\n", g, gap, qBeg, qEnd, p.unobsQueue.size());
                 for (int q = qBeg; q < qEnd + 1; q++) {
                     const int u = p.unobsQueue[q];
                     if (!p.indiv[u].queued) continue;

@@ -11,12 +11,15 @@ from .synth import SynthData
 
 
 def write_run_dir(data: SynthData, run_dir, *, max_unobs: int = 1, min_age: float = 1.0, max_age: float = 1.0,
-                  observe_frac: float = 0.8, max_gen: int = 0, seeds=(2590, 7579545), loci=None, seed_marriages: bool = False):
+                  observe_frac: float = 0.8, max_gen: int = 0, seeds=(2590, 7579545), loci=None, seed_marriages: bool = False,
+                  seed_one_kid: bool = False):
     """Writes run_dir/{geno.txt, prior.txt, rand}. Only observed individuals are listed (ids 1..n
     in slot order); `gen` is the generation index (0 = youngest), founders are the oldest observed
     generation when max_gen == 0 (R/renderGeno.R:84-86). With `seed_marriages` the optional
     marriage.txt (`kid pa ma` rows by user id; `nMar` = number of couples) seeds the chain with the
-    true trios whose three members are all observed."""
+    true trios whose three members are all observed; `seed_one_kid` keeps only the first kid of every
+    couple (the reference's marriage.txt reader never grows a marriage beyond its initial capacity
+    of one kid — `_doubleKidCap` is called from `_PickAndUpdate` only — so it faults on more)."""
     run = Path(run_dir)
     run.mkdir(parents=True, exist_ok=True)
     sl = slice(None) if loci is None else slice(0, loci)
@@ -44,6 +47,9 @@ def write_run_dir(data: SynthData, run_dir, *, max_unobs: int = 1, min_age: floa
         uid = {int(i): k + 1 for k, i in enumerate(order)}
         rows = [(uid[int(i)], uid[int(data.pa[i])], uid[int(data.ma[i])]) for i in order
                 if data.pa[i] >= 0 and int(data.pa[i]) in uid and int(data.ma[i]) in uid]
+        if seed_one_kid:
+            seen = set()
+            rows = [r for r in rows if (r[1], r[2]) not in seen and not seen.add((r[1], r[2]))]
         n_mar = len({(p_, m_) for _, p_, m_ in rows})
         (run / "marriage.txt").write_text("".join(f"{k} {p_} {m_}\n" for k, p_, m_ in rows))
     obs_frac = np.zeros(n_gen)
