@@ -171,6 +171,23 @@ static void on_trap(int sig, siginfo_t *si, void *uc_) {
     ucontext_t *uc = uc_;
     greg_t *g = uc->uc_mcontext.gregs;
     if ((unsigned long)g[REG_RIP] - 1 == 0x100019ec0ul && getenv("PEDFAC_REF_DUMP")) dump_ref_state(stderr, (char *)g[REG_RDI], (int)g[REG_RSI]);
+    /* PEDFAC_REF_DUMP_LL=1 with `_AddObsFracPrior@0x100019800` (ped, focal slot, choice) traced: the
+     * whole proposal list of the Gibbs step with its log-likelihoods at full precision, before the
+     * observation-fraction prior is added (choice layout: SURVEY.md App. B). */
+    if ((unsigned long)g[REG_RIP] - 1 == 0x100019800ul && getenv("PEDFAC_REF_DUMP_LL")) {
+        char *ch = (char *)g[REG_RDX];
+        int n = *RD(int *, ch, 0x8);
+        double *ll = RD(double *, ch, 0x10);
+        int **ent = RD(int **, ch, 0x0);
+        fprintf(stderr, "choices kid %d n %d\n", (int)g[REG_RSI], n);
+        for (int k = 0; k < n; ++k) {
+            int *ids = *(int **)ent[k];                        /* entry = { int *ids; int *aux; } */
+            fprintf(stderr, "c %d ids %d %d %d %d %.17g\n", k, ids[0], ids[1], ids[2], ids[3], ll[k]);
+        }
+        g[REG_RSP] -= 8;
+        *(uint64_t *)g[REG_RSP] = (uint64_t)g[REG_RBP];
+        return;
+    }
     fprintf(stderr, "ref-call 0x%lx rdi=%ld rsi=%ld rdx=%ld rcx=%ld r8=%ld\n", (unsigned long)g[REG_RIP] - 1,
             (long)g[REG_RDI], (long)g[REG_RSI], (long)g[REG_RDX], (long)g[REG_RCX], (long)g[REG_R8]);
     g[REG_RSP] -= 8;

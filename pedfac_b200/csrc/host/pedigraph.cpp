@@ -1110,6 +1110,11 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
     p.t++;
     if (p.check) p.chll_data = p.chll;
     if (getenv("PEDFAC_DUMP_PRE") && getenv("PEDFAC_DUMP_KID") && atoi(getenv("PEDFAC_DUMP_KID")) == id) DumpState(p, getenv("PEDFAC_DUMP_PRE"));   // last visit wins
+    if (getenv("PEDFAC_DEBUG_LL")) {                          // same format as oracle/macho_run.c's PEDFAC_REF_DUMP_LL
+        fprintf(stderr, "choices kid %d n %zu\n", id, p.ch.size());
+        for (size_t k = 0; k < p.ch.size(); k++)
+            fprintf(stderr, "c %zu ids %d %d %d %d %.17g\n", k, p.ch[k].mnode, p.ch[k].pa, p.ch[k].ma, p.ch[k].selfing, p.chll[k]);
+    }
     AddObsFracPrior(p, id);
     const int dbg_prev[3] = {p.prev[0], p.prev[1], p.prev[2]};
     PickAndUpdate(p, id);

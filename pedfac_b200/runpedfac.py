@@ -154,7 +154,9 @@ def write_intermed_geno(param) -> dict:
              "aFreq " + " ".join(_fmt(a, 3) for a in af),
              "epsilon " + " ".join(_fmt(e, 6) for e in eps),
              "obsFrac " + " ".join(_fmt(x, 3) for x in obs_frac),
-             f"maxAge {_fmt(param['max.age'], 6)}", f"minAge {_fmt(param['min.age'], 6)}",
+             # no maxAge / minAge lines: R/renderGeno.R:224-239 never writes them, so the sampler runs
+             # with its defaults 1.0 / 1.0 and min.age / max.age act only through `gen` above
+             # (= floor((max year - year) / min.age), already in generation units)
              f"maxUnobsLayer {param['max.unobs']}"]
     (out / "prior.txt").write_text("\n".join(prior))
     return {"n.indiv": n, "n.snp": n_snp, "n.gen": n_gen, "gen": gen, "afreq": af, "epsilon": eps}

@@ -1,0 +1,115 @@
+"""Parity against the REFERENCE ITSELF. tests/golden/ref_traces.json holds what ngthomas/pedFac's own
+`exec/pedigraph` (the Mach-O binary, run under oracle/macho_run.c) printed for a fixed list of small run
+directories: the `prior:` line, out/ped.txt, out/ll.txt and, for the first Gibbs steps, every proposal
+with its log-likelihood at full precision (tools/make_reference_goldens.py made it). Both builds of the
+product's sampler — host chain logic on the CPU oracle (here) and on libpedfac_cuda (-m gpu) — must
+reproduce the traces byte for byte and every proposal's log-likelihood within north_star's 1e-9
+relative. Where the loader binary itself is present (oracle/_ref/, built where /root/reference
+exists; it travels to the GPU box) fresh random cases are also compared live."""
+import json
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from pedfac_b200 import frontend, synth
+
+ROOT = Path(__file__).resolve().parent.parent
+CPU = ROOT / "oracle" / "pedigraph_ref"
+GPU = ROOT / "pedfac_b200" / "bin" / "pedigraph"
+MACHO = ROOT / "oracle" / "_ref" / "pedigraph_macho"
+GOLD = json.loads((ROOT / "tests" / "golden" / "ref_traces.json").read_text())["cases"]
+LL_RTOL = 1e-9          # north_star: per-proposal log-likelihoods within 1e-9 relative
+
+
+def run_ours(binary, run_dir, n_iter, flags, dump_ll=True):
+    env = dict(os.environ, **({"PEDFAC_DEBUG_LL": "1"} if dump_ll else {}))
+    r = subprocess.run([str(binary), "-d", str(run_dir), "-n", str(n_iter), "-r", str(run_dir / "rand"), *flags],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stderr[-500:]
+    steps = []
+    for line in r.stderr.splitlines():
+        t = line.split()
+        if line.startswith("choices kid"):
+            steps.append({"kid": int(t[2]), "ids": [], "ll": []})
+        elif line.startswith("c ") and steps:
+            steps[-1]["ids"].append([int(x) for x in t[3:7]]); steps[-1]["ll"].append(float(t[7]))
+    prior = [l for l in r.stdout.splitlines() if l.startswith("prior:")][0].strip()
+    return prior, (run_dir / "out" / "ped.txt").read_text(), (run_dir / "out" / "ll.txt").read_text(), steps
+
+
+def check_case(binary, name, tmp_path):
+    g = GOLD[name]
+    rd = tmp_path / name
+    rd.mkdir()
+    for fn, text in g["files"].items():
+        (rd / fn).write_text(text)
+    prior, ped, ll, steps = run_ours(binary, rd, g["n_iter"], g["flags"])
+    assert prior == g["prior"]                               # `prior: %f` of the initial sweep
+    assert ped == g["ped"]                                   # the sampled pedigree trace, byte for byte
+    assert ll == g["ll"]                                     # `%d %d %f` of every picked move
+    assert len(steps) == g["n_steps"]
+    worst = 0.0
+    for mine, ref in zip(steps, g["proposals"]):
+        assert mine["kid"] == ref["kid"] and mine["ids"] == ref["ids"]          # same proposals in the same order
+        a, b = np.array(mine["ll"]), np.array([float(x) for x in ref["ll"]])
+        fin = np.isfinite(b)
+        assert (np.isfinite(a) == fin).all()
+        if fin.any():
+            worst = max(worst, float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(1.0, np.abs(b[fin])))))
+    assert worst <= LL_RTOL, worst
+    return worst
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_cpu_sampler_reproduces_the_reference_binary(name, tmp_path):
+    check_case(CPU, name, tmp_path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_gpu_sampler_reproduces_the_reference_binary(name, tmp_path):
+    check_case(GPU, name, tmp_path)
+
+
+def test_goldens_cover_the_modes_the_verdict_asked_for():
+    flags = {n: tuple(c["flags"]) for n, c in GOLD.items()}
+    assert ("-w",) in flags.values() and ("-s", "-w") in flags.values() and () in flags.values()
+    assert any("marriage.txt" in c["files"] for c in GOLD.values())                      # seeded start
+    assert any("," in c["files"]["geno.txt"].split("\n")[0] for c in GOLD.values())       # soft calls
+    assert any(len(c["ped"].splitlines()) > c["n_steps"] for c in GOLD.values())          # a picked swap prints several rows
+    assert "example_case_0_n5" in GOLD                                                     # BASELINE.json configs[0]
+    # every row the reference printed has four fields: the 3-field swap row of
+    # _PickAndUpdate@0x100019745 (kind-4 swaps) never appeared
+    assert all(len(r.split()) == 4 for c in GOLD.values() for r in c["ped"].splitlines())
+
+
+def live_case(binary, tmp_path, seed, n, S, soft, flags, n_iter, **wr):
+    d = synth.simulate(n, S, soft=soft, seed=seed)
+    outs = []
+    for tag, b in (("ref", MACHO), ("ours", binary)):
+        rd = tmp_path / f"{tag}{seed}"
+        frontend.write_run_dir(d, rd, seeds=(1000 + seed, 77 + seed), **wr)
+        r = subprocess.run([str(b), "-d", str(rd), "-n", str(n_iter), "-r", str(rd / "rand"), *flags], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, (tag, r.stderr[-400:])
+        outs.append(((rd / "out" / "ped.txt").read_text(), (rd / "out" / "ll.txt").read_text(),
+                     [l for l in r.stdout.splitlines() if l.startswith("prior:")][0].strip()))
+    assert outs[0] == outs[1]
+
+
+needs_loader = pytest.mark.skipif(not MACHO.exists(), reason="oracle/_ref/pedigraph_macho is built only where /root/reference exists")
+
+
+@needs_loader
+@pytest.mark.parametrize("seed,n,S,soft,flags", [(1, 70, 40, False, ()), (2, 60, 30, True, ()), (3, 90, 50, False, ("-w",)), (4, 50, 25, True, ())])
+def test_cpu_sampler_matches_the_reference_binary_live(tmp_path, seed, n, S, soft, flags):
+    live_case(CPU, tmp_path, seed, n, S, soft, flags, 3)
+
+
+@pytest.mark.gpu
+@needs_loader
+@pytest.mark.parametrize("seed,n,S,soft,flags", [(5, 220, 130, False, ()), (6, 160, 96, True, ()), (7, 120, 70, True, ("-w",))])
+def test_gpu_sampler_matches_the_reference_binary_live(tmp_path, seed, n, S, soft, flags):
+    live_case(GPU, tmp_path, seed, n, S, soft, flags, 2)
