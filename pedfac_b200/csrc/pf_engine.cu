@@ -5,6 +5,7 @@
 #include "../../include/pedfac_cuda.h"
 #include "pf_kernels.cuh"
 #include "pf_prefilter.cuh"
+#include "pf_sweep2.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -97,6 +98,8 @@ struct pf_engine {
     int force_shape = 0;              // PF_SWEEP_SHAPE=latency|throughput overrides the per-launch choice (measurement aid)
     bool sweep_clocks = false;        // PF_SWEEP_CLOCKS=1: per-level clocks of the largest group after every sweep
     bool host_prof = false; double t_plan = 0, t_submit = 0, t_wait = 0, t_evalprep = 0; long n_prof = 0, n_prof_calls = 0; double t_ph[6] = {0, 0, 0, 0, 0, 0};
+    bool sweep_v2 = true;             // PF_SWEEP_V2=0: first-generation sweep kernel only (measurement aid)
+    long sweeps_v2 = 0, sweeps_v1_fallback = 0;
     bool no_mailbox = false;          // PEDFAC_NO_MAILBOX=1 or no mapped memory: results by copy + stream synchronise
     int sm_count = 0;
     int eval_capacity = 0;            // resident eval_kernel blocks on this device
@@ -160,6 +163,7 @@ extern "C" int pf_destroy(pf_engine *e)
         fprintf(stderr, "pf-host-prof sweeps %ld plan_us %.1f submit_us %.1f evalprep_us %.1f wait_us %.1f (per sweep)\n", e->n_prof,
                 1e6 * e->t_plan / e->n_prof, 1e6 * e->t_submit / e->n_prof, 1e6 * e->t_evalprep / e->n_prof, 1e6 * e->t_wait / e->n_prof);
     if (!e) return PF_OK;
+    if (getenv("PF_SWEEP_STATS")) fprintf(stderr, "pf-sweep-stats v2 %ld v1-fallback %ld\n", e->sweeps_v2, e->sweeps_v1_fallback);
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_rows); cudaFree(e->d_eps); cudaFree(e->d_hard);
@@ -231,6 +235,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->no_mailbox = getenv("PEDFAC_NO_MAILBOX") != nullptr;
     e->host_prof = getenv("PF_HOST_PROF") != nullptr;
     e->sweep_clocks = getenv("PF_SWEEP_CLOCKS") != nullptr;
+    if (const char *v2 = getenv("PF_SWEEP_V2")) e->sweep_v2 = v2[0] != '0';
     if (const char *fs = getenv("PF_SWEEP_SHAPE")) e->force_shape = fs[0] == 't' ? 2 : fs[0] == 'l' ? 1 : 0;
     *out = e;
     return PF_OK;
@@ -447,6 +452,33 @@ struct ViewWork {           // scratch vectors reused across calls
     std::vector<int> it_off, it_cnt, it_type, it_first, it_n, it_kids, it_prow;   // sibship items per marriage (see item_factor)
 };
 
+// ---- second-generation plan (pf_sweep2.cuh): compiled task records ----
+struct Plan2Task { int group, level; uint32_t off; int cost; };
+struct Plan2 {
+    std::vector<Plan2Task> tasks;
+    std::vector<uint32_t> pool;
+    std::vector<Emis2> emis;
+    std::vector<Stage2> stage;
+    std::vector<Sweep2Group> groups;
+    int target_tasks_per_group = 1 << 30;
+    int format = 0;             // Fmt2 of the launch (0 generic, 1 hard calls, 2 dec16 over one denominator)
+    bool fits = true;           // false: some count exceeded a 16-bit field -> first-generation kernel
+    void reset() { tasks.clear(); pool.clear(); emis.clear(); stage.clear(); groups.clear(); target_tasks_per_group = 1 << 30; fits = true; format = 0; }
+    void begin_component()
+    {
+        if (groups.empty() || groups.back().task_end >= target_tasks_per_group) {
+            Sweep2Group g{};
+            g.pool_begin = (int)pool.size();
+            g.emis_begin = (int)emis.size();
+            g.n_rows = 2;                       // row 0: ones, row 1: trash
+            g.emis_bytes = format == 1 ? 16 : format == 2 ? 3 * TILE_LOCI * 2 : 0;   // tile 0: the constant "no data" tile
+            pool.push_back(0);                  // word 0 of a group's pool is never a list (offset 0 = "no extra rows")
+            groups.push_back(g);
+        }
+    }
+    Sweep2Group &cur() { return groups.back(); }
+};
+
 } // namespace
 
 static thread_local ViewWork g_work;
@@ -456,7 +488,9 @@ static thread_local ViewWork g_work;
 // The band offset is fixed up by the caller once every view has been added. While a group is
 // being filled, SweepGroup::task_end counts its tasks and n_rows / emis_count its transient rows
 // and genotype entries.
-static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only, const SweepShape &shape, int *loc = nullptr)
+static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan2 &plan, ViewWork &w, int &max_up_levels, bool up_only);
+
+static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only, const SweepShape &shape, int *loc = nullptr, Plan2 *plan2 = nullptr)
 {
     if (!loc) loc = e->loc.data();
     if (!v) return fail(PF_EINVAL, "null view");
@@ -580,6 +614,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         for (int m = 0; m < nM; m++)
             if (!w.vis_m[m]) { rc = fail(PF_EINVAL, "marriage %d not reachable", v->marr[m]); goto cleanup; }
         hp_mark(1);
+        if (plan2) { rc = emit2(e, v, chain, out_base, *plan2, w, max_up_levels, up_only); goto cleanup; }
         // heights of the FAMILY_UP tasks, children first (reverse BFS order)
         int up_levels = 0;
         for (int b = (int)w.bfs_m.size() - 1; b >= 0; b--) {
@@ -866,12 +901,536 @@ cleanup:
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Second-generation plan builder (record formats: pf_sweep2.cuh). Runs after plan_add_view's
+// validation and traversal, on the same ViewWork: adjacency (adj_*), members (mem_*), the rooted
+// tree (Ui, um, urole), the marriages in BFS order (bfs_m), roots / order_i / comp_members_end.
+
+namespace {
+struct Work2 {
+    std::vector<int> kid_off, kid_x, n_inline, chunk_off, n_chunks, chunk_first, chunk_n, chunk_row, chunk_level;
+    std::vector<int> lvl2, up_m_row, dn_row, park_row, emis_idx, depth2, cnt_d, cnt_t, rows;
+    std::vector<char> in_chunk;
+    std::vector<uint32_t> rec;
+};
+}
+static thread_local Work2 g_work2;
+
+static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan2 &plan, ViewWork &w, int &max_up_levels, bool up_only)
+{
+    Work2 &x2 = g_work2;
+    const int nI = v->n_indiv, nM = v->n_marr;
+    x2.kid_off.assign(nM + 1, 0); x2.kid_x.clear(); x2.n_inline.assign(nM, 0); x2.chunk_off.assign(nM, 0); x2.n_chunks.assign(nM, 0);
+    x2.chunk_first.clear(); x2.chunk_n.clear(); x2.chunk_row.clear(); x2.chunk_level.clear();
+    x2.lvl2.assign(nM, 0); x2.up_m_row.assign(nM, 0); x2.dn_row.assign(nI, -1); x2.park_row.assign(nM, -1); x2.emis_idx.assign(nI, -1);
+    x2.depth2.assign(nM, 0); x2.in_chunk.assign(nI, 0);
+    std::vector<uint32_t> &pool = plan.pool, &rec = x2.rec;
+    auto n_marr_of = [&](int i) { return w.adj_off[i + 1] - w.adj_off[i]; };
+    // kids of every marriage below it (the up individual excluded), kids with marriages of their own first
+    for (int m = 0; m < nM; m++) {
+        x2.kid_off[m] = (int)x2.kid_x.size();
+        for (int pass = 0; pass < 2; pass++)
+            for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                const int i = w.mem_i[k];
+                if (w.mem_role[k] != 2 || i == w.um[m]) continue;
+                if ((n_marr_of(i) > 1) == (pass == 0)) x2.kid_x.push_back(i);
+            }
+    }
+    x2.kid_off[nM] = (int)x2.kid_x.size();
+
+    size_t bfs_pos = 0;
+    for (size_t ri = 0; ri < w.roots.size(); ri++) {
+        const int r = w.roots[ri];
+        plan.begin_component();
+        const int gid = (int)plan.groups.size() - 1;
+        Sweep2Group &G = plan.cur();
+        const int ib = ri == 0 ? 0 : w.comp_members_end[ri - 1], ie = w.comp_members_end[ri];
+        size_t mb = bfs_pos, me = bfs_pos;
+        while (me < w.bfs_m.size() && v->indiv_cc[w.um[w.bfs_m[me]]] == v->indiv_cc[r]) me++;
+        bfs_pos = me;
+
+        // genotype entries of the component's individuals
+        for (int oi = ib; oi < ie; oi++) {
+            const int i = w.order_i[oi], slot = v->indiv[i];
+            const uint32_t kind = e->h_kind[slot];
+            if (kind == EMIS_NONE) continue;
+            const int align = kind == EMIS_HARD ? 8 : 16;
+            G.emis_bytes = (G.emis_bytes + align - 1) & ~(align - 1);
+            x2.emis_idx[i] = plan.format == 0 ? G.emis_count : G.emis_bytes;      // table index, or the tile's offset itself
+            G.emis_count++;
+            if (plan.format == 0) G.emis_tab++;
+            plan.emis.push_back(Emis2{(uint32_t)G.emis_bytes, e->h_denom[slot], e->h_rcp[slot]});
+            plan.stage.push_back(Stage2{(unsigned long long)(uintptr_t)e->h_eptr[slot], kind, (uint32_t)G.emis_bytes});
+            G.emis_bytes += emis_tile_bytes(kind);
+        }
+        // rows: one per marriage, one pair per chunk of a large sibship
+        for (size_t b = mb; b < me; b++) {
+            const int m = w.bfs_m[b];
+            x2.up_m_row[m] = G.n_rows++;
+            const int nk = x2.kid_off[m + 1] - x2.kid_off[m];
+            x2.n_inline[m] = std::min(nk, FAM2_INLINE_KIDS);
+            x2.chunk_off[m] = (int)x2.chunk_first.size();
+            for (int k0 = x2.n_inline[m]; k0 < nk; k0 += CHUNK2_KIDS) {
+                const int n = std::min(CHUNK2_KIDS, nk - k0);
+                x2.chunk_first.push_back(x2.kid_off[m] + k0); x2.chunk_n.push_back(n);
+                x2.chunk_row.push_back(G.n_rows); G.n_rows += 2;
+                x2.chunk_level.push_back(0);
+                for (int j = 0; j < n; j++) x2.in_chunk[x2.kid_x[x2.kid_off[m] + k0 + j]] = 1;
+            }
+            x2.n_chunks[m] = (int)x2.chunk_first.size() - x2.chunk_off[m];
+        }
+        // up-band levels by dependency, children first
+        int up_levels = 0;
+        auto below_level = [&](int i, int m) {
+            int l = 0;
+            for (int a = w.adj_off[i]; a < w.adj_off[i + 1]; a++)
+                if (w.adj_m[a] != m) l = std::max(l, x2.lvl2[w.adj_m[a]] + 1);
+            return l;
+        };
+        for (size_t b = me; b-- > mb;) {
+            const int m = w.bfs_m[b];
+            int lv = 0;
+            for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                const int i = w.mem_i[k];
+                if (i == w.um[m] || x2.in_chunk[i]) continue;
+                lv = std::max(lv, below_level(i, m));
+            }
+            for (int c = x2.chunk_off[m]; c < x2.chunk_off[m] + x2.n_chunks[m]; c++) {
+                int cl = 0;
+                for (int j = 0; j < x2.chunk_n[c]; j++) cl = std::max(cl, below_level(x2.kid_x[x2.chunk_first[c] + j], m));
+                x2.chunk_level[c] = cl;
+                lv = std::max(lv, cl + 1);
+            }
+            x2.lvl2[m] = lv;
+            up_levels = std::max(up_levels, lv + 1);
+        }
+        max_up_levels = std::max(max_up_levels, up_levels);
+        // down band: FAMDOWN2(m) and the KIDCHUNK2 tasks of m run one level after the task that writes
+        // the message into m's up individual; message rows are written at level l and read at l + 1:
+        // two banks by the parity of l
+        if (!up_only) {
+            int max_l = 0;
+            for (size_t b = mb; b < me; b++) {
+                const int m = w.bfs_m[b], u = w.um[m];
+                const int l = w.Ui[u] >= 0 ? x2.depth2[w.Ui[u]] + 1 : 0;
+                x2.depth2[m] = l;
+                max_l = std::max(max_l, l + 1);
+            }
+            x2.cnt_d.assign(max_l + 2, 0);
+            int bank_d = 0;
+            for (size_t b = mb; b < me; b++) {
+                const int m = w.bfs_m[b], l = x2.depth2[m];
+                for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                    const int i = w.mem_i[k];
+                    if (i == w.um[m] || n_marr_of(i) <= 1) continue;
+                    x2.dn_row[i] = (x2.cnt_d[l]++) * 2 + (l & 1);
+                    bank_d = std::max(bank_d, 2 * x2.cnt_d[l]);
+                }
+            }
+            const int base_d = G.n_rows;
+            G.n_rows += bank_d;
+            for (int oi = ib; oi < ie; oi++) {
+                const int i = w.order_i[oi];
+                if (x2.dn_row[i] >= 0) x2.dn_row[i] += base_d;
+            }
+        }
+
+        // ---- records ----
+        bool rec_extras = false;                               // some operand of the record being built has more than three rows
+        auto push_cmp = [&](int i, int m_ex, int first_row) {
+            std::vector<int> &rows = x2.rows;
+            rows.clear();
+            if (first_row >= 0) rows.push_back(first_row);
+            for (int a = w.adj_off[i]; a < w.adj_off[i + 1]; a++) {
+                const int m2 = w.adj_m[a];
+                if (m2 == m_ex || m2 == w.Ui[i]) continue;
+                rows.push_back(x2.up_m_row[m2]);
+            }
+            const uint32_t kind = e->h_kind[v->indiv[i]];
+            uint32_t w0 = v->indiv_founder[i] ? CMP_FOUNDER : 0u;
+            if (plan.format == 0) w0 |= kind | (kind != EMIS_NONE ? (uint32_t)x2.emis_idx[i] << 3 : 0u);
+            else if (kind != EMIS_NONE) w0 |= (uint32_t)x2.emis_idx[i];
+            uint32_t extra = 0;
+            if (rows.size() > 3) {
+                extra = (uint32_t)(pool.size() - (size_t)G.pool_begin);
+                if (extra > 0xffffu) plan.fits = false;
+                pool.push_back((uint32_t)rows.size() - 3);
+                for (size_t j = 3; j < rows.size(); j++) pool.push_back((uint32_t)rows[j]);
+                rec_extras = true;
+            }
+            auto row_or_ones = [&](size_t j) { return j < rows.size() ? (uint32_t)rows[j] : ROW2_ONES; };
+            rec.push_back(w0);
+            rec.push_back(row_or_ones(0) | row_or_ones(1) << 16);
+            rec.push_back(row_or_ones(2) | (extra & 0xffffu) << 16);
+        };
+        auto push_absent = [&]() { rec.push_back(0); rec.push_back(0); rec.push_back(0); };      // no data, rows 0: ones
+        auto push_pairs = [&](int m) {
+            const int np = x2.n_chunks[m];
+            for (int j = 0; j < np; j += 2) {
+                uint32_t wd = (uint32_t)x2.chunk_row[x2.chunk_off[m] + j];
+                if (j + 1 < np) wd |= (uint32_t)x2.chunk_row[x2.chunk_off[m] + j + 1] << 16;
+                rec.push_back(wd);
+            }
+        };
+        auto add_task = [&](int level) {
+            const uint32_t kind = rec[0] & 0xffu;
+            if (rec_extras || (kind != T2_ROOT && (rec[0] & (1u << 8)))) rec[0] |= T2_GENERAL;     // selfing, or an operand with extra rows
+            rec_extras = false;
+            plan.tasks.push_back(Plan2Task{gid, level, (uint32_t)(pool.size() - (size_t)G.pool_begin), (int)rec.size()});
+            pool.insert(pool.end(), rec.begin(), rec.end());
+            G.task_end++;
+        };
+        auto row16 = [&](int row) { return row < 0 ? ROW2_TRASH : (uint32_t)row; };
+        // kid entry of the down band: cmp, stub row, dn row
+        auto push_kid_down = [&](int i, int m) {
+            push_cmp(i, m, -1);
+            rec.push_back((uint32_t)e->stub_row(chain, v->indiv[i]));
+            rec.push_back(row16(x2.dn_row[i]));
+        };
+
+        // levels: >= 0 = up band; -1 = first level of the down band; -(2 + k) = down-band level k
+        rec.clear();
+        rec.push_back(T2_ROOT | (up_only ? 0u : 1u) << 8);
+        rec.push_back(up_only ? 0u : (uint32_t)e->stub_row(chain, v->indiv[r]));
+        rec.push_back((uint32_t)(out_base + v->indiv_cc[r]));
+        rec.push_back(up_only ? (uint32_t)G.n_rows++ : 0u);
+        push_cmp(r, -1, -1);
+        add_task(-1);
+
+        for (size_t b = mb; b < me; b++) {
+            const int m = w.bfs_m[b], u = w.um[m];
+            const uint32_t flags = (v->marr_selfing[m] ? 1u : 0u) | (uint32_t)w.urole[m] << 1;
+            int pa = -1, ma = -1;
+            for (int k = w.mem_off[m]; k < w.mem_off[m + 1]; k++) {
+                if (w.mem_i[k] == u && w.mem_role[k] == w.urole[m]) continue;
+                if (w.mem_role[k] == 0) pa = w.mem_i[k]; else if (w.mem_role[k] == 1) ma = w.mem_i[k];
+            }
+            const int k0 = x2.kid_off[m], nki = x2.n_inline[m], np = x2.n_chunks[m];
+            // chunk products (up band)
+            for (int c = x2.chunk_off[m]; c < x2.chunk_off[m] + np; c++) {
+                rec.clear();
+                rec.push_back(T2_KFOLD | (uint32_t)x2.chunk_n[c] << 16);
+                rec.push_back((uint32_t)x2.chunk_row[c]);
+                for (int j = 0; j < x2.chunk_n[c]; j++) push_cmp(x2.kid_x[x2.chunk_first[c] + j], m, -1);
+                add_task(x2.chunk_level[c]);
+            }
+            rec.clear();
+            rec.push_back(T2_FAMUP | flags << 8 | (uint32_t)nki << 16 | (uint32_t)np << 24);
+            rec.push_back((uint32_t)x2.up_m_row[m]);
+            if (pa >= 0) push_cmp(pa, m, -1); else push_absent();
+            if (ma >= 0) push_cmp(ma, m, -1); else push_absent();
+            for (int j = 0; j < nki; j++) push_cmp(x2.kid_x[k0 + j], m, -1);
+            push_pairs(m);
+            add_task(x2.lvl2[m]);
+            if (up_only) continue;
+
+            const int l = x2.depth2[m];
+            const int u_dn = w.Ui[u] >= 0 ? x2.dn_row[u] : -1;
+            rec.clear();
+            rec.push_back(T2_FAMDOWN | flags << 8 | (pa >= 0 ? T2_HAS_A : 0u) | (ma >= 0 ? T2_HAS_B : 0u) | (uint32_t)nki << 16 | (uint32_t)np << 24);
+            rec.push_back((uint32_t)e->prong_row(chain, v->marr[m]));
+            push_cmp(u, m, u_dn);
+            if (pa >= 0) { push_cmp(pa, m, -1); rec.push_back((uint32_t)e->stub_row(chain, v->indiv[pa])); } else { push_absent(); rec.push_back(0); }
+            if (ma >= 0) { push_cmp(ma, m, -1); rec.push_back((uint32_t)e->stub_row(chain, v->indiv[ma])); } else { push_absent(); rec.push_back(0); }
+            rec.push_back(row16(pa >= 0 ? x2.dn_row[pa] : -1) | row16(ma >= 0 ? x2.dn_row[ma] : -1) << 16);
+            for (int j = 0; j < nki; j++) push_kid_down(x2.kid_x[k0 + j], m);
+            push_pairs(m);
+            add_task(-(2 + l));
+            for (int ci = 0; ci < np; ci++) {
+                const int c = x2.chunk_off[m] + ci;
+                rec.clear();
+                rec.push_back(T2_KIDCHUNK | flags << 8 | (pa >= 0 ? T2_HAS_A : 0u) | (ma >= 0 ? T2_HAS_B : 0u) | (uint32_t)x2.chunk_n[c] << 16 | (uint32_t)np << 24);
+                rec.push_back((uint32_t)nki | (uint32_t)ci << 8);
+                push_cmp(u, m, u_dn);
+                if (pa >= 0) push_cmp(pa, m, -1); else push_absent();
+                if (ma >= 0) push_cmp(ma, m, -1); else push_absent();
+                for (int j = 0; j < x2.chunk_n[c]; j++) push_kid_down(x2.kid_x[x2.chunk_first[c] + j], m);
+                for (int j = 0; j < nki; j++) push_cmp(x2.kid_x[k0 + j], m, -1);
+                push_pairs(m);
+                add_task(-(2 + l));
+            }
+        }
+        G.pool_len = (int)pool.size() - G.pool_begin;
+        if (G.n_rows >= 0xffff) plan.fits = false;
+        for (size_t b = mb; b < me; b++) if (x2.n_chunks[w.bfs_m[b]] > 255) plan.fits = false;
+    }
+    return PF_OK;
+}
+
+// Plans the views with the second-generation builder and launches sweep2_kernel. Returns
+// PF2_FALLBACK (nothing launched) when some group does not fit the kernel's shared-memory or field
+// limits: the caller then runs the first-generation kernel, which can spill rows.
+constexpr int PF2_FALLBACK = 1000;
+
+static int run_sweeps2(pf_engine *e, int n, const int32_t *chains, const pf_graph_view *views, double *out_dev, int *n_out_total, bool up_only)
+{
+    const int n_tiles = (e->Sl + TILE_LOCI - 1) / TILE_LOCI;
+    const double t_begin = e->host_prof ? host_now() : 0.0;
+    static thread_local Plan2 plan_storage;
+    static thread_local Plan dummy;
+    Plan2 &plan = plan_storage;
+    plan.reset();
+    long long est_tasks = 0, est_comp = 0;
+    for (int i = 0; i < n; i++) { est_tasks += (long long)std::max(views[i].n_cc, 0) + 2LL * std::max(views[i].n_marr, 0); est_comp += std::max(views[i].n_cc, 0); }
+    {
+        // enough groups that (tiles x groups) fills the GPU, but no more than 256 tasks per group
+        const long long want_groups = std::max<long long>((592 + n_tiles - 1) / n_tiles, (est_tasks + 255) / 256);
+        const long long Gn = std::max<long long>(1, std::min<long long>(std::min<long long>(want_groups, est_comp), 65535));
+        plan.target_tasks_per_group = (int)std::max<long long>(1, (est_tasks + Gn - 1) / Gn);
+    }
+    int sm_count = e->sm_count;
+    if (sm_count <= 0) { cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, e->cfg.device); e->sm_count = sm_count = sm_count > 0 ? sm_count : 148; }
+    // genotype format of the launch (pf_sweep2.cu: Fmt2): all hard calls, or all 16-bit numerators over
+    // one denominator (individuals without data fit both), else generic
+    uint32_t dec16_denom = 0;
+    {
+        bool hard = false, dec16 = false, other = false, denoms_differ = false;
+        for (int i = 0; i < n; i++) {
+            const pf_graph_view &v = views[i];
+            if (v.n_indiv <= 0 || !v.indiv) continue;
+            for (int k = 0; k < v.n_indiv; k++) {
+                const int slot = v.indiv[k];
+                if (slot < 0 || slot >= e->cfg.cap_indiv) continue;          // reported by plan_add_view
+                const uint8_t kd = e->h_kind[slot];
+                if (kd == EMIS_HARD) hard = true;
+                else if (kd == EMIS_DEC16) {
+                    if (dec16 && e->h_denom[slot] != dec16_denom) denoms_differ = true;
+                    dec16 = true; dec16_denom = e->h_denom[slot];
+                } else if (kd != EMIS_NONE) other = true;
+            }
+        }
+        if (!other && hard && !dec16) plan.format = 1;
+        else if (!other && dec16 && !hard && !denoms_differ && dec16_denom <= 0xffffu) plan.format = 2;
+        else if (!other && !hard && !dec16) plan.format = 1;               // nobody carries data
+    }
+    int max_up = 0, out_base = 0;
+    if (n >= 16) {
+        const int T = (int)std::min<unsigned>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), (unsigned)n / 4u);
+        std::vector<int> bases(n + 1, 0);
+        for (int i = 0; i < n; i++) bases[i + 1] = bases[i] + std::max(views[i].n_cc, 0);
+        struct Part { Plan2 plan; int max_up = 0, rc = PF_OK; std::string err; };
+        std::vector<Part> parts(T);
+        std::vector<std::thread> th;
+        const int target = plan.target_tasks_per_group;
+        for (int t = 0; t < T; t++)
+            th.emplace_back([&, t]() {
+                static thread_local std::vector<int> tl_loc;
+                static thread_local Plan tl_dummy;
+                if ((int)tl_loc.size() < e->cfg.cap_indiv) tl_loc.assign(e->cfg.cap_indiv, -1);
+                Part &P = parts[t];
+                P.plan.target_tasks_per_group = target;
+                P.plan.format = plan.format;
+                const int i0 = (int)((long long)n * t / T), i1 = (int)((long long)n * (t + 1) / T);
+                for (int i = i0; i < i1 && P.rc == PF_OK; i++) {
+                    P.rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, bases[i], tl_dummy, P.max_up, up_only, SWEEP_LATENCY, tl_loc.data(), &P.plan);
+                    if (P.rc) P.err = g_err;
+                }
+            });
+        for (auto &x : th) x.join();
+        for (int t = 0; t < T; t++) {
+            Part &P = parts[t];
+            if (P.rc) return fail(P.rc, "%s", P.err.c_str());
+            const int gb = (int)plan.groups.size(), pb = (int)plan.pool.size(), eb = (int)plan.emis.size();
+            for (auto &tk : P.plan.tasks) plan.tasks.push_back(Plan2Task{tk.group + gb, tk.level, tk.off, tk.cost});
+            for (auto &sg : P.plan.groups) { Sweep2Group g2 = sg; g2.pool_begin += pb; g2.emis_begin += eb; plan.groups.push_back(g2); }
+            plan.pool.insert(plan.pool.end(), P.plan.pool.begin(), P.plan.pool.end());
+            plan.emis.insert(plan.emis.end(), P.plan.emis.begin(), P.plan.emis.end());
+            plan.stage.insert(plan.stage.end(), P.plan.stage.begin(), P.plan.stage.end());
+            plan.fits = plan.fits && P.plan.fits;
+            max_up = std::max(max_up, P.max_up);
+        }
+        out_base = bases[n];
+    } else {
+        for (int i = 0; i < n; i++) {
+            int rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, dummy, max_up, up_only, SWEEP_LATENCY, nullptr, &plan);
+            if (rc) return rc;
+            out_base += views[i].n_cc;
+        }
+    }
+    *n_out_total = out_base;
+    if (plan.tasks.empty()) {
+        if (out_base > 0) CU(cudaMemsetAsync(out_dev, 0, (size_t)out_base * sizeof(double), e->stream));
+        return PF_OK;
+    }
+    if (!plan.fits) return PF2_FALLBACK;
+
+    int n_levels = 1;
+    for (auto &t : plan.tasks) {
+        if (t.level == -1) t.level = max_up;
+        else if (t.level <= -2) t.level = max_up + (-t.level - 2);
+        n_levels = std::max(n_levels, t.level + 1);
+    }
+    int G = (int)plan.groups.size();
+    if (G > 65535) return PF2_FALLBACK;
+    int smem_bytes = 0;
+    for (int g = 0; g < G; g++) {
+        Sweep2Group sg = plan.groups[g];
+        sg.task_begin = 0;                      // task_end still counts the group's tasks
+        smem_bytes = std::max(smem_bytes, sweep2_smem_layout(sg, n_levels).total);
+    }
+    if (smem_bytes > SWEEP2_SMEM_MAX) return PF2_FALLBACK;
+    // heaviest groups first (see run_sweeps)
+    if (G > 1 && (long long)G * n_tiles > sm_count) {
+        std::vector<int> &perm = g_work.cost_of, &inv = g_work.start;
+        perm.resize(G); inv.resize(G);
+        for (int g = 0; g < G; g++) perm[g] = g;
+        std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return plan.groups[a].task_end > plan.groups[b].task_end; });
+        bool moved = false;
+        for (int k = 0; k < G; k++) { inv[perm[k]] = k; moved = moved || perm[k] != k; }
+        if (moved) {
+            std::vector<Sweep2Group> sorted(G);
+            for (int k = 0; k < G; k++) sorted[k] = plan.groups[perm[k]];
+            plan.groups.swap(sorted);
+            for (auto &t : plan.tasks) t.group = inv[t.group];
+        }
+    }
+    // counting sort by (group, level)
+    std::vector<int> &level_off = g_work.level_off, &start = g_work.start;
+    level_off.assign((size_t)G * (n_levels + 1) + 1, 0);
+    for (auto &t : plan.tasks) level_off[(size_t)t.group * (n_levels + 1) + t.level + 1]++;
+    start.assign((size_t)G * n_levels, 0);
+    {
+        int base = 0;
+        for (int g = 0; g < G; g++) {
+            int *lo = &level_off[(size_t)g * (n_levels + 1)];
+            int run = base;
+            for (int l = 0; l < n_levels; l++) { const int c = lo[l + 1]; start[(size_t)g * n_levels + l] = run; lo[l] = run; run += c; }
+            lo[n_levels] = run;
+            plan.groups[g].task_begin = base;
+            plan.groups[g].task_end = run;
+            base = run;
+        }
+    }
+    const double t_planned = e->host_prof ? host_now() : 0.0;
+    const size_t bytes_tasks = plan.tasks.size() * sizeof(Sweep2Task);
+    const size_t bytes_pool = plan.pool.size() * sizeof(uint32_t);
+    const size_t bytes_loff = (size_t)G * (n_levels + 1) * sizeof(int);
+    const size_t bytes_emis = plan.emis.size() * sizeof(Emis2);
+    const size_t bytes_stage = plan.stage.size() * sizeof(Stage2);
+    const size_t bytes_groups = (size_t)G * sizeof(Sweep2Group);
+    const size_t off_pool = (bytes_tasks + 15) & ~(size_t)15;
+    const size_t off_loff = (off_pool + bytes_pool + 15) & ~(size_t)15;
+    const size_t off_emis = (off_loff + bytes_loff + 15) & ~(size_t)15;
+    const size_t off_stage = (off_emis + bytes_emis + 15) & ~(size_t)15;
+    const size_t off_groups = (off_stage + bytes_stage + 15) & ~(size_t)15;
+    const size_t blob = off_groups + bytes_groups;
+
+    void *hp = nullptr; int slot = 0;
+    CU(e->staging.get(blob, &hp, &slot));
+    Sweep2Task *ht = static_cast<Sweep2Task *>(hp);
+    {
+        std::vector<int> &cost = g_work.cost_of;
+        cost.resize(plan.tasks.size());
+        for (auto &t : plan.tasks) {
+            const int pos = start[(size_t)t.group * n_levels + t.level]++;
+            ht[pos].off = t.off; cost[pos] = t.cost;
+        }
+        // a level with more tasks than warps runs in rounds: longest first
+        std::vector<std::pair<int, SweepTask>> &tmp = g_work.sort_tmp;
+        for (int g = 0; g < G; g++)
+            for (int l = 0; l < n_levels; l++) {
+                const int b0 = level_off[(size_t)g * (n_levels + 1) + l], b1 = level_off[(size_t)g * (n_levels + 1) + l + 1];
+                if (b1 - b0 <= SWEEP2_WARPS_SMALL) continue;
+                tmp.clear();
+                for (int k = b0; k < b1; k++) tmp.push_back({cost[k], SweepTask{0, (int)ht[k].off}});
+                std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<int, SweepTask> &x, const std::pair<int, SweepTask> &y) { return x.first > y.first; });
+                for (int k = b0; k < b1; k++) ht[k].off = (uint32_t)tmp[k - b0].second.off;
+            }
+    }
+    memcpy(static_cast<char *>(hp) + off_pool, plan.pool.data(), bytes_pool);
+    memcpy(static_cast<char *>(hp) + off_loff, level_off.data(), bytes_loff);
+    memcpy(static_cast<char *>(hp) + off_emis, plan.emis.data(), bytes_emis);
+    memcpy(static_cast<char *>(hp) + off_stage, plan.stage.data(), bytes_stage);
+    memcpy(static_cast<char *>(hp) + off_groups, plan.groups.data(), bytes_groups);
+
+    CU(e->plan.reserve(blob));
+    CU(e->partial.reserve((size_t)n_tiles * std::max(out_base, 1) * sizeof(double)));
+    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    CU(e->staging.mark(slot, e->stream));
+    // a component label without individuals has no ROOT task: its sum is 0, as in the oracle
+    CU(cudaMemsetAsync(e->partial.p, 0, (size_t)n_tiles * out_base * sizeof(double), e->stream));
+
+    Sweep2Params P;
+    P.D = dev_view(e);
+    char *dp = static_cast<char *>(e->plan.p);
+    P.tasks = reinterpret_cast<const Sweep2Task *>(dp);
+    P.pool = reinterpret_cast<const uint32_t *>(dp + off_pool);
+    P.level_off = reinterpret_cast<const int *>(dp + off_loff);
+    P.emis = reinterpret_cast<const Emis2 *>(dp + off_emis);
+    P.stage = reinterpret_cast<const Stage2 *>(dp + off_stage);
+    P.groups = reinterpret_cast<const Sweep2Group *>(dp + off_groups);
+    P.n_groups = G; P.n_levels = n_levels;
+    P.partial = static_cast<double *>(e->partial.p);
+    P.n_out = out_base;
+    P.clocks = nullptr; P.clock_group = 0;
+    const bool fused_reduce = out_base > 0 && out_base <= 256;
+    if (e->sweep_counter.cap == 0) {
+        CU(e->sweep_counter.reserve(256));
+        CU(cudaMemsetAsync(e->sweep_counter.p, 0, e->sweep_counter.cap, e->stream));
+    }
+    P.out = fused_reduce ? out_dev : nullptr;
+    P.counter = static_cast<unsigned *>(e->sweep_counter.p);
+    P.debug_flags = getenv("PF_V2_NOPERSIST") ? 1 : 0;                             // measurement aid: skip the stub / prong stores
+    P.format = plan.format; P.dec16_denom = dec16_denom ? dec16_denom : 1u; P.dec16_rcp = 1.0 / (double)P.dec16_denom;
+    if (e->sweep_clocks) {
+        CU(e->clockbuf.reserve((size_t)(n_levels + 2) * sizeof(long long)));
+        P.clocks = static_cast<long long *>(e->clockbuf.p);
+        int best = 0;
+        for (int g = 0; g < G; g++) if (plan.groups[g].task_end - plan.groups[g].task_begin > plan.groups[best].task_end - plan.groups[best].task_begin) best = g;
+        P.clock_group = best;
+    }
+    {
+        int rows = 0;
+        for (auto &sg : plan.groups) rows += sg.n_rows;
+        const int32_t st[8] = {n_levels, G, (int)plan.tasks.size(), smem_bytes, rows, rows, max_up, n_tiles};
+        memcpy(e->last_plan, st, sizeof st);
+    }
+    e->prof_begin(0);
+    launch_sweep2(P, n_tiles, smem_bytes, e->stream);
+    e->prof_end();
+    e->launches++;
+    e->sweeps_v2++;
+    CU(cudaGetLastError());
+    if (P.clocks) {
+        std::vector<long long> hc(n_levels + 1);
+        CU(cudaStreamSynchronize(e->stream));
+        CU(cudaMemcpy(hc.data(), P.clocks, hc.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        const int *lo = &level_off[(size_t)P.clock_group * (n_levels + 1)];
+        int n_general = 0, hist[8] = {0, 0, 0, 0, 0, 0, 0, 0}, hg[8] = {0, 0, 0, 0, 0, 0, 0, 0}, self = 0, npn = 0;
+        for (auto &t : plan.tasks) {
+            const uint32_t w0 = plan.pool[(size_t)plan.groups[t.group].pool_begin + t.off];
+            hist[w0 & 7]++;
+            if (w0 & T2_GENERAL) { n_general++; hg[w0 & 7]++; if (w0 & 256u) self++; if (w0 >> 24) npn++; }
+        }
+        fprintf(stderr, "sweep2-general-tasks %d of %zu; by kind %d/%d %d/%d %d/%d %d/%d %d/%d %d/%d; bit8 %d np %d\n", n_general, plan.tasks.size(),
+                hg[0], hist[0], hg[1], hist[1], hg[2], hist[2], hg[3], hist[3], hg[4], hist[4], hg[5], hist[5], self, npn);
+        fprintf(stderr, "sweep2-clocks fmt %d levels %d group-tasks %d smem %d:", plan.format, n_levels, lo[n_levels] - lo[0], smem_bytes);
+        for (int l = 0; l < n_levels; l++) fprintf(stderr, " %d:%lld", lo[l + 1] - lo[l], hc[l + 1] - hc[l]);
+        fprintf(stderr, "\n");
+    }
+    if (e->host_prof && ++e->n_prof_calls > 100) { const double t = host_now(); e->t_plan += t_planned - t_begin; e->t_submit += t - t_planned; e->n_prof++; }
+    if (out_base > 0 && !fused_reduce) {
+        ReduceParams R{static_cast<const double *>(e->partial.p), out_dev, n_tiles, out_base};
+        e->prof_begin(2);
+        launch_reduce(R, e->stream);
+        e->prof_end();
+        e->launches++;
+        CU(cudaGetLastError());
+    }
+    return PF_OK;
+}
+
 // Upload the plan and launch sweep + reduce. out_dev receives n_out doubles.
 static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph_view *views, double *out_dev, int *n_out_total, bool up_only = false)
 {
     CU(cudaSetDevice(e->cfg.device));
     int rc = sync_tables(e);
     if (rc) return rc;
+    if (e->sweep_v2) {
+        rc = run_sweeps2(e, n, chains, views, out_dev, n_out_total, up_only);
+        if (rc != PF2_FALLBACK) return rc;
+        e->sweeps_v1_fallback++;
+    }
     const int n_tiles = (e->Sl + TILE_LOCI - 1) / TILE_LOCI;
     const double t_begin = e->host_prof ? host_now() : 0.0;
     static thread_local Plan plan_storage;
@@ -977,7 +1536,10 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
         }
         plan.n_out = out_base;
         *n_out_total = out_base;
-        if (plan.tasks.empty()) return PF_OK;
+        if (plan.tasks.empty()) {
+            if (out_base > 0) CU(cudaMemsetAsync(out_dev, 0, (size_t)out_base * sizeof(double), e->stream));
+            return PF_OK;
+        }
 
         // levels: 0 = leaf caching, up band [1, 1 + max_up), down band starts at 1 + max_up
         n_levels = 1;
@@ -1087,6 +1649,8 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     CU(e->partial.reserve((size_t)n_tiles * std::max(plan.n_out, 1) * sizeof(double)));
     CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
     CU(e->staging.mark(slot, e->stream));
+    // a component label without individuals has no ROOT task: its sum is 0, as in the oracle
+    CU(cudaMemsetAsync(e->partial.p, 0, (size_t)n_tiles * plan.n_out * sizeof(double), e->stream));
 
     SweepParams P;
     P.D = dev_view(e);

@@ -103,13 +103,6 @@ __device__ __forceinline__ int scratch_ref(const SweepCtx &C, int idx)
     return SCRATCH_BIT | idx | (idx < C.n_rows_smem ? SMEM_ROW_BIT : 0);
 }
 
-// exact num / den for 16-bit numerators: Markstein's correction step on the rounded reciprocal
-__device__ __forceinline__ double div_exact(double num, double den, double rcp)
-{
-    const double q = num * rcp;
-    return fma(fma(-den, q, num), rcp, q);
-}
-
 // one locus of a genotype row: planes of `ps` loci starting at p, this thread's locus index i
 // (_ReadPedfile@0x10000b1ca-0x10000b6e2 emission model)
 __device__ __forceinline__ Tri decode_emis(const char *p, unsigned kind, int i, int ps, const EmisEnt &E, double ep)
@@ -154,36 +147,6 @@ __device__ __forceinline__ Tri prod_rows(const SweepCtx &C, const int *rows, int
 {
     for (int j = 0; j < n; j++) acc = mul(acc, ld_t(C, rows[j]));
     return acc;
-}
-
-// ---- family contractions -----------------------------------------------------------------------
-// A marriage with father message a[gp], mother message b[gm] and kid messages k_j contracts
-//     W[gm][gp] = a[gp] * b[gm] * prod_j K_j(gm,gp),   K_j(gm,gp) = sum_gk T[gk][gm][gp] k_j[gk].
-// Every K_j is symmetric in (gm,gp) and so is their elementwise product P (6 values); only the
-// parents' own factors break the symmetry. Messages out of the marriage:
-//     to the father  out[gp] = sum_gm b[gm] P[gm][gp]        (a left out)
-//     to the mother  out[gm] = sum_gp a[gp] P[gm][gp]        (b left out)
-//     to kid j       out[gk] = sum T[gk][gm][gp] a[gp] b[gm] P_{-j}[gm][gp]
-//     prong          the same with all kids in P                (_FillInProngs@0x10001dd70)
-// A selfing marriage has one parent state g = gm = gp: only the diagonal of P and a are used.
-__device__ __forceinline__ Sym3 sym_ones() { return Sym3{1.0, 1.0, 1.0, 1.0, 1.0, 1.0}; }
-__device__ __forceinline__ void sym_mul(Sym3 &P, const Sym3 &K)
-{
-    P.a00 *= K.a00; P.a01 *= K.a01; P.a02 *= K.a02; P.a11 *= K.a11; P.a12 *= K.a12; P.a22 *= K.a22;
-}
-__device__ __forceinline__ Tri fam_to_pa(const Sym3 &P, Tri b, int selfing)
-{
-    if (selfing) return Tri{P.a00, P.a11, P.a22};
-    return Tri{b.x * P.a00 + b.y * P.a01 + b.z * P.a02, b.x * P.a01 + b.y * P.a11 + b.z * P.a12, b.x * P.a02 + b.y * P.a12 + b.z * P.a22};
-}
-__device__ __forceinline__ Tri fam_to_kid(const Sym3 &P, Tri a, Tri b, int selfing)
-{
-    if (selfing) return self_to_kid(Tri{a.x * P.a00, a.y * P.a11, a.z * P.a22});
-    Mat3 W;     // W[gm][gp] = b[gm] * a[gp] * P[gm][gp]
-    W.m[0] = b.x * a.x * P.a00; W.m[1] = b.x * a.y * P.a01; W.m[2] = b.x * a.z * P.a02;
-    W.m[3] = b.y * a.x * P.a01; W.m[4] = b.y * a.y * P.a11; W.m[5] = b.y * a.z * P.a12;
-    W.m[6] = b.z * a.x * P.a02; W.m[7] = b.z * a.y * P.a12; W.m[8] = b.z * a.z * P.a22;
-    return mat_to_kid(W);
 }
 
 // up message of a family member: a stored row, or recomputed for a leaf without a cached row
