@@ -199,7 +199,8 @@ int pf_eval_swaps_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, in
  * in the parents). Reduced on the device to the top_k highest scores per kid (ties: earlier
  * candidate first; top_k <= 32). out_slot/out_score are [n_kids][top_k]; unused entries are
  * -1 / -inf. The caller groups kids that share a candidate set (same generation time: the age
- * window test of @0x100014dbf-0x100014def). Unsharded engines only (ranking needs all loci). */
+ * window test of @0x100014dbf-0x100014def). On a locus shard this needs the communicator
+ * (pf_comm_connect): the dense partial scores are summed over the shards before the ranking. */
 int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,
                  const uint8_t *as_father, int32_t n_cands, const int32_t *cands,
                  const double *cand_bias, int32_t top_k, int32_t *out_slot, double *out_score);
@@ -220,8 +221,28 @@ int pf_prefilter_topk_dev(pf_engine *e, int32_t chain, int32_t n_kids, const int
 int pf_get_stub(pf_engine *e, int32_t chain, int32_t slot, double *out);
 int pf_get_prong(pf_engine *e, int32_t chain, int32_t marr, double *out);
 
+/*
+ * Locus shards on several GPUs of one node, one process per GPU (the reference has no
+ * counterpart: it is one thread on one core). Every rank creates its engine with its own
+ * [locus_begin, locus_end) and makes the identical sequence of calls. After pf_comm_connect every
+ * result that is a sum over loci (ll_cc, lsum, swap sums, prefilter scores) is the sum over ALL
+ * shards, bit-identical on every rank: the library adds the ranks' partial vectors itself, in rank
+ * order, inside one kernel that writes to the peers' mailboxes over NVLink (no NCCL, no host hop).
+ * Set-up: each rank calls pf_comm_local_handle (allocates its mailbox, returns an opaque
+ * PF_COMM_HANDLE_BYTES-byte handle = cudaIpcMemHandle_t), the caller exchanges the handles between
+ * the processes by any means (pedigraph: files in the run directory; Python: torch.distributed),
+ * then pf_comm_connect(rank, world, handles of ranks 0..world-1 concatenated). world <= 8.
+ */
+#define PF_COMM_HANDLE_BYTES 64
+int pf_comm_local_handle(pf_engine *e, int32_t world, void *handle_out);
+int pf_comm_connect(pf_engine *e, int32_t rank, int32_t world, const void *handles);
+int64_t pf_comm_reduce_count(const pf_engine *e);   /* cross-GPU sums performed so far */
+
 /* Counters: kernels launched by this engine since creation. */
 int64_t pf_launch_count(const pf_engine *e);
+/* Counters: bytes the host-buffer entry points copied to the device (plans, views, proposal lists)
+ * and back (results) since creation — what bench.py reports as h2d / d2h bytes per step. */
+int pf_io_bytes(const pf_engine *e, uint64_t *h2d, uint64_t *d2h);
 
 /* Measurement aid: while enabled, every kernel launch is bracketed by CUDA events on the
  * engine's stream. pf_profile_read synchronises, returns the summed device time in

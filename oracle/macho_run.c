@@ -116,6 +116,8 @@ static void *resolve(const char *name) {
     return p;
 }
 
+static void stats_flush(void);
+
 /* A fault inside the reference: print where (Mach-O VM addresses; the binary is -O0 with frame
  * pointers, so the rbp chain is a usable backtrace) and exit like a crash would. */
 static void on_fault(int sig, siginfo_t *si, void *uc_) {
@@ -129,6 +131,7 @@ static void on_fault(int sig, siginfo_t *si, void *uc_) {
         rbp = next;
     }
     fprintf(stderr, "\n");
+    stats_flush();
     fflush(0);
     _exit(128 + sig);
 }
@@ -166,10 +169,44 @@ static void dump_ref_state(FILE *f, char *ped, int id) {
     }
 }
 
+/* PEDFAC_REF_STATS=1 (traps `_MCMC_sampling@0x100019ec0` and `_AddObsFracPrior@0x100019800` by itself):
+ * per MCMC iteration the Gibbs steps entered, the proposals scored (entries of the choice list when the
+ * observation-fraction prior is about to be added) and the wall time from the iteration's first Gibbs
+ * step to the next iteration's first (or to the end of the run), one line per iteration on stderr:
+ *   ref-stats iter I calls N steps M proposals P seconds T
+ * This is how bench.py times the reference itself. */
+static int stats_on = 0, stats_iter = -1;
+static long stats_calls = 0, stats_steps = 0, stats_props = 0;
+static struct timespec stats_t0;
+static double stats_now(const struct timespec *t0) {
+    struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
+    return (double)(t.tv_sec - t0->tv_sec) + 1e-9 * (double)(t.tv_nsec - t0->tv_nsec);
+}
+static void stats_flush(void) {
+    if (stats_on && stats_iter >= 0)
+        fprintf(stderr, "ref-stats iter %d calls %ld steps %ld proposals %ld seconds %.6f\n", stats_iter, stats_calls, stats_steps, stats_props, stats_now(&stats_t0));
+    stats_iter = -1;
+}
+
 static void on_trap(int sig, siginfo_t *si, void *uc_) {
     (void)sig; (void)si;
     ucontext_t *uc = uc_;
     greg_t *g = uc->uc_mcontext.gregs;
+    if (stats_on) {
+        const unsigned long at = (unsigned long)g[REG_RIP] - 1;
+        if (at == 0x100019ec0ul) {                               /* _MCMC_sampling(ped, slot, ...): *ped->f158 = iteration */
+            const int it = **(int **)((char *)g[REG_RDI] + 0x158);
+            if (it != stats_iter) { stats_flush(); stats_iter = it; stats_calls = stats_steps = stats_props = 0; clock_gettime(CLOCK_MONOTONIC, &stats_t0); }
+            stats_calls++;
+        } else if (at == 0x100019800ul) {                        /* _AddObsFracPrior(ped, slot, choice): *choice->f8 = list length */
+            stats_steps++; stats_props += **(int **)((char *)g[REG_RDX] + 0x8);
+        }
+        if (!getenv("PEDFAC_REF_DUMP") && !getenv("PEDFAC_REF_DUMP_LL") && !getenv("PEDFAC_REF_TRACE_FN")) {
+            g[REG_RSP] -= 8;
+            *(uint64_t *)g[REG_RSP] = (uint64_t)g[REG_RBP];
+            return;
+        }
+    }
     if ((unsigned long)g[REG_RIP] - 1 == 0x100019ec0ul && getenv("PEDFAC_REF_DUMP")) dump_ref_state(stderr, (char *)g[REG_RDI], (int)g[REG_RSI]);
     /* PEDFAC_REF_DUMP_LL=1 with `_AddObsFracPrior@0x100019800` (ped, focal slot, choice) traced: the
      * whole proposal list of the Gibbs step with its log-likelihoods at full precision, before the
@@ -256,10 +293,14 @@ int main(int argc, char **argv, char **envp) {
         }
         lc += c->cmdsize;
     }
-    if (getenv("PEDFAC_REF_TRACE_FN")) {
-        char *list = strdup(getenv("PEDFAC_REF_TRACE_FN"));
+    stats_on = getenv("PEDFAC_REF_STATS") != 0;
+    if (stats_on || getenv("PEDFAC_REF_TRACE_FN")) {
+        char *list = malloc(64 + (getenv("PEDFAC_REF_TRACE_FN") ? strlen(getenv("PEDFAC_REF_TRACE_FN")) : 0));
+        strcpy(list, stats_on ? "0x100019ec0,0x100019800," : "");
+        if (getenv("PEDFAC_REF_TRACE_FN")) strcat(list, getenv("PEDFAC_REF_TRACE_FN"));
         for (char *t = strtok(list, ","); t; t = strtok(0, ",")) {
             unsigned char *fn = (unsigned char *)(uintptr_t)strtoull(t, 0, 16);
+            if (*fn == 0xcc) continue;                               /* listed twice */
             if (*fn != 0x55) die("PEDFAC_REF_TRACE_FN: address does not start with push rbp");
             *fn = 0xcc;
         }
@@ -286,6 +327,7 @@ int main(int argc, char **argv, char **envp) {
     static char *apple[] = {(char *)"executable_path=pedigraph", 0};
     typedef int (*macho_main)(int, char **, char **, char **);
     macho_main entry = (macho_main)(uintptr_t)(text_vm + ep->entryoff);
+    atexit(stats_flush);
     int rc = entry(argc, argv, envp, apple);
     fflush(0);
     return rc;

@@ -870,3 +870,11 @@ int pfo_get_prong(pfo_engine *e, int32_t chain, int32_t marr, double *out)
     memcpy(out, e->prong[marr], sizeof(double) * 3 * e->Sl);
     return PF_OK;
 }
+
+int pfo_io_bytes(const pfo_engine *e, uint64_t *h2d, uint64_t *d2h)
+{
+    (void)e;
+    if (h2d) *h2d = 0;
+    if (d2h) *d2h = 0;
+    return 0;
+}

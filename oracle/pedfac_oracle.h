@@ -31,6 +31,8 @@ const double *pfo_tprob(void); /* 27 doubles, [gk][gm][gp] */
 
 int pfo_create(pfo_engine **out, const pf_config *cfg);
 int pfo_destroy(pfo_engine *e);
+/* no device: nothing is ever copied (keeps the sampler source identical for both backends) */
+int pfo_io_bytes(const pfo_engine *e, uint64_t *h2d, uint64_t *d2h);
 int pfo_set_locus_params(pfo_engine *e, const double *eps, const double *afreq);
 int pfo_set_genotypes_hard(pfo_engine *e, int32_t slot, const uint8_t *codes);
 int pfo_set_genotypes_soft(pfo_engine *e, int32_t slot, const float *lik);

@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "profile", "profile_read", "plan_stats",
+    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "io_bytes", "comm_local_handle", "comm_connect", "comm_reduce_count", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -98,6 +98,10 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("get_stub", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
     sig("get_prong", C.c_int, vp, C.c_int32, C.c_int32, _f64p)
     sig("launch_count", C.c_int64, vp)
+    sig("io_bytes", C.c_int, vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
+    sig("comm_local_handle", C.c_int, vp, C.c_int32, vp)
+    sig("comm_connect", C.c_int, vp, C.c_int32, C.c_int32, vp)
+    sig("comm_reduce_count", C.c_int64, vp)
     sig("plan_stats", C.c_int, vp, _i32p)
     sig("profile", C.c_int, vp, C.c_int32)
     sig("profile_read", C.c_int, vp, _f64p, C.POINTER(C.c_int64))
@@ -368,6 +372,31 @@ class CEngine:
     def launch_count(self) -> int:
         fn = getattr(self._lib, self._prefix + "launch_count", None)
         return int(fn(self._h)) if fn is not None else 0
+
+    def io_bytes(self):
+        h2d, d2h = C.c_uint64(0), C.c_uint64(0)
+        self._check(self._fn("io_bytes")(self._h, C.byref(h2d), C.byref(d2h)))
+        return int(h2d.value), int(d2h.value)
+
+    # ---- locus shards on several GPUs (pf_comm_*): the library sums over the shards itself ----
+    def comm_local_handle(self, world: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._check(self._fn("comm_local_handle")(self._h, world, buf))
+        return buf.raw
+
+    def comm_connect(self, rank: int, world: int, handles: bytes) -> None:
+        assert len(handles) == 64 * world
+        self._check(self._fn("comm_connect")(self._h, rank, world, C.create_string_buffer(handles, len(handles))))
+
+    def comm_reduce_count(self) -> int:
+        return int(self._fn("comm_reduce_count")(self._h))
+
+    def comm_init_from_torch(self, dist, rank: int, world: int) -> None:
+        """Exchange the mailbox handles through an initialised torch.distributed group (plumbing only)."""
+        mine = self.comm_local_handle(world)
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        self.comm_connect(rank, world, b"".join(allh))
 
 
 def compose_swap_ll(ll_tot, lsum, ll_cc_x, ll_cc_pa, use_ma, ll_cc_ma):

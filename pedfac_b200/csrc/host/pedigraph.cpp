@@ -36,6 +36,8 @@
 #include <ctime>
 #include <string>
 #include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <vector>
 
 #define PF_CAT2(a, b) a##b
@@ -1150,6 +1152,42 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
 // ---------------------------------------------------------------------------------------------
 // input (_ReadPedfile@0x1000094f0, _CalculateMaxSize@0x1000079c0)
 
+// ---------------------------------------------------------------------------------------------
+// Several GPUs (no counterpart in the reference, which is one thread on one core): PEDFAC_GPUS=N makes
+// `pedigraph` fork one process per GPU. Every process runs the identical chain — same seed, same host
+// logic — on its own slice of the loci; libpedfac_cuda adds the slices' partial sums across the GPUs
+// inside its own kernels (pf_comm_*), so every process sees the same log-likelihoods and makes the
+// same moves. Rank 0 writes the output files and stdout; the others write under out/.shard<r>/.
+static int g_shard_rank = 0, g_shard_world = 1;
+static std::string g_shard_dir;          // where the ranks exchange their mailbox handles
+
+#ifndef PF_NO_COMM
+static void ConnectShards(Ped &p)
+{
+    if (g_shard_world <= 1) return;
+    char mine[PF_COMM_HANDLE_BYTES];
+    if (PFN(comm_local_handle)(p.eng, g_shard_world, mine) != PF_OK) die("cannot create the cross-GPU mailbox");
+    const char *nonce = getenv("PEDFAC_SHARD_NONCE") ? getenv("PEDFAC_SHARD_NONCE") : "0";
+    auto path = [&](int r, bool tmp) { return g_shard_dir + "/.pf_comm_" + nonce + "_" + std::to_string(r) + (tmp ? ".tmp" : ""); };
+    {
+        FILE *f = fopen(path(g_shard_rank, true).c_str(), "wb");
+        if (!f || fwrite(mine, 1, sizeof mine, f) != sizeof mine) die("cannot write the mailbox handle");
+        fclose(f);
+        rename(path(g_shard_rank, true).c_str(), path(g_shard_rank, false).c_str());
+    }
+    std::vector<char> all((size_t)g_shard_world * PF_COMM_HANDLE_BYTES);
+    for (int r = 0; r < g_shard_world; r++) {
+        FILE *f = nullptr;
+        for (int tries = 0; tries < 6000 && !(f = fopen(path(r, false).c_str(), "rb")); tries++) usleep(10000);
+        if (!f || fread(&all[(size_t)r * PF_COMM_HANDLE_BYTES], 1, PF_COMM_HANDLE_BYTES, f) != PF_COMM_HANDLE_BYTES) die("a GPU shard did not come up");
+        fclose(f);
+    }
+    if (PFN(comm_connect)(p.eng, g_shard_rank, g_shard_world, all.data()) != PF_OK) die("cannot connect the GPU shards (peer access between the GPUs is required)");
+}
+#else
+static void ConnectShards(Ped &) { if (g_shard_world > 1) die("this build has one likelihood engine: PEDFAC_GPUS is for the CUDA build"); }
+#endif
+
 static std::vector<std::string> split(const std::string &s, char sep)
 {
     std::vector<std::string> out;
@@ -1299,7 +1337,13 @@ static void ReadGeno(Ped &p, const std::string &path)
     pf_config cfg{};
     cfg.n_loci = p.S; cfg.locus_begin = 0; cfg.locus_end = p.S; cfg.cap_indiv = p.capIndiv; cfg.cap_marr = p.capMarr;
     cfg.n_chains = 1; cfg.device = getenv("PEDFAC_DEVICE") ? atoi(getenv("PEDFAC_DEVICE")) : 0;
+    if (g_shard_world > 1) {                                  // this process owns one slice of the loci (see main)
+        cfg.locus_begin = (int)((long long)p.S * g_shard_rank / g_shard_world);
+        cfg.locus_end = (int)((long long)p.S * (g_shard_rank + 1) / g_shard_world);
+        if (cfg.locus_end <= cfg.locus_begin) die("more GPU shards than loci");
+    }
     if (PFN(create)(&p.eng, &cfg) != PF_OK) die("cannot create the likelihood engine");
+    ConnectShards(p);
     if (PFN(set_locus_params)(p.eng, p.eps.data(), p.afreq.data()) != PF_OK) die("set_locus_params");
 
     // pass 2: rows. Observed rows fill slots 0..nObs-1 in file order, unobserved rows follow
@@ -1536,6 +1580,39 @@ static Opts GetCommLineOpts(int argc, char **argv)
 int main(int argc, char **argv)
 {
     Opts o = GetCommLineOpts(argc, argv);
+    if (getenv("PEDFAC_SHARD_WORLD")) {                        // a child of the launcher below
+        g_shard_world = atoi(getenv("PEDFAC_SHARD_WORLD"));
+        g_shard_rank = getenv("PEDFAC_SHARD_RANK") ? atoi(getenv("PEDFAC_SHARD_RANK")) : 0;
+    } else if (getenv("PEDFAC_GPUS") && atoi(getenv("PEDFAC_GPUS")) > 1) {
+        const int n = atoi(getenv("PEDFAC_GPUS"));
+        mkdir((o.dir + "/out").c_str(), 0777);
+        std::vector<pid_t> kids;
+        const std::string nonce = std::to_string((long)getpid());
+        for (int r = 0; r < n; r++) {
+            const pid_t c = fork();
+            if (c < 0) { perror("fork"); return -1; }
+            if (c == 0) {
+                setenv("PEDFAC_SHARD_WORLD", std::to_string(n).c_str(), 1);
+                setenv("PEDFAC_SHARD_RANK", std::to_string(r).c_str(), 1);
+                setenv("PEDFAC_SHARD_NONCE", nonce.c_str(), 1);
+                setenv("PEDFAC_DEVICE", std::to_string(r).c_str(), 1);
+                execv("/proc/self/exe", argv);
+                perror("execv"); _exit(127);
+            }
+            kids.push_back(c);
+        }
+        int rc = 0;
+        for (int r = 0; r < n; r++) {
+            int st = 0;
+            waitpid(kids[r], &st, 0);
+            const int code = WIFEXITED(st) ? WEXITSTATUS(st) : 128 + (WIFSIGNALED(st) ? WTERMSIG(st) : 0);
+            if (code != 0 && rc == 0) rc = code;
+        }
+        for (int r = 0; r < n; r++) unlink((o.dir + "/out/.pf_comm_" + nonce + "_" + std::to_string(r)).c_str());
+        return rc;
+    }
+    g_shard_dir = o.dir + "/out";
+    if (g_shard_rank > 0 && !freopen("/dev/null", "w", stdout)) return -1;
     Ped p;
     {   // _SeedFromFile@0x100027070
         long a = 0, b = 0;
@@ -1551,8 +1628,9 @@ int main(int argc, char **argv)
         rng::setall(a, b);
     }
     {   // _PrepOutFiles@0x10001a3a0
-        const std::string out = o.dir + "/out";
+        std::string out = o.dir + "/out";
         mkdir(out.c_str(), 0777);
+        if (g_shard_rank > 0) { out += "/.shard" + std::to_string(g_shard_rank); mkdir(out.c_str(), 0777); }
         p.fEdge = fopen((out + "/historyEdge.csv").c_str(), "w");
         p.fNode = fopen((out + "/historyNode.csv").c_str(), "w");
         p.fPed = fopen((out + "/ped.txt").c_str(), "w");
@@ -1598,6 +1676,8 @@ int main(int argc, char **argv)
     for (p.iter = 0; p.iter < o.nIter; p.iter++) {             // _main@0x10001a812-0x10001aaea
         const double t_iter = now();
         const long props0 = p.n_proposals, sweeps0 = p.n_sweeps, steps0 = p.n_steps, swaps0 = p.n_swaps, picked0 = p.n_swaps_picked;
+        uint64_t io0[2] = {0, 0};
+        PFN(io_bytes)(p.eng, &io0[0], &io0[1]);
         p.unobsQueue.clear();
         int qBeg = 0, qEnd = -1;
         for (int k = 0; k < p.nObs; k++) {
@@ -1622,8 +1702,11 @@ int main(int argc, char **argv)
         fflush(stdout);
         if (stats)
         {
-            fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld swaps %ld swaps_picked %ld seconds %.6f\n", p.iter,
-                    p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, p.n_swaps - swaps0, p.n_swaps_picked - picked0, now() - t_iter);
+            uint64_t h2d = 0, d2h = 0;
+            PFN(io_bytes)(p.eng, &h2d, &d2h);
+            fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld swaps %ld swaps_picked %ld seconds %.6f h2d_bytes %llu d2h_bytes %llu\n", p.iter,
+                    p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, p.n_swaps - swaps0, p.n_swaps_picked - picked0, now() - t_iter,
+                    (unsigned long long)(h2d - io0[0]), (unsigned long long)(d2h - io0[1]));
             fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view);
             p.t_sweep = p.t_eval = p.t_view = 0;
         }

@@ -100,6 +100,7 @@ struct pf_engine {
     bool host_prof = false; double t_plan = 0, t_submit = 0, t_wait = 0, t_evalprep = 0; long n_prof = 0, n_prof_calls = 0; double t_ph[6] = {0, 0, 0, 0, 0, 0};
     bool sweep_v2 = true;             // PF_SWEEP_V2=0: first-generation sweep kernel only (measurement aid)
     long sweeps_v2 = 0, sweeps_v1_fallback = 0;
+    unsigned long long io_h2d = 0, io_d2h = 0;       // bytes copied per call path: plans / proposals up, results down (pf_io_bytes)
     bool no_mailbox = false;          // PEDFAC_NO_MAILBOX=1 or no mapped memory: results by copy + stream synchronise
     int sm_count = 0;
     int eval_capacity = 0;            // resident eval_kernel blocks on this device
@@ -125,6 +126,16 @@ struct pf_engine {
     // mapped pinned mailbox for small results: [0] = sequence flag, [8..] = values (see publish_kernel)
     static constexpr int MAILBOX_MAX = 4096;
     unsigned long long *h_mail = nullptr, *d_mail = nullptr, mail_seq = 0;
+
+    // locus shards on several GPUs (pf_comm_*): peer-mapped mailboxes for the cross-GPU sum (xreduce_kernel)
+    struct Comm {
+        bool on = false;
+        int rank = 0, world = 1;
+        void *local = nullptr;                       // this rank's mailbox allocation: flags, then data
+        void *peer_base[XREDUCE_MAX_WORLD] = {};     // every rank's allocation as mapped here (own: local)
+        unsigned long long seq = 1;
+        long n_reduce = 0;
+    } comm;
 
     std::vector<int> loc;                 // slot -> index in the view being planned
     int64_t launches = 0;
@@ -173,6 +184,9 @@ extern "C" int pf_destroy(pf_engine *e)
     e->staging.release();
     if (e->h_result) cudaFreeHost(e->h_result);
     if (e->h_mail) cudaFreeHost(e->h_mail);
+    for (int r = 0; r < e->comm.world && e->comm.on; r++)
+        if (r != e->comm.rank && e->comm.peer_base[r]) cudaIpcCloseMemHandle(e->comm.peer_base[r]);
+    if (e->comm.local) cudaFree(e->comm.local);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return PF_OK;
@@ -252,6 +266,13 @@ extern "C" int pf_set_stream(pf_engine *e, void *cuda_stream)
 }
 
 extern "C" int64_t pf_launch_count(const pf_engine *e) { return e ? e->launches : 0; }
+
+extern "C" int pf_io_bytes(const pf_engine *e, uint64_t *h2d, uint64_t *d2h)
+{
+    if (!e || !h2d || !d2h) return fail(PF_EINVAL, "null argument");
+    *h2d = e->io_h2d; *d2h = e->io_d2h;
+    return PF_OK;
+}
 
 extern "C" int pf_plan_stats(const pf_engine *e, int32_t *out)
 {
@@ -1345,7 +1366,7 @@ static int run_sweeps2(pf_engine *e, int n, const int32_t *chains, const pf_grap
 
     CU(e->plan.reserve(blob));
     CU(e->partial.reserve((size_t)n_tiles * std::max(out_base, 1) * sizeof(double)));
-    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream)); e->io_h2d += blob;
     CU(e->staging.mark(slot, e->stream));
     // a component label without individuals has no ROOT task: its sum is 0, as in the oracle
     CU(cudaMemsetAsync(e->partial.p, 0, (size_t)n_tiles * out_base * sizeof(double), e->stream));
@@ -1647,7 +1668,7 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     CU(e->plan.reserve(blob));
     CU(e->scratch.reserve((size_t)std::max(scratch_rows, 1) * e->row_elems() * sizeof(double)));
     CU(e->partial.reserve((size_t)n_tiles * std::max(plan.n_out, 1) * sizeof(double)));
-    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream)); e->io_h2d += blob;
     CU(e->staging.mark(slot, e->stream));
     // a component label without individuals has no ROOT task: its sum is 0, as in the oracle
     CU(cudaMemsetAsync(e->partial.p, 0, (size_t)n_tiles * plan.n_out * sizeof(double), e->stream));
@@ -1712,6 +1733,72 @@ static int run_sweeps(pf_engine *e, int n, const int32_t *chains, const pf_graph
     return PF_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Locus shards on several GPUs of one node, one process per GPU. Every rank runs the
+// identical call sequence on its own slice of the loci; results that are sums over loci are added
+// up across the ranks by xreduce_kernel through peer-mapped mailboxes before they are delivered, so
+// a sharded engine answers every call exactly as an unsharded one does.
+
+static constexpr size_t COMM_FLAG_BYTES = 256;
+static size_t comm_bytes(int world) { return COMM_FLAG_BYTES + (size_t)2 * world * XREDUCE_MAX * sizeof(double); }
+
+extern "C" int pf_comm_local_handle(pf_engine *e, int32_t world, void *handle_out)
+{
+    if (!e || !handle_out) return fail(PF_EINVAL, "null argument");
+    if (world < 1 || world > XREDUCE_MAX_WORLD) return fail(PF_EINVAL, "world size %d outside [1,%d]", world, XREDUCE_MAX_WORLD);
+    if (e->comm.on) return fail(PF_EINVAL, "communicator already connected");
+    CU(cudaSetDevice(e->cfg.device));
+    if (e->comm.local) { CU(cudaFree(e->comm.local)); e->comm.local = nullptr; }
+    CU(cudaMalloc(&e->comm.local, comm_bytes(world)));
+    CU(cudaMemset(e->comm.local, 0, comm_bytes(world)));
+    e->comm.world = world;
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->comm.local));
+    static_assert(sizeof(cudaIpcMemHandle_t) == PF_COMM_HANDLE_BYTES, "handle size");
+    memcpy(handle_out, &h, sizeof h);
+    return PF_OK;
+}
+
+extern "C" int pf_comm_connect(pf_engine *e, int32_t rank, int32_t world, const void *handles)
+{
+    if (!e || !handles) return fail(PF_EINVAL, "null argument");
+    if (!e->comm.local || world != e->comm.world) return fail(PF_EINVAL, "pf_comm_local_handle(world = %d) must come first", world);
+    if (rank < 0 || rank >= world) return fail(PF_EINVAL, "rank %d outside [0,%d)", rank, world);
+    CU(cudaSetDevice(e->cfg.device));
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { e->comm.peer_base[r] = e->comm.local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(handles) + (size_t)r * PF_COMM_HANDLE_BYTES, sizeof h);
+        const cudaError_t ce = cudaIpcOpenMemHandle(&e->comm.peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (ce != cudaSuccess) return fail(PF_ECUDA, "cannot map the mailbox of rank %d (needs peer access between the GPUs): %s", r, cudaGetErrorString(ce));
+    }
+    e->comm.rank = rank; e->comm.on = world > 1;
+    return PF_OK;
+}
+
+extern "C" int64_t pf_comm_reduce_count(const pf_engine *e) { return e ? e->comm.n_reduce : 0; }
+
+// Sum buf[0..n) over the shards, in place, on the engine's stream; optionally deliver the sums to the
+// mapped host mailbox in the same kernel.
+static int comm_reduce(pf_engine *e, double *buf, int n, double *host_dst = nullptr, unsigned long long *host_flag = nullptr, unsigned long long host_seq = 0)
+{
+    if (n <= 0) return PF_OK;
+    XReduceParams X{};
+    X.src = buf; X.dst = buf; X.n = n; X.rank = e->comm.rank; X.world = e->comm.world; X.seq0 = e->comm.seq;
+    for (int r = 0; r < e->comm.world; r++) {
+        X.peer_flags[r] = static_cast<unsigned long long *>(e->comm.peer_base[r]);
+        X.peer_mail[r] = reinterpret_cast<double *>(static_cast<char *>(e->comm.peer_base[r]) + COMM_FLAG_BYTES);
+    }
+    X.host_dst = host_dst; X.host_flag = host_flag; X.host_seq = host_seq;
+    e->comm.seq += (unsigned long long)((n + XREDUCE_MAX - 1) / XREDUCE_MAX);
+    e->prof_begin(2);
+    launch_xreduce(X, e->stream);
+    e->prof_end();
+    e->launches++; e->comm.n_reduce++;
+    CU(cudaGetLastError());
+    return PF_OK;
+}
+
 static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2 = nullptr, int n2 = 0)
 {
     const int n1 = n;
@@ -1732,9 +1819,15 @@ static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2
         }
         if (e->h_mail) {
             const unsigned long long seq = ++e->mail_seq;
-            launch_publish(static_cast<const double *>(e->result.p), reinterpret_cast<double *>(e->d_mail + 8), n, e->d_mail, seq, e->stream);
-            e->launches++;
-            CU(cudaGetLastError());
+            if (e->comm.on) {          // cross-GPU sum and delivery in one kernel
+                int rc = comm_reduce(e, static_cast<double *>(e->result.p), n, reinterpret_cast<double *>(e->d_mail + 8), e->d_mail, seq);
+                if (rc) return rc;
+            } else {
+                launch_publish(static_cast<const double *>(e->result.p), reinterpret_cast<double *>(e->d_mail + 8), n, e->d_mail, seq, e->stream);
+                e->launches++;
+                CU(cudaGetLastError());
+            }
+            e->io_d2h += (size_t)n * sizeof(double) + 8;
             const double t_w0 = e->host_prof ? host_now() : 0.0;
             volatile unsigned long long *flag = e->h_mail;
             for (unsigned spins = 1; *flag != seq; spins++) {
@@ -1753,6 +1846,7 @@ static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2
             return PF_OK;
         }
     }
+    if (e->comm.on) { int rc = comm_reduce(e, static_cast<double *>(e->result.p), n); if (rc) return rc; }
     if ((size_t)n * sizeof(double) > e->h_result_cap) {
         if (e->h_result) CU(cudaFreeHost(e->h_result));
         e->h_result = nullptr; e->h_result_cap = 0;
@@ -1761,6 +1855,7 @@ static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2
         e->h_result_cap = want;
     }
     CU(cudaMemcpyAsync(e->h_result, e->result.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    e->io_d2h += (size_t)n * sizeof(double);
     CU(cudaStreamSynchronize(e->stream));
     if (n1 > 0) memcpy(host_out, e->h_result, (size_t)n1 * sizeof(double));
     if (n2 > 0) memcpy(host_out2, e->h_result + n1, (size_t)n2 * sizeof(double));
@@ -1791,7 +1886,9 @@ extern "C" int pf_sweep_batch_dev(pf_engine *e, int32_t n, const int32_t *chains
 {
     if (!e || !views || n < 0) return fail(PF_EINVAL, "null argument");
     int n_out = 0;
-    return run_sweeps(e, n, chains, views, ll_cc_dev, &n_out);
+    int rc = run_sweeps(e, n, chains, views, ll_cc_dev, &n_out);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, ll_cc_dev, n_out);
+    return rc;
 }
 
 extern "C" int pf_sweep(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc)
@@ -1803,7 +1900,9 @@ extern "C" int pf_sweep_dev(pf_engine *e, int32_t chain, const pf_graph_view *vi
 {
     if (!e || !view) return fail(PF_EINVAL, "null argument");
     int n_out = 0;
-    return run_sweeps(e, 1, &chain, view, ll_cc_dev, &n_out);
+    int rc = run_sweeps(e, 1, &chain, view, ll_cc_dev, &n_out);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, ll_cc_dev, n_out);
+    return rc;
 }
 
 // forward: defined with the proposal evaluation below
@@ -1957,7 +2056,9 @@ extern "C" int pf_eval_swaps_dev(pf_engine *e, int32_t chain, const pf_graph_vie
 {
     if (!e) return fail(PF_EINVAL, "null argument");
     if (n > 0 && !lsum_dev) return fail(PF_EINVAL, "null output");
-    return run_swaps(e, chain, view, n, swaps, lsum_dev);
+    int rc = run_swaps(e, chain, view, n, swaps, lsum_dev);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, n);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2026,7 +2127,7 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
         CU(e->counters.reserve((size_t)group_blocks * sizeof(unsigned) * 2));
         CU(cudaMemsetAsync(e->counters.p, 0, e->counters.cap, e->stream));
     }
-    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream)); e->io_h2d += blob;
     CU(e->staging.mark(slot, e->stream));
     EvalParams P;
     P.D = dev_view(e);
@@ -2063,7 +2164,9 @@ extern "C" int pf_eval_batch_dev(pf_engine *e, int32_t n, const int32_t *chains,
 {
     if (!e || n < 0 || !kids || !prop_begin) return fail(PF_EINVAL, "null argument");
     if (prop_begin[n] > 0 && (!props || !lsum_dev)) return fail(PF_EINVAL, "null argument");
-    return run_evals(e, n, chains, kids, prop_begin, props, lsum_dev);
+    int rc = run_evals(e, n, chains, kids, prop_begin, props, lsum_dev);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, prop_begin[n]);
+    return rc;
 }
 
 extern "C" int pf_eval(pf_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_proposal *props, double *lsum)
@@ -2076,7 +2179,9 @@ extern "C" int pf_eval_dev(pf_engine *e, int32_t chain, int32_t kid, int32_t n, 
 {
     if (!e || n < 0 || (n > 0 && (!props || !lsum_dev))) return fail(PF_EINVAL, "null argument");
     const int32_t pb[2] = {0, n};
-    return run_evals(e, 1, &chain, &kid, pb, props, lsum_dev);
+    int rc = run_evals(e, 1, &chain, &kid, pb, props, lsum_dev);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, n);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2105,7 +2210,7 @@ static int prefilter_setup(pf_engine *e, int32_t chain, int32_t n_kids, const in
     for (int k = 0; k < n_kids; k++) hk[k] = e->stub_row(chain, kids[k]);
     for (int j = 0; j < n_cands; j++) { hc[j] = e->stub_row(chain, cands[j]); hbias[j] = cand_bias ? cand_bias[j] : 0.0; }
     CU(e->plan.reserve(blob));
-    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream)); e->io_h2d += blob;
     CU(e->staging.mark(slot, e->stream));
     P.D = dev_view(e);
     char *d = static_cast<char *>(e->plan.p);
@@ -2132,6 +2237,7 @@ static int prefilter_rank(pf_engine *e, PrefilterParams &P, const int32_t *cands
     CU(cudaGetLastError());
     std::vector<char> hout(out_bytes);
     CU(cudaMemcpyAsync(hout.data(), e->result.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    e->io_d2h += out_bytes;
     CU(cudaStreamSynchronize(e->stream));
     const double *sc = reinterpret_cast<const double *>(hout.data());
     const int *ix = reinterpret_cast<const int *>(hout.data() + (size_t)n_kids * top_k * sizeof(double));
@@ -2151,10 +2257,12 @@ extern "C" int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const i
     if (!e || n_kids < 0 || n_cands < 0 || !kids || !as_father || !out_slot || !out_score) return fail(PF_EINVAL, "null argument");
     if (n_cands > 0 && !cands) return fail(PF_EINVAL, "null candidates");
     if (top_k <= 0 || top_k > PREF_MAX_TOPK) return fail(PF_EINVAL, "top_k must be in [1, %d]", PREF_MAX_TOPK);
-    if (e->Sl != e->cfg.n_loci) return fail(PF_EINVAL, "pf_prefilter needs an unsharded engine (ranking requires all loci): use pf_prefilter_scores_dev + an all-reduce + pf_prefilter_topk_dev");
+    if (e->Sl != e->cfg.n_loci && !e->comm.on) return fail(PF_EINVAL, "pf_prefilter on a locus shard needs the communicator (pf_comm_connect): ranking requires the scores summed over all loci");
     if (n_kids == 0) return PF_OK;
     PrefilterParams P;
-    int rc = prefilter_setup(e, chain, n_kids, kids, n_cands, cands, cand_bias, P);
+    // shards: the bias is a per-candidate constant, added by rank 0 only; the dense partial scores are
+    // summed across the ranks before anyone ranks them
+    int rc = prefilter_setup(e, chain, n_kids, kids, n_cands, cands, (e->comm.on && e->comm.rank != 0) ? nullptr : cand_bias, P);
     if (rc) return rc;
     CU(e->partial.reserve(std::max<size_t>((size_t)n_kids * n_cands, 1) * sizeof(double)));
     P.scores = static_cast<double *>(e->partial.p);
@@ -2162,6 +2270,13 @@ extern "C" int pf_prefilter(pf_engine *e, int32_t chain, int32_t n_kids, const i
     e->launches += launch_prefilter_scores(P, e->stream);
     e->prof_end();
     CU(cudaGetLastError());
+    if (e->comm.on) {
+        const long long tot = (long long)n_kids * n_cands;
+        for (long long o = 0; o < tot; o += 1 << 24) {          // int-sized pieces
+            rc = comm_reduce(e, P.scores + o, (int)std::min<long long>(1 << 24, tot - o));
+            if (rc) return rc;
+        }
+    }
     return prefilter_rank(e, P, cands, top_k, out_slot, out_score);
 }
 

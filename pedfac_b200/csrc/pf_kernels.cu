@@ -618,6 +618,60 @@ __global__ void __launch_bounds__(256) publish_kernel(const double *src, double 
     if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned long long *>(flag) = seq; __threadfence_system(); }
 }
 
+// ---- cross-GPU sum of a short result vector over NVLink peer memory -----------------------------
+// Loci are sharded over `world` GPUs (one process each); a Gibbs step ends with the per-proposal /
+// per-component sums of every shard added up. The vectors are a few KB, so the exchange is pure
+// latency: ONE kernel on the engine's stream writes this rank's partial vector straight into every
+// peer's mailbox (peer-to-peer stores through NVSwitch), raises a sequence flag there, waits for the
+// flags of the other ranks in its own mailbox, adds the `world` vectors in rank order — the same
+// order on every rank, so all ranks hold bit-identical results and their host logic stays in lock
+// step — and publishes the sums to the host. No NCCL call, no extra launch, no host round trip.
+// Mailboxes are double-buffered by the parity of the sequence number: a rank can be at most one
+// exchange ahead of a peer (it cannot finish exchange s + 1 before that peer has sent s + 1, which
+// the peer does only after it has read everything of exchange s).
+__global__ void __launch_bounds__(1024) xreduce_kernel(const __grid_constant__ XReduceParams X)
+{
+    const int tid = threadIdx.x;
+    for (int c0 = 0, round = 0; c0 < X.n; c0 += XREDUCE_MAX, round++) {
+        const unsigned long long seq = X.seq0 + (unsigned long long)round;
+        const int par = (int)(seq & 1ull), cnt = min(XREDUCE_MAX, X.n - c0);
+        for (int p = 0; p < X.world; p++) {
+            double *dst = X.peer_mail[p] + ((size_t)par * X.world + X.rank) * XREDUCE_MAX;
+            for (int i = tid; i < cnt; i += blockDim.x) dst[i] = X.src[c0 + i];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid < X.world) {
+            *reinterpret_cast<volatile unsigned long long *>(X.peer_flags[tid] + X.rank) = seq;
+            __threadfence_system();
+            volatile unsigned long long *mine = X.peer_flags[X.rank] + tid;
+            const long long t0 = clock64();
+            while (*mine < seq)
+                if (clock64() - t0 > (20ll << 30)) __trap();      // a peer died: ~10 s at 2 GHz, then fail loudly
+        }
+        __syncthreads();
+        __threadfence_system();
+        const double *in = X.peer_mail[X.rank] + (size_t)par * X.world * XREDUCE_MAX;
+        for (int i = tid; i < cnt; i += blockDim.x) {
+            double acc = 0.0;
+            for (int q = 0; q < X.world; q++) acc += *reinterpret_cast<const volatile double *>(in + (size_t)q * XREDUCE_MAX + i);
+            X.dst[c0 + i] = acc;
+            if (X.host_dst) X.host_dst[c0 + i] = acc;
+        }
+        __syncthreads();
+    }
+    if (X.host_flag) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) { *reinterpret_cast<volatile unsigned long long *>(X.host_flag) = X.host_seq; __threadfence_system(); }
+    }
+}
+
+void launch_xreduce(const XReduceParams &X, cudaStream_t st)
+{
+    xreduce_kernel<<<1, 1024, 0, st>>>(X);
+}
+
 void launch_publish(const double *src, double *dst_mapped, int n, unsigned long long *flag_mapped, unsigned long long seq, cudaStream_t st)
 {
     publish_kernel<<<1, 256, 0, st>>>(src, dst_mapped, n, flag_mapped, seq);

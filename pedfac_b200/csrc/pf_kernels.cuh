@@ -182,6 +182,21 @@ struct ReduceParams {
     int n_parts, n;
 };
 
+// cross-GPU sum over peer memory (xreduce_kernel)
+constexpr int XREDUCE_MAX = 8192;        // doubles per (parity, rank) mailbox slot
+constexpr int XREDUCE_MAX_WORLD = 8;
+struct XReduceParams {
+    const double *src;                   // this rank's partial sums [n]
+    double *dst;                         // [n] sums over all ranks (may alias src)
+    int n, rank, world;
+    unsigned long long seq0;             // sequence number of the first round (n / XREDUCE_MAX rounds follow)
+    double *peer_mail[XREDUCE_MAX_WORLD];            // every rank's mailbox data [2][world][XREDUCE_MAX]
+    unsigned long long *peer_flags[XREDUCE_MAX_WORLD];   // every rank's flags [world]
+    double *host_dst;                    // mapped pinned result vector, or null
+    unsigned long long *host_flag, host_seq;
+};
+void launch_xreduce(const XReduceParams &X, cudaStream_t st);
+
 void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, bool throughput_shape, cudaStream_t st);
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st);
 int eval_resident_blocks();

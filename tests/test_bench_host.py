@@ -1,5 +1,6 @@
 """CPU tests of bench.py's host side: the Gibbs-step trace it replays, its byte accounting, the CPU
-sample sizing and the reference arm's JSON line (no GPU needed: the reference arm runs the oracle)."""
+sample sizing and the reference arm's JSON line (no GPU needed: the reference arm runs the reference's
+own binary inside oracle/_ref/pedigraph_macho where that was built, else the C port)."""
 import json
 import subprocess
 import sys
@@ -70,5 +71,8 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "mcmc_proposals_per_sec" and line["unit"] == "proposals/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 1
+    kind = "reference" if (ROOT / "oracle" / "_ref" / "pedigraph_macho").exists() else "port"
+    assert line["cpu_baseline"]["kind"] == kind and line["cpu_baseline"]["cores"] == 1 and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "proposals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # same `config` object as the CUDA arm prints for this workload and GPU count
+    assert line["config"] == bench.workload_config("A", 1, trace_steps=6)
