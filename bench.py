@@ -350,6 +350,7 @@ def replay(wl, args, rank, world, local_rank, trace_steps, steps, warmup, with_c
     eng.set_stream(stream.cuda_stream)
     if sharded:
         eng.comm_init_from_torch(dist, rank, world)          # the library reduces over the shards itself from here on
+        eng.comm_set_async(True)                             # device-resident replay: the sums overlap the next sweep
     synth.upload(eng, data)
     S_local = s1 - s0
     for c in range(chains):
@@ -400,9 +401,10 @@ def replay(wl, args, rank, world, local_rank, trace_steps, steps, warmup, with_c
         for c in range(chains):
             cb = c * tot
             for t, ((view, kid, props), o) in enumerate(zip(trace.steps, offs)):
-                eng.sweep_dev(view, base_ptr + 8 * (cb + o), chain=c)
-                eng.eval_dev(kid, props, base_ptr + 8 * (cb + o + view.n_cc), chain=c)
+                eng.sweep_eval_dev(view, kid, props, base_ptr + 8 * (cb + o), chain=c)
             eng.sweep_dev(trace.final_view, base_ptr + 8 * (cb + off_final), chain=c)
+        if sharded:
+            eng.comm_fence()                                 # the step ends when every cross-GPU sum has landed
 
     def step_e2e():
         """The call sequence pedigraph makes: host buffers in, host results out, every call."""

@@ -131,6 +131,10 @@ int pf_eval(pf_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_propos
  * calls; n may be 0. */
 int pf_sweep_eval(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc,
                   int32_t kid, int32_t n, const pf_proposal *props, double *lsum);
+/* The same with the results left in device memory on the engine's stream:
+ * out_dev = [ll_cc (view->n_cc) | lsum (n)]; on a sharded engine one cross-GPU sum covers both. */
+int pf_sweep_eval_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t kid, int32_t n,
+                      const pf_proposal *props, double *out_dev);
 
 /* Same as pf_sweep / pf_eval but results stay on the device (ll_cc_dev / lsum_dev are device
  * pointers, written on the engine's stream, no host synchronisation): the form used when an
@@ -237,6 +241,13 @@ int pf_get_prong(pf_engine *e, int32_t chain, int32_t marr, double *out);
 int pf_comm_local_handle(pf_engine *e, int32_t world, void *handle_out);
 int pf_comm_connect(pf_engine *e, int32_t rank, int32_t world, const void *handles);
 int64_t pf_comm_reduce_count(const pf_engine *e);   /* cross-GPU sums performed so far */
+/* Optional overlap for the device-buffer (_dev) entry points: with asynchronous sums enabled their
+ * cross-GPU sums run on a second stream, ordered after the kernels that produce their input, while
+ * the engine's stream goes on with the next call; the exchange is pure latency (and waits for the
+ * slowest rank), so this hides it. The caller must not read or reuse an output buffer before
+ * pf_comm_fence, which makes the engine's stream wait for every sum issued so far. */
+int pf_comm_set_async(pf_engine *e, int32_t enable);
+int pf_comm_fence(pf_engine *e);
 
 /* Counters: kernels launched by this engine since creation. */
 int64_t pf_launch_count(const pf_engine *e);

@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "io_bytes", "comm_local_handle", "comm_connect", "comm_reduce_count", "profile", "profile_read", "plan_stats",
+    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "io_bytes", "comm_local_handle", "comm_connect", "comm_reduce_count", "comm_set_async", "comm_fence", "sweep_eval_dev", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -102,6 +102,9 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("comm_local_handle", C.c_int, vp, C.c_int32, vp)
     sig("comm_connect", C.c_int, vp, C.c_int32, C.c_int32, vp)
     sig("comm_reduce_count", C.c_int64, vp)
+    sig("comm_set_async", C.c_int, vp, C.c_int32)
+    sig("comm_fence", C.c_int, vp)
+    sig("sweep_eval_dev", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), C.c_int32, C.c_int32, vp, vp)
     sig("plan_stats", C.c_int, vp, _i32p)
     sig("profile", C.c_int, vp, C.c_int32)
     sig("profile_read", C.c_int, vp, _f64p, C.POINTER(C.c_int64))
@@ -387,6 +390,16 @@ class CEngine:
     def comm_connect(self, rank: int, world: int, handles: bytes) -> None:
         assert len(handles) == 64 * world
         self._check(self._fn("comm_connect")(self._h, rank, world, C.create_string_buffer(handles, len(handles))))
+
+    def comm_set_async(self, enable: bool) -> None:
+        self._check(self._fn("comm_set_async")(self._h, 1 if enable else 0))
+
+    def comm_fence(self) -> None:
+        self._check(self._fn("comm_fence")(self._h))
+
+    def sweep_eval_dev(self, view, kid: int, props, out_ptr: int, chain: int = 0) -> None:
+        """pf_sweep_eval_dev: [ll_cc | lsum] left at device address `out_ptr` (props: make_proposals array)."""
+        self._check(self._fn("sweep_eval_dev")(self._h, chain, C.byref(view.struct), kid, len(props), C.c_void_p(props.ctypes.data), C.c_void_p(out_ptr)))
 
     def comm_reduce_count(self) -> int:
         return int(self._fn("comm_reduce_count")(self._h))

@@ -135,6 +135,10 @@ struct pf_engine {
         void *peer_base[XREDUCE_MAX_WORLD] = {};     // every rank's allocation as mapped here (own: local)
         unsigned long long seq = 1;
         long n_reduce = 0;
+        bool async = false;                          // pf_comm_set_async: sums of the _dev calls run on `stream2`
+        cudaStream_t stream2 = nullptr;
+        cudaEvent_t ev_main = nullptr, ev_comm = nullptr;
+        bool pending = false;                        // a sum was issued on stream2 since the last fence
     } comm;
 
     std::vector<int> loc;                 // slot -> index in the view being planned
@@ -187,6 +191,9 @@ extern "C" int pf_destroy(pf_engine *e)
     for (int r = 0; r < e->comm.world && e->comm.on; r++)
         if (r != e->comm.rank && e->comm.peer_base[r]) cudaIpcCloseMemHandle(e->comm.peer_base[r]);
     if (e->comm.local) cudaFree(e->comm.local);
+    if (e->comm.stream2) cudaStreamDestroy(e->comm.stream2);
+    if (e->comm.ev_main) cudaEventDestroy(e->comm.ev_main);
+    if (e->comm.ev_comm) cudaEventDestroy(e->comm.ev_comm);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
     return PF_OK;
@@ -1778,11 +1785,50 @@ extern "C" int pf_comm_connect(pf_engine *e, int32_t rank, int32_t world, const 
 
 extern "C" int64_t pf_comm_reduce_count(const pf_engine *e) { return e ? e->comm.n_reduce : 0; }
 
-// Sum buf[0..n) over the shards, in place, on the engine's stream; optionally deliver the sums to the
-// mapped host mailbox in the same kernel.
-static int comm_reduce(pf_engine *e, double *buf, int n, double *host_dst = nullptr, unsigned long long *host_flag = nullptr, unsigned long long host_seq = 0)
+// Asynchronous sums: the cross-GPU sums of the _dev entry points are issued on a second stream (after
+// the kernels that produce their input), so the engine's stream goes on with the next sweep while
+// the exchange — which is latency, and waits for the slowest rank — is in flight. The caller owns the
+// output buffers and must not touch them before pf_comm_fence, which makes the engine's stream wait
+// for every sum issued so far. Host-buffer entry points are unaffected (they deliver complete sums).
+extern "C" int pf_comm_set_async(pf_engine *e, int32_t enable)
+{
+    if (!e) return fail(PF_EINVAL, "null engine");
+    CU(cudaSetDevice(e->cfg.device));
+    if (enable && !e->comm.stream2) {
+        CU(cudaStreamCreateWithFlags(&e->comm.stream2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&e->comm.ev_main, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&e->comm.ev_comm, cudaEventDisableTiming));
+    }
+    if (!enable && e->comm.pending) { CU(cudaStreamSynchronize(e->comm.stream2)); e->comm.pending = false; }
+    e->comm.async = enable != 0;
+    return PF_OK;
+}
+
+extern "C" int pf_comm_fence(pf_engine *e)
+{
+    if (!e) return fail(PF_EINVAL, "null engine");
+    if (!e->comm.pending) return PF_OK;
+    CU(cudaSetDevice(e->cfg.device));
+    CU(cudaEventRecord(e->comm.ev_comm, e->comm.stream2));
+    CU(cudaStreamWaitEvent(e->stream, e->comm.ev_comm, 0));
+    e->comm.pending = false;
+    return PF_OK;
+}
+
+// Sum buf[0..n) over the shards, in place; optionally deliver the sums to the mapped host mailbox in
+// the same kernel. The exchanges of one engine are totally ordered (their sequence numbers drive the
+// mailbox protocol): they all run on stream2 once asynchronous sums are enabled, else on the engine's
+// stream.
+static int comm_reduce(pf_engine *e, double *buf, int n, double *host_dst = nullptr, unsigned long long *host_flag = nullptr, unsigned long long host_seq = 0, bool may_defer = false)
 {
     if (n <= 0) return PF_OK;
+    cudaStream_t st = e->stream;
+    if (e->comm.stream2 && (e->comm.async || e->comm.pending)) {
+        CU(cudaEventRecord(e->comm.ev_main, e->stream));
+        CU(cudaStreamWaitEvent(e->comm.stream2, e->comm.ev_main, 0));
+        st = e->comm.stream2;
+        e->comm.pending = true;
+    }
     XReduceParams X{};
     X.src = buf; X.dst = buf; X.n = n; X.rank = e->comm.rank; X.world = e->comm.world; X.seq0 = e->comm.seq;
     for (int r = 0; r < e->comm.world; r++) {
@@ -1791,11 +1837,12 @@ static int comm_reduce(pf_engine *e, double *buf, int n, double *host_dst = null
     }
     X.host_dst = host_dst; X.host_flag = host_flag; X.host_seq = host_seq;
     e->comm.seq += (unsigned long long)((n + XREDUCE_MAX - 1) / XREDUCE_MAX);
-    e->prof_begin(2);
-    launch_xreduce(X, e->stream);
-    e->prof_end();
+    if (st == e->stream) e->prof_begin(2);
+    launch_xreduce(X, st);
+    if (st == e->stream) e->prof_end();
     e->launches++; e->comm.n_reduce++;
     CU(cudaGetLastError());
+    if (st != e->stream && !(may_defer && e->comm.async)) { int rc = pf_comm_fence(e); if (rc) return rc; }
     return PF_OK;
 }
 
@@ -1887,7 +1934,7 @@ extern "C" int pf_sweep_batch_dev(pf_engine *e, int32_t n, const int32_t *chains
     if (!e || !views || n < 0) return fail(PF_EINVAL, "null argument");
     int n_out = 0;
     int rc = run_sweeps(e, n, chains, views, ll_cc_dev, &n_out);
-    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, ll_cc_dev, n_out);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, ll_cc_dev, n_out, nullptr, nullptr, 0, true);
     return rc;
 }
 
@@ -1901,7 +1948,7 @@ extern "C" int pf_sweep_dev(pf_engine *e, int32_t chain, const pf_graph_view *vi
     if (!e || !view) return fail(PF_EINVAL, "null argument");
     int n_out = 0;
     int rc = run_sweeps(e, 1, &chain, view, ll_cc_dev, &n_out);
-    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, ll_cc_dev, n_out);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, ll_cc_dev, n_out, nullptr, nullptr, 0, true);
     return rc;
 }
 
@@ -1929,6 +1976,24 @@ extern "C" int pf_sweep_eval(pf_engine *e, int32_t chain, const pf_graph_view *v
         if (rc) return rc;
     }
     return fetch_result(e, ll_cc, n_out, lsum, n);
+}
+
+// the same with the results left on the device: out_dev = [ll_cc (view->n_cc) | lsum (n)], one
+// cross-GPU sum over both on a sharded engine
+extern "C" int pf_sweep_eval_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t kid, int32_t n, const pf_proposal *props, double *out_dev)
+{
+    if (!e || !view || n < 0 || (n > 0 && !props)) return fail(PF_EINVAL, "null argument");
+    if ((view->n_cc > 0 || n > 0) && !out_dev) return fail(PF_EINVAL, "null output");
+    int n_out = 0;
+    int rc = run_sweeps(e, 1, &chain, view, out_dev, &n_out);
+    if (rc) return rc;
+    if (n > 0) {
+        const int32_t pb[2] = {0, n};
+        rc = run_evals(e, 1, &chain, &kid, pb, props, out_dev + n_out);
+        if (rc) return rc;
+    }
+    if (e->comm.on) rc = comm_reduce(e, out_dev, n_out + n, nullptr, nullptr, 0, true);
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -2057,7 +2122,7 @@ extern "C" int pf_eval_swaps_dev(pf_engine *e, int32_t chain, const pf_graph_vie
     if (!e) return fail(PF_EINVAL, "null argument");
     if (n > 0 && !lsum_dev) return fail(PF_EINVAL, "null output");
     int rc = run_swaps(e, chain, view, n, swaps, lsum_dev);
-    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, n);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, n, nullptr, nullptr, 0, true);
     return rc;
 }
 
@@ -2165,7 +2230,7 @@ extern "C" int pf_eval_batch_dev(pf_engine *e, int32_t n, const int32_t *chains,
     if (!e || n < 0 || !kids || !prop_begin) return fail(PF_EINVAL, "null argument");
     if (prop_begin[n] > 0 && (!props || !lsum_dev)) return fail(PF_EINVAL, "null argument");
     int rc = run_evals(e, n, chains, kids, prop_begin, props, lsum_dev);
-    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, prop_begin[n]);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, prop_begin[n], nullptr, nullptr, 0, true);
     return rc;
 }
 
@@ -2180,7 +2245,7 @@ extern "C" int pf_eval_dev(pf_engine *e, int32_t chain, int32_t kid, int32_t n, 
     if (!e || n < 0 || (n > 0 && (!props || !lsum_dev))) return fail(PF_EINVAL, "null argument");
     const int32_t pb[2] = {0, n};
     int rc = run_evals(e, 1, &chain, &kid, pb, props, lsum_dev);
-    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, n);
+    if (rc == PF_OK && e->comm.on) rc = comm_reduce(e, lsum_dev, n, nullptr, nullptr, 0, true);
     return rc;
 }
 

@@ -34,18 +34,24 @@ namespace pf {
 //   FAM_DOWN(m)  in_u(m); dn_m(x) and stub(x) = up_i(x) * dn_m(x) for every down
 //                member x; prong(m)                                              level base + depth
 // Task records live in an int32 pool. Row references: plain = persistent row index; bit 30 =
-// transient row (group-local index), and bit 29 as well when that row lives in shared memory;
+// transient row (group-local index: shared memory below the group's n_rows_smem, else spilled);
 // bit 31 (LEAF_REF_BIT) = no row: recompute the leaf's local factor from its genotype tile.
-//   ROOT:     member, stub_row, out_idx, nD, up_m_row[nD]
-//   LEAF_IN:  member, up_i_row
-//   FAM_UP:   flags, up_m_row, nC, { member, up_i_row, nD, below_up_m_row[nD] } * nC, pa_ref, ma_ref, nk, kid_ref[nk]
-//   FAM_DOWN: flags, prong_row, u_member, u_dn_row (-1 = root), nSib, sib_up_m_row[nSib],
-//             pa{ref, stub_row, dn_row}, ma{ref, stub_row, dn_row}, nk, kid{ref, stub_row, dn_row} * nk, tmp_row
-//             (ref = NO_REF: that parent is the up individual / absent; dn_row = -1: not needed;
-//              tmp_row: scratch rows of a large sibship — 2 for the parents' messages + 2 per chunk — or -1)
+// A sibship is a list of items {type, value}: type 0 = one kid (value = its up reference), type 1 =
+// a chunk of 2..FAM_CHUNK leaf kids whose factor product a KFOLD task left in rows value, value + 1.
+//   ROOT:      member, stub_row, out_idx, nD, up_m_row[nD]
+//   LEAF_IN:   member, up_i_row
+//   KFOLD:     out_row (2 rows), n, kid_ref[n]
+//   FAM_UP:    flags, up_m_row, nC, { member, up_i_row, nD, below_up_m_row[nD] } * nC, pa_ref, ma_ref,
+//              n_items, item[n_items]
+//   FAM_DOWN:  flags, prong_row, u_member, u_dn_row (-1 = root), nSib, sib_up_m_row[nSib],
+//              pa{ref, stub_row, dn_row}, ma{ref, stub_row, dn_row}, n_items, tmp_row, item[n_items]
+//              (+ stub_row, dn_row of the kid when the sibship is one single kid: tmp_row = -1;
+//              ref = NO_REF: that parent is the up individual / absent; dn_row = -1: not needed)
+//   FAM_EXCL:  n_items (>= 2), out_row, item[n_items]
+//   KID_CHUNK: flags, ab_row (a, b, Pu: 4 rows), out_row (-1 = the only item), n, { up_ref, stub_row, dn_row } * n
 // member = role | founder << 2 | (group-local genotype entry index) << 3; roles: 0 father,
 // 1 mother, 2 kid. flags = selfing | (role of u(m) in m) << 1.
-//   KID_CHUNK (large sibships; next level): flags, ab_row, outside_row, n, { up_ref, stub_row, dn_row } * n
+// (This is the first-generation plan; the compiled records of sweep2_kernel are in pf_sweep2.cuh.)
 enum TaskKind : int { TASK_ROOT = 0, TASK_LEAF_IN = 1, TASK_FAM_UP = 2, TASK_FAM_DOWN = 3, TASK_KID_CHUNK = 4, TASK_KFOLD = 5, TASK_FAM_EXCL = 6 };
 constexpr int NO_REF = 0x1fffffff;
 #ifndef PF_FAM_CHUNK

@@ -48,6 +48,14 @@ for soft in (False, True):
     eng.set_stream(torch.cuda.current_stream().cuda_stream)
     eng.eval_dev(kid, props, buf.data_ptr()); torch.cuda.synchronize()
     np.testing.assert_allclose(buf.cpu().numpy(), ls_f, rtol=1e-12, atol=1e-11)
+    # one submission, one cross-GPU sum, issued on the second stream and fenced
+    eng.comm_set_async(True)
+    buf2 = torch.zeros(view.n_cc + len(props), dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        eng.sweep_eval_dev(view, kid, props, buf2.data_ptr())
+    eng.comm_fence(); torch.cuda.synchronize()
+    np.testing.assert_allclose(buf2.cpu().numpy(), np.concatenate([cc_f, ls_f]), rtol=1e-12, atol=1e-11)
+    eng.comm_set_async(False)
     # prefilter: ranking needs the scores of all loci
     obs = np.flatnonzero(d.observed)
     kids = np.array([int(d.slot[i]) for i in obs if d.gen[i] == 0][:24], dtype=np.int32)
