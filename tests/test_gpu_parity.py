@@ -234,7 +234,8 @@ def test_gpu_prefilter_matches_oracle():
         assert abs(ov[k, t] - gv[k, t]) <= 1e-9 * abs(ov[k, t])
 
 
-@pytest.mark.parametrize("name,n,S,soft", [("A_1k_x_500_hard", 1000, 500, False), ("B_5k_x_2k_soft", 5000, 2000, True)])
+@pytest.mark.parametrize("name,n,S,soft", [("A_1k_x_500_hard", 1000, 500, False), ("B_5k_x_2k_soft", 5000, 2000, True),
+                                           ("C_20k_x_10k_hard", 20000, 10000, False)])
 def test_gpu_full_size_properties(name, n, S, soft):
     """BASELINE.json sizes, where the oracle is too slow to be the checker: size-independent
     properties. (1) additivity over locus shards (a checksum of checksums); (2) the joined-family
@@ -489,3 +490,37 @@ def test_gpu_repeated_sweeps_are_bitwise_identical():
         np.testing.assert_array_equal(g.get_stub(i), s)
     for m, s in zip(marrs, ref_prongs):
         np.testing.assert_array_equal(g.get_prong(m), s)
+
+
+def test_gpu_config_d_scale_batch_equals_single_chain():
+    """BASELINE.json's last configuration at full size: 64 chains batched on one GPU over the config-B
+    data (5 000 x 2 000 soft calls). All chains are given the same views and proposals, so every chain
+    of every batched call must return, bit for bit, what chain 0 returns when it is called alone
+    (the chains share the genotype arrays and differ only in their row block; proposal sums to 1e-12, their
+    locus chunking depends on the batch size), through a few Gibbs-step
+    passes of the bench trace; stubs and prongs of the last chain are compared with the first's."""
+    import bench
+    n_chains = 64
+    d = synth.simulate(5000, 2000, soft=True, seed=46)
+    tr = bench.Trace(d, 4)
+    g = Engine(d.n_loci, tr.cap_i, tr.cap_m, n_chains=n_chains)
+    synth.upload(g, d)
+    chains = np.arange(n_chains, dtype=np.int32)
+    ll_all = g.sweep_batch(chains, [tr.full_view] * n_chains).reshape(n_chains, -1)
+    ll_one = g.sweep(tr.full_view, chain=0)
+    assert np.isfinite(ll_one).all()
+    assert (ll_all == ll_one[None, :]).all()
+    for view, kid, props in tr.steps:
+        got_cc = g.sweep_batch(chains, [view] * n_chains).reshape(n_chains, -1)
+        pb = np.arange(n_chains + 1, dtype=np.int32) * len(props)
+        got_ls = g.eval_batch(chains, np.full(n_chains, kid, dtype=np.int32), pb, np.tile(props, n_chains)).reshape(n_chains, -1)
+        one_cc, one_ls = g.sweep_eval(view, kid, props, chain=0)
+        assert (got_cc == one_cc[None, :]).all()
+        assert (got_ls == got_ls[0][None, :]).all()            # every chain of the batch: the same bits
+        # batch vs single call: the locus chunking of the eval grid depends on the batch size, so the sums
+        # are associated differently
+        np.testing.assert_allclose(got_ls[0], one_ls, rtol=1e-12, atol=1e-11)
+        assert np.isfinite(one_ls).all()
+    slot = int(tr.steps[-1][1])
+    assert (g.get_stub(slot, chain=n_chains - 1) == g.get_stub(slot, chain=0)).all()
+    g.sweep_batch(chains, [tr.final_view] * n_chains)
