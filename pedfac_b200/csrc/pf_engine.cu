@@ -99,6 +99,7 @@ struct pf_engine {
     bool sweep_clocks = false;        // PF_SWEEP_CLOCKS=1: per-level clocks of the largest group after every sweep
     bool host_prof = false; double t_plan = 0, t_submit = 0, t_wait = 0, t_evalprep = 0; long n_prof = 0, n_prof_calls = 0; double t_ph[6] = {0, 0, 0, 0, 0, 0};
     bool sweep_v2 = true;             // PF_SWEEP_V2=0: first-generation sweep kernel only (measurement aid)
+    bool eval_singles = true;         // PF_EVAL_SINGLES=0: single-parent proposals through the general path (measurement aid)
     long sweeps_v2 = 0, sweeps_v1_fallback = 0;
     unsigned long long io_h2d = 0, io_d2h = 0;       // bytes copied per call path: plans / proposals up, results down (pf_io_bytes)
     bool no_mailbox = false;          // PEDFAC_NO_MAILBOX=1 or no mapped memory: results by copy + stream synchronise
@@ -257,6 +258,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->host_prof = getenv("PF_HOST_PROF") != nullptr;
     e->sweep_clocks = getenv("PF_SWEEP_CLOCKS") != nullptr;
     if (const char *v2 = getenv("PF_SWEEP_V2")) e->sweep_v2 = v2[0] != '0';
+    if (const char *v2 = getenv("PF_EVAL_SINGLES")) e->eval_singles = v2[0] != '0';
     if (const char *fs = getenv("PF_SWEEP_SHAPE")) e->force_shape = fs[0] == 't' ? 2 : fs[0] == 'l' ? 1 : 0;
     *out = e;
     return PF_OK;
@@ -2136,11 +2138,18 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     const int n_props = prop_begin[n];
     if (n_props <= 0) return PF_OK;
     const double t_e0 = e->host_prof ? host_now() : 0.0;
+    // Single-parent proposals (one given parent or none, the other an HWE founder) go eight to a warp
+    // through the one-row form, everything else four to a warp: the kernel's proposal array is in that
+    // order, every entry carrying its index in the caller's list.
+    for (int i = 0; i < n; i++)
+        if (prop_begin[i + 1] < prop_begin[i]) return fail(PF_EINVAL, "prop_begin not monotone");
+    auto is_single = [&](const pf_proposal &q) { return e->eval_singles && q.kind == PF_PROP_TRIO && (q.pa < 0 || q.ma < 0); };
     int n_groups = 0;
     for (int i = 0; i < n; i++) {
-        const int c = prop_begin[i + 1] - prop_begin[i];
-        if (c < 0) return fail(PF_EINVAL, "prop_begin not monotone");
-        n_groups += (c + EVAL_G - 1) / EVAL_G;
+        int ns = 0;
+        for (int p = prop_begin[i]; p < prop_begin[i + 1]; p++) ns += is_single(props[p]) ? 1 : 0;
+        const int ng = prop_begin[i + 1] - prop_begin[i] - ns;
+        n_groups += (ns + EVAL_GS - 1) / EVAL_GS + (ng + EVAL_G - 1) / EVAL_G;
     }
     const size_t bytes_groups = (size_t)n_groups * sizeof(EvalGroup);
     const size_t off_props = (bytes_groups + 15) & ~(size_t)15;
@@ -2149,27 +2158,34 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     CU(e->staging.get(blob, &hp, &slot));
     EvalGroup *hg = static_cast<EvalGroup *>(hp);
     EvalProp *hq = reinterpret_cast<EvalProp *>(static_cast<char *>(hp) + off_props);
-    int gi = 0;
+    int gi = 0, pos = 0;
     for (int i = 0; i < n; i++) {
         const int chain = chains ? chains[i] : 0, kid = kids[i];
         if (chain < 0 || chain >= e->cfg.n_chains) return fail(PF_EINVAL, "chain %d out of range", chain);
         if (kid < 0 || kid >= e->cfg.cap_indiv) return fail(PF_EINVAL, "kid slot %d out of range", kid);
-        for (int p = prop_begin[i]; p < prop_begin[i + 1]; p++) {
-            const pf_proposal &q = props[p];
-            EvalProp d{q.kind, ROW_PRIOR, ROW_PRIOR, 0};
-            if (q.kind == PF_PROP_TRIO || q.kind == PF_PROP_SELFING) {
-                if (q.pa < -1 || q.pa >= e->cfg.cap_indiv || q.ma < -1 || q.ma >= e->cfg.cap_indiv)
-                    return fail(PF_EINVAL, "proposal %d: parent slot out of range", p);
-                if (q.pa >= 0) d.row_p = e->stub_row(chain, q.pa);
-                if (q.kind == PF_PROP_TRIO && q.ma >= 0) d.row_m = e->stub_row(chain, q.ma);
-            } else if (q.kind == PF_PROP_PRONG) {
-                if (q.marr < 0 || q.marr >= e->cfg.cap_marr) return fail(PF_EINVAL, "proposal %d: marriage slot out of range", p);
-                d.row_p = e->prong_row(chain, q.marr);
-            } else return fail(PF_EINVAL, "proposal %d: unknown kind %d", p, q.kind);
-            hq[p] = d;
+        for (int pass = 0; pass < 2; pass++) {
+            const int first = pos;
+            for (int p = prop_begin[i]; p < prop_begin[i + 1]; p++) {
+                const pf_proposal &q = props[p];
+                if (q.kind != PF_PROP_TRIO && q.kind != PF_PROP_SELFING && q.kind != PF_PROP_PRONG) return fail(PF_EINVAL, "proposal %d: unknown kind %d", p, q.kind);
+                if (is_single(q) != (pass == 0)) continue;
+                EvalProp d{q.kind, ROW_PRIOR, ROW_PRIOR, p};
+                if (q.kind == PF_PROP_TRIO || q.kind == PF_PROP_SELFING) {
+                    if (q.pa < -1 || q.pa >= e->cfg.cap_indiv || q.ma < -1 || q.ma >= e->cfg.cap_indiv)
+                        return fail(PF_EINVAL, "proposal %d: parent slot out of range", p);
+                    if (q.pa >= 0) d.row_p = e->stub_row(chain, q.pa);
+                    if (q.kind == PF_PROP_TRIO && q.ma >= 0) d.row_m = e->stub_row(chain, q.ma);
+                    if (pass == 0 && q.pa < 0) { d.row_p = d.row_m; d.row_m = ROW_PRIOR; }      // the given parent's row, whichever role
+                } else {
+                    if (q.marr < 0 || q.marr >= e->cfg.cap_marr) return fail(PF_EINVAL, "proposal %d: marriage slot out of range", p);
+                    d.row_p = e->prong_row(chain, q.marr);
+                }
+                hq[pos++] = d;
+            }
+            const int per = pass == 0 ? EVAL_GS : EVAL_G;
+            for (int b = first; b < pos; b += per)
+                hg[gi++] = EvalGroup{e->stub_row(chain, kid), b, std::min(per, pos - b), pass == 0 ? 1 : 0};
         }
-        for (int b = prop_begin[i]; b < prop_begin[i + 1]; b += EVAL_G)
-            hg[gi++] = EvalGroup{e->stub_row(chain, kid), b, std::min(EVAL_G, prop_begin[i + 1] - b), 0};
     }
     // chunking: (chunks x group blocks) fills one wave of resident blocks without spilling into a
     // second, mostly empty one (measured at config C: a 1.45-wave grid 91 us, one wave 80 us); at

@@ -495,60 +495,126 @@ void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged
 
 // ---- proposal evaluation ---------------------------------------------------------------------
 
-// All row loads of a locus (kid + two rows per proposal of the group) are issued up front and
-// unconditionally — a proposal that has no second row points at the prior row — so one warp keeps
-// 27 independent 256 B segments in flight; the three contraction forms are then all computed and
-// the proposal's kind selects one (a few spare flops on a memory-bound kernel).
-__global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_constant__ EvalParams P)
+// A group is one warp's work: up to EVAL_G general proposals, or up to EVAL_GS single-parent
+// proposals, of one focal kid over one chunk of loci (lanes = consecutive loci, so every row read is
+// a coalesced 256 B segment). All row loads of a locus are issued up front and unconditionally, so a
+// warp keeps 27 (general) or 30 (singles) independent segments in flight.
+//   general: the three contraction forms are all computed and the proposal's kind selects one;
+//   singles: a proposal with one given parent x (or none: x = the prior) and an HWE founder as the
+//            other is  v = x . (A prior)  with A = kid_matrix(kid stub) symmetric — one row and three
+//            FMAs per proposal instead of two rows and twelve, and these are the proposals whose rows
+//            come from HBM (every unobserved individual and the prefilter list are single-parent
+//            candidates; the pairs re-read the ten best rows from L2). Twice the proposals per warp:
+//            twice the useful bytes in flight.
+template <int G, bool SINGLE>
+__device__ __forceinline__ void eval_group(const EvalParams &P, const EvalGroup &g, int chunk, int lane)
 {
     const DevView &D = P.D;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gi = blockIdx.y * EVAL_WARPS + warp;
-    const int chunk = blockIdx.x;
-    EvalGroup g{ROW_PRIOR, 0, 0, 0};
-    if (gi < P.n_groups) g = P.groups[gi];
     const int s_beg = chunk * P.chunk_loci;
     const int s_end = min(s_beg + P.chunk_loci, D.Sl);
     const size_t row_elems = (size_t)3 * D.Sp;
-
-    int kind[EVAL_G];
-    const double *rp[EVAL_G], *rm[EVAL_G];
-    LogProd acc[EVAL_G];
+    int kind[G];
+    const double *rp[G], *rm[SINGLE ? 1 : G];
+    LogProd acc[G];
 #pragma unroll
-    for (int j = 0; j < EVAL_G; j++) {
+    for (int j = 0; j < G; j++) {
         lp_init(acc[j]);
         EvalProp pr{0, ROW_PRIOR, ROW_PRIOR, 0};
         if (j < g.n) pr = P.props[g.begin + j];
         kind[j] = pr.kind;
         rp[j] = D.rows + (size_t)pr.row_p * row_elems;
-        rm[j] = D.rows + (size_t)pr.row_m * row_elems;
+        if (!SINGLE) rm[j] = D.rows + (size_t)pr.row_m * row_elems;
     }
     const double *kid_row = D.rows + (size_t)g.kid_row * row_elems;
-
+    const double *prior_row = D.rows + (size_t)ROW_PRIOR * row_elems;
     for (int s = s_beg + lane; s < s_end; s += 32) {
         const Tri kid = ld_tri(kid_row, D.Sp, s);
-        Tri xp[EVAL_G], xm[EVAL_G];
+        Tri xp[G], xm[SINGLE ? 1 : G];
 #pragma unroll
-        for (int j = 0; j < EVAL_G; j++) { xp[j] = ld_tri(rp[j], D.Sp, s); xm[j] = ld_tri(rm[j], D.Sp, s); }
+        for (int j = 0; j < G; j++) { xp[j] = ld_tri(rp[j], D.Sp, s); if (!SINGLE) xm[j] = ld_tri(rm[j], D.Sp, s); }
         const Sym3 A = kid_matrix(kid);
+        if (SINGLE) {
+            const Tri c = sym_mv(A, ld_tri(prior_row, D.Sp, s));
 #pragma unroll
-        for (int j = 0; j < EVAL_G; j++) {
-            const double vt = dot(xm[j], sym_mv(A, xp[j]));         // trio
-            const double vs = dot(kid, self_to_kid(xp[j]));        // selfing
-            const double vp = dot(xp[j], kid);                      // prong
-            const double v = kind[j] == 0 ? vt : kind[j] == 1 ? vs : vp;
-            if (j < g.n) lp_mul(acc[j], v);
+            for (int j = 0; j < G; j++)
+                if (j < g.n) lp_mul(acc[j], dot(xp[j], c));
+        } else {
+#pragma unroll
+            for (int j = 0; j < G; j++) {
+                const double vt = dot(xm[j], sym_mv(A, xp[j]));         // trio
+                const double vs = dot(kid, self_to_kid(xp[j]));        // selfing
+                const double vp = dot(xp[j], kid);                      // prong
+                const double v = kind[j] == 0 ? vt : kind[j] == 1 ? vs : vp;
+                if (j < g.n) lp_mul(acc[j], v);
+            }
         }
     }
 #pragma unroll
-    for (int j = 0; j < EVAL_G; j++) {
+    for (int j = 0; j < G; j++) {
         if (j >= g.n) continue;
         const LogProd r = lp_warp_reduce(acc[j]);
         if (lane == 0) { P.partial[(size_t)chunk * P.n_props + g.begin + j] = lp_log(r); __threadfence(); }
     }
+}
+
+// singles, two loci per lane: every row read is one 128-bit load per lane (a 512 B segment per warp
+// and plane), so half as many load instructions carry the same bytes
+__device__ __forceinline__ void eval_singles2(const EvalParams &P, const EvalGroup &g, int chunk, int lane)
+{
+    constexpr int G = EVAL_GS;
+    const DevView &D = P.D;
+    const int s_beg = chunk * P.chunk_loci;
+    const int s_end = min(s_beg + P.chunk_loci, D.Sl);
+    const size_t row_elems = (size_t)3 * D.Sp;
+    const double *rp[G];
+    LogProd acc[G];
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+        lp_init(acc[j]);
+        rp[j] = D.rows + (size_t)(j < g.n ? P.props[g.begin + j].row_p : ROW_PRIOR) * row_elems;
+    }
+    const double *kid_row = D.rows + (size_t)g.kid_row * row_elems;
+    const double *prior_row = D.rows + (size_t)ROW_PRIOR * row_elems;
+    auto ld2 = [&](const double *row, int pl, int s) { return *reinterpret_cast<const double2 *>(row + (size_t)pl * D.Sp + s); };
+    for (int s = s_beg + 2 * lane; s < s_end; s += 64) {           // s even, Sp a multiple of 64: 16-byte aligned, in bounds
+        double2 x[G][3];
+#pragma unroll
+        for (int j = 0; j < G; j++)
+#pragma unroll
+            for (int pl = 0; pl < 3; pl++) x[j][pl] = ld2(rp[j], pl, s);
+        const double2 k0 = ld2(kid_row, 0, s), k1 = ld2(kid_row, 1, s), k2 = ld2(kid_row, 2, s);
+        const double2 q0 = ld2(prior_row, 0, s), q1 = ld2(prior_row, 1, s), q2 = ld2(prior_row, 2, s);
+        const Tri ca = sym_mv(kid_matrix(Tri{k0.x, k1.x, k2.x}), Tri{q0.x, q1.x, q2.x});
+        const Tri cb = sym_mv(kid_matrix(Tri{k0.y, k1.y, k2.y}), Tri{q0.y, q1.y, q2.y});
+        const bool second = s + 1 < s_end;
+#pragma unroll
+        for (int j = 0; j < G; j++) {
+            if (j >= g.n) continue;
+            lp_mul(acc[j], dot(Tri{x[j][0].x, x[j][1].x, x[j][2].x}, ca));
+            if (second) lp_mul(acc[j], dot(Tri{x[j][0].y, x[j][1].y, x[j][2].y}, cb));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < G; j++) {
+        if (j >= g.n) continue;
+        const LogProd r = lp_warp_reduce(acc[j]);
+        if (lane == 0) { P.partial[(size_t)chunk * P.n_props + g.begin + j] = lp_log(r); __threadfence(); }
+    }
+}
+
+__global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_constant__ EvalParams P)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gi = blockIdx.y * EVAL_WARPS + warp;
+    const int chunk = blockIdx.x;
+    EvalGroup g{ROW_PRIOR, 0, 0, 0};
+    if (gi < P.n_groups) g = P.groups[gi];
+    if (g.single) eval_singles2(P, g, chunk, lane);
+    else eval_group<EVAL_G, false>(P, g, chunk, lane);
 
     // fused fixed-order reduction: the last block of this column of the grid to finish adds the
-    // chunks' partial sums in chunk order (deterministic whichever block happens to be last)
+    // chunks' partial sums in chunk order (deterministic whichever block happens to be last) and
+    // scatters them to the caller's proposal order
     __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -558,8 +624,8 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_c
         if (s_last) P.counters[blockIdx.y] = 0;     // ready for the next launch
     }
     __syncthreads();
-    if (s_last && threadIdx.x < EVAL_WARPS * EVAL_G) {
-        const int gi2 = blockIdx.y * EVAL_WARPS + threadIdx.x / EVAL_G, j = threadIdx.x % EVAL_G;
+    if (s_last && threadIdx.x < EVAL_WARPS * EVAL_GS) {
+        const int gi2 = blockIdx.y * EVAL_WARPS + threadIdx.x / EVAL_GS, j = threadIdx.x % EVAL_GS;
         if (gi2 < P.n_groups) {
             const EvalGroup g2 = P.groups[gi2];
             if (j < g2.n) {
@@ -567,7 +633,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_c
                 double sum = 0.0;
 #pragma unroll 8
                 for (int c = 0; c < (int)gridDim.x; c++) sum += __ldcg(src + (size_t)c * P.n_props);
-                P.out[g2.begin + j] = sum;
+                P.out[P.props[g2.begin + j].out] = sum;
             }
         }
     }

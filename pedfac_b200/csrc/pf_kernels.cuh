@@ -165,11 +165,15 @@ __host__ __device__ inline SweepSmem sweep_smem_layout(const SweepGroup &g, int 
 //   SELFING: v = sum_gk kid[gk] sum_g T[gk][g][g] xp[g]         (_CalculateLikeByStubsSelfing@0x10001f7ab)
 //   PRONG:   v = sum_g prong[g] kid[g]                          (_CalculateLikeByProngs@0x10001fb44)
 // partial[chunk][proposal] = log of the product of v over the chunk's loci.
-constexpr int EVAL_G = 4;
+constexpr int EVAL_G = 4;        // general proposals per warp
+#ifndef PF_EVAL_GS
+#define PF_EVAL_GS 4
+#endif
+constexpr int EVAL_GS = PF_EVAL_GS;   // single-parent proposals per warp (one row and three FMAs each, two loci per lane)
 constexpr int EVAL_WARPS = 4;
 
-struct EvalProp { int kind; int row_p; int row_m; int pad; };
-struct EvalGroup { int kid_row; int begin; int n; int pad; };
+struct EvalProp { int kind; int row_p; int row_m; int out; };    // out: index of the proposal in the caller's list
+struct EvalGroup { int kid_row; int begin; int n; int single; };
 
 struct EvalParams {
     DevView D;
