@@ -36,9 +36,12 @@
 #include <ctime>
 #include <string>
 #include <sys/stat.h>
+#include <sys/mman.h>
 #include <sys/wait.h>
+#include <ucontext.h>
 #include <unistd.h>
 #include <vector>
+#include <cstdarg>
 
 #define PF_CAT2(a, b) a##b
 #define PF_CAT(a, b) PF_CAT2(a, b)
@@ -51,6 +54,19 @@
 // ranlib subset (netlib ranlib.c, Brown & Lovato; L'Ecuyer-Cote combined generator). Only
 // generator 1 is ever current, so setall() reduces to loading the two seeds
 // (_setall@0x10002a2d8, _ignlgi@0x100029fa3, _ranf@0x10002b838, _genunf@0x10002e948, _genbet@0x10002accf).
+// stdout of the chains other than chain 0 (PEDFAC_CHAINS) is dropped: one program, one progress log
+static bool g_quiet = false;
+static int out_printf(const char *fmt, ...)
+{
+    if (g_quiet) return 0;
+    va_list ap;
+    va_start(ap, fmt);
+    const int n = vprintf(fmt, ap);
+    va_end(ap);
+    return n;
+}
+#define printf out_printf
+
 namespace rng {
 static long s1 = 1234567890L, s2 = 123456789L;
 static const long m1 = 2147483563L, m2 = 2147483399L, a1 = 40014L, a2 = 40692L;
@@ -197,6 +213,7 @@ struct Ped {
     // candidate lists by sex (0 unknown, 1 male, 2 female)
     std::vector<std::pair<int, double>> cand[3];
     PF_ENGINE_T *eng = nullptr;
+    int chain = 0;                                   // row block of this chain inside the engine (PEDFAC_CHAINS)
     FILE *fNode = nullptr, *fEdge = nullptr, *fPed = nullptr, *fGeno = nullptr, *fLL = nullptr;
     long n_proposals = 0, n_sweeps = 0, n_steps = 0, n_swaps = 0, n_swaps_picked = 0;
     bool underflow_warned = false; long underflow_steps = 0;
@@ -517,6 +534,59 @@ static void store_sweep(Ped &p, const ViewBuf &b, const std::vector<double> &ll)
     p.nDirty = 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Several chains in one process (PEDFAC_CHAINS=C; BASELINE.json's last configuration: independent
+// chains batched per GPU). Every chain is the unchanged single-chain sampler running on its own fiber
+// (ucontext) with its own Ped, RNG stream (seeds + c) and output directory; the only thing they share
+// is the engine, whose n_chains row blocks they own one each. The likelihood calls below do not go to
+// the engine directly: a fiber posts its request and yields, and when every live chain has posted,
+// the scheduler submits the requests of a kind as ONE pf_sweep_batch / pf_eval_batch — one launch
+// serves all chains — and hands the results back. A chain therefore computes exactly what it would
+// compute alone: chain c's trace is the single-chain trace for the seeds (a + c, b + c).
+namespace mc {
+enum Kind { NONE = 0, SWEEP, EVAL, SWEEP_EVAL, SWAPS };
+struct Req { Kind kind = NONE; const pf_graph_view *view = nullptr; double *ll = nullptr; int kid = -1, n = 0;
+             const pf_proposal *props = nullptr; double *lsum = nullptr; const pf_swap *swaps = nullptr; int rc = 0; };
+struct Fiber { ucontext_t ctx; void *stack = nullptr; Req req; bool done = false; long s1 = 0, s2 = 0; int chain = 0; };
+static bool active = false;
+static int current = -1;
+static std::vector<Fiber> fibers;
+static ucontext_t sched_ctx;
+
+static int post(const Req &r)
+{
+    Fiber &f = fibers[current];
+    f.req = r;
+    swapcontext(&f.ctx, &sched_ctx);             // back in the scheduler; resumed when the result is in
+    return f.req.rc;
+}
+} // namespace mc
+
+static int eng_sweep(Ped &p, const pf_graph_view *v, double *ll)
+{
+    if (!mc::active) return PFN(sweep)(p.eng, p.chain, v, ll);
+    mc::Req r; r.kind = mc::SWEEP; r.view = v; r.ll = ll;
+    return mc::post(r);
+}
+static int eng_eval(Ped &p, int kid, int n, const pf_proposal *props, double *lsum)
+{
+    if (!mc::active) return PFN(eval)(p.eng, p.chain, kid, n, props, lsum);
+    mc::Req r; r.kind = mc::EVAL; r.kid = kid; r.n = n; r.props = props; r.lsum = lsum;
+    return mc::post(r);
+}
+static int eng_sweep_eval(Ped &p, const pf_graph_view *v, double *ll, int kid, int n, const pf_proposal *props, double *lsum)
+{
+    if (!mc::active) return PFN(sweep_eval)(p.eng, p.chain, v, ll, kid, n, props, lsum);
+    mc::Req r; r.kind = mc::SWEEP_EVAL; r.view = v; r.ll = ll; r.kid = kid; r.n = n; r.props = props; r.lsum = lsum;
+    return mc::post(r);
+}
+static int eng_eval_swaps(Ped &p, const pf_graph_view *v, int n, const pf_swap *sw, double *lsum)
+{
+    if (!mc::active) return PFN(eval_swaps)(p.eng, p.chain, v, n, sw, lsum);
+    mc::Req r; r.kind = mc::SWAPS; r.view = v; r.n = n; r.swaps = sw; r.lsum = lsum;
+    return mc::post(r);
+}
+
 static void Propagating_msg(Ped &p)
 {
     if (p.nDirty == 0) return;     // the reference re-propagates everything; nothing would change
@@ -525,7 +595,7 @@ static void Propagating_msg(Ped &p)
     dirty_view(p, b);
     std::vector<double> ll(b.labels.size() + 1);
     const double t1 = now_s();
-    if (PFN(sweep)(p.eng, 0, &b.v, ll.data()) != PF_OK) die("sweep failed");
+    if (eng_sweep(p, &b.v, ll.data()) != PF_OK) die("sweep failed");
     p.t_view += t1 - t0; p.t_sweep += now_s() - t1;
     store_sweep(p, b, ll);
 }
@@ -555,7 +625,7 @@ static void flush(Ped &p, int kid, Batch &b)
     if (b.props.empty()) return;
     std::vector<double> lsum(b.props.size());
     const double t0 = now_s();
-    if (PFN(eval)(p.eng, 0, kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("eval failed");
+    if (eng_eval(p, kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("eval failed");
     p.t_eval += now_s() - t0;
     p.n_proposals += (long)b.props.size();
     for (size_t k = 0; k < b.props.size(); k++) p.chll[b.slot[k]] = compose(p, kid, b.props[k], lsum[k]);
@@ -572,7 +642,7 @@ static void sweep_and_flush(Ped &p, int kid, Batch &b)
     dirty_view(p, vb);
     std::vector<double> ll(vb.labels.size() + 1), lsum(b.props.size() + 1);
     const double t1 = now_s();
-    if (PFN(sweep_eval)(p.eng, 0, &vb.v, ll.data(), kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("sweep_eval failed");
+    if (eng_sweep_eval(p, &vb.v, ll.data(), kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("sweep_eval failed");
     p.t_view += t1 - t0; p.t_sweep += now_s() - t1;
     store_sweep(p, vb, ll);
     p.n_proposals += (long)b.props.size();
@@ -682,7 +752,7 @@ static void ProposeSwaps(Ped &p, int x, bool redPa, bool redMa)
     build_view(p, want, b);
     std::vector<double> lsum(sw.size());
     const double t1 = now_s();
-    if (PFN(eval_swaps)(p.eng, 0, &b.v, (int)sw.size(), sw.data(), lsum.data()) != PF_OK) die("eval_swaps failed");
+    if (eng_eval_swaps(p, &b.v, (int)sw.size(), sw.data(), lsum.data()) != PF_OK) die("eval_swaps failed");
     p.t_view += t1 - t0; p.t_eval += now_s() - t1;
     p.n_proposals += (long)sw.size(); p.n_swaps += (long)sw.size();
     const int cp = p.cc[P], cq = p.cc[Q];
@@ -1159,6 +1229,7 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
 // inside its own kernels (pf_comm_*), so every process sees the same log-likelihoods and makes the
 // same moves. Rank 0 writes the output files and stdout; the others write under out/.shard<r>/.
 static int g_shard_rank = 0, g_shard_world = 1;
+static int g_n_chains = 1;               // PEDFAC_CHAINS: independent chains batched on this GPU
 static std::string g_shard_dir;          // where the ranks exchange their mailbox handles
 
 #ifndef PF_NO_COMM
@@ -1336,7 +1407,7 @@ static void ReadGeno(Ped &p, const std::string &path)
 
     pf_config cfg{};
     cfg.n_loci = p.S; cfg.locus_begin = 0; cfg.locus_end = p.S; cfg.cap_indiv = p.capIndiv; cfg.cap_marr = p.capMarr;
-    cfg.n_chains = 1; cfg.device = getenv("PEDFAC_DEVICE") ? atoi(getenv("PEDFAC_DEVICE")) : 0;
+    cfg.n_chains = g_n_chains; cfg.device = getenv("PEDFAC_DEVICE") ? atoi(getenv("PEDFAC_DEVICE")) : 0;
     if (g_shard_world > 1) {                                  // this process owns one slice of the loci (see main)
         cfg.locus_begin = (int)((long long)p.S * g_shard_rank / g_shard_world);
         cfg.locus_end = (int)((long long)p.S * (g_shard_rank + 1) / g_shard_world);
@@ -1524,7 +1595,7 @@ static void RefineParentOffPair(Ped &p)
                 for (size_t k = 0; k < ks.size(); k++) role[k] = p.indiv[ks[k]].sex == 1 ? 1 : 0;
                 std::vector<int> slot(ks.size() * K);
                 std::vector<double> score(ks.size() * K);
-                if (PFN(prefilter)(p.eng, 0, (int)ks.size(), ks.data(), role.data(), (int)cands.size(), cands.data(),
+                if (PFN(prefilter)(p.eng, p.chain, (int)ks.size(), ks.data(), role.data(), (int)cands.size(), cands.data(),
                                    bs.data(), K, slot.data(), score.data()) != PF_OK) die("prefilter failed");
                 for (size_t k = 0; k < ks.size(); k++) {
                     auto &pc = p.parentCand[ks[k]];
@@ -1577,6 +1648,194 @@ static Opts GetCommLineOpts(int argc, char **argv)
     return o;
 }
 
+static void SampleLoop(Ped &p, const Opts &o)
+{
+    printf("sample for %d iterations: -- \n", o.nIter);
+    // measurement aids (not part of the reference contract): PEDFAC_STATS=1 prints per-iteration
+    // counters and wall time to stderr; PEDFAC_MAX_STEPS=K stops after K Gibbs steps in total
+    const bool stats = getenv("PEDFAC_STATS") != nullptr;
+    p.check = getenv("PEDFAC_CHECK") != nullptr;             // PEDFAC_CHECK=1: re-propagate after every move and compare with its score
+    const long max_steps = getenv("PEDFAC_MAX_STEPS") ? atol(getenv("PEDFAC_MAX_STEPS")) : -1;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    for (p.iter = 0; p.iter < o.nIter; p.iter++) {             // _main@0x10001a812-0x10001aaea
+        const double t_iter = now();
+        const long props0 = p.n_proposals, sweeps0 = p.n_sweeps, steps0 = p.n_steps, swaps0 = p.n_swaps, picked0 = p.n_swaps_picked;
+        uint64_t io0[2] = {0, 0};
+        PFN(io_bytes)(p.eng, &io0[0], &io0[1]);
+        p.unobsQueue.clear();
+        int qBeg = 0, qEnd = -1;
+        for (int k = 0; k < p.nObs; k++) {
+            const int id = p.observedSorted[k];
+            if (max_steps >= 0 && p.n_steps >= max_steps) break;
+            MCMC_sampling(p, o, id);
+            const bool last = k == p.nObs - 1;
+            if (!last && !(p.indiv[id].gen < p.indiv[p.observedSorted[k + 1]].gen)) continue;
+            const int gap = last ? p.nGen - p.indiv[id].gen : p.indiv[p.observedSorted[k + 1]].gen - p.indiv[id].gen;
+            for (int g = 1; g <= gap; g++) {
+                if (getenv("PEDFAC_DEBUG_CALLS")) fprintf(stderr, "pass g %d of %d window %d..%d queue %zu\n", g, gap, qBeg, qEnd, p.unobsQueue.size());
+                for (int q = qBeg; q < qEnd + 1; q++) {
+                    const int u = p.unobsQueue[q];
+                    if (!p.indiv[u].queued) continue;
+                    MCMC_sampling(p, o, u);
+                    p.indiv[u].queued = false;
+                }
+                if ((int)p.unobsQueue.size() - qEnd > 1) { qBeg = qEnd + 1; qEnd = (int)p.unobsQueue.size() - 1; }
+            }
+        }
+        printf("..%i\n", p.iter);
+        fflush(stdout);
+        if (stats)
+        {
+            uint64_t h2d = 0, d2h = 0;
+            PFN(io_bytes)(p.eng, &h2d, &d2h);
+            fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld swaps %ld swaps_picked %ld seconds %.6f h2d_bytes %llu d2h_bytes %llu chain %d\n", p.iter,
+                    p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, p.n_swaps - swaps0, p.n_swaps_picked - picked0, now() - t_iter,
+                    (unsigned long long)(h2d - io0[0]), (unsigned long long)(d2h - io0[1]), p.chain);
+            if (p.chain == 0) fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view);
+            p.t_sweep = p.t_eval = p.t_view = 0;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// PEDFAC_CHAINS: the scheduler of the chain fibers (see namespace mc above)
+#ifndef PF_NO_COMM
+static std::vector<Ped> *g_peds = nullptr;
+static const Opts *g_opts = nullptr;
+
+static void fiber_entry(int c)
+{
+    SampleLoop((*g_peds)[c], *g_opts);
+    mc::fibers[c].done = true;
+    mc::fibers[c].req.kind = mc::NONE;
+    swapcontext(&mc::fibers[c].ctx, &mc::sched_ctx);
+}
+
+static bool open_outputs(Ped &p, const std::string &out)
+{
+    mkdir(out.c_str(), 0777);
+    p.fEdge = fopen((out + "/historyEdge.csv").c_str(), "w");
+    p.fNode = fopen((out + "/historyNode.csv").c_str(), "w");
+    p.fPed = fopen((out + "/ped.txt").c_str(), "w");
+    p.fGeno = fopen((out + "/geno.txt").c_str(), "w");
+    p.fLL = fopen((out + "/ll.txt").c_str(), "w");
+    return p.fEdge && p.fNode && p.fPed && p.fGeno && p.fLL;
+}
+
+static void copy_file_so_far(FILE *from, const std::string &path_from, FILE *to)
+{
+    fflush(from);
+    if (FILE *f = fopen(path_from.c_str(), "r")) {
+        char buf[1 << 16];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, f)) > 0) fwrite(buf, 1, n, to);
+        fclose(f);
+    }
+}
+
+// Runs C chains to the end. `p0` is chain 0, set up to the point where sampling starts (files read,
+// initial sweep and prefilter done); the other chains start as copies of it with their own row block in
+// the engine (everything dirty, so their first Gibbs step propagates it), RNG stream and output files
+// under out/chain<c>/.
+static void RunChains(Ped &p0, const Opts &o, long seed_a, long seed_b)
+{
+    const int C = g_n_chains;
+    std::vector<Ped> peds(C);
+    peds[0] = p0;
+    const std::string out0 = o.dir + "/out";
+    for (int c = 1; c < C; c++) {
+        peds[c] = p0;
+        Ped &q = peds[c];
+        q.chain = c;
+        if (!open_outputs(q, out0 + "/chain" + std::to_string(c))) { fprintf(stderr, "cannot open output files of chain %d\n", c); exit(-1); }
+        copy_file_so_far(p0.fNode, out0 + "/historyNode.csv", q.fNode);
+        copy_file_so_far(p0.fEdge, out0 + "/historyEdge.csv", q.fEdge);
+        for (int k = 0; k < q.nCC; k++) mark_dirty(q, k);
+    }
+    g_peds = &peds; g_opts = &o;
+    mc::fibers.resize(C);
+    const size_t stack_bytes = (size_t)16 << 20;
+    for (int c = 0; c < C; c++) {
+        mc::Fiber &f = mc::fibers[c];
+        f.chain = c;
+        f.stack = mmap(nullptr, stack_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+        if (f.stack == MAP_FAILED) { perror("mmap"); exit(-1); }
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = &mc::sched_ctx;
+        makecontext(&f.ctx, (void (*)())fiber_entry, 1, c);
+        rng::setall(seed_a + c, seed_b + c);
+        f.s1 = rng::s1; f.s2 = rng::s2;
+    }
+    mc::active = true;
+    std::vector<int> idx, chains, kids, pb;
+    std::vector<pf_graph_view> views;
+    std::vector<pf_proposal> props;
+    std::vector<double> ll, lsum;
+    for (;;) {
+        int alive = 0;
+        for (int c = 0; c < C; c++) {
+            mc::Fiber &f = mc::fibers[c];
+            if (f.done) continue;
+            mc::current = c; g_quiet = c != 0;
+            rng::s1 = f.s1; rng::s2 = f.s2;
+            swapcontext(&mc::sched_ctx, &f.ctx);
+            f.s1 = rng::s1; f.s2 = rng::s2;
+            if (!f.done) alive++;
+        }
+        g_quiet = false;
+        if (alive == 0) break;
+        // the sweeps of this round (SWEEP and the sweep half of SWEEP_EVAL) as one batch
+        idx.clear(); chains.clear(); views.clear();
+        size_t n_ll = 0;
+        for (int c = 0; c < C; c++) {
+            mc::Req &r = mc::fibers[c].req;
+            if (mc::fibers[c].done || (r.kind != mc::SWEEP && r.kind != mc::SWEEP_EVAL)) continue;
+            idx.push_back(c); chains.push_back(c); views.push_back(*r.view); n_ll += (size_t)std::max(r.view->n_cc, 0);
+        }
+        if (!idx.empty()) {
+            ll.assign(n_ll + 1, 0.0);
+            const int rc = PFN(sweep_batch)(p0.eng, (int)idx.size(), chains.data(), views.data(), ll.data());
+            size_t at = 0;
+            for (int c : idx) {
+                mc::Req &r = mc::fibers[c].req;
+                r.rc = rc;
+                for (int j = 0; j < r.view->n_cc; j++) r.ll[j] = ll[at + j];
+                at += (size_t)std::max(r.view->n_cc, 0);
+            }
+        }
+        // the proposal lists of this round (EVAL and the eval half of SWEEP_EVAL) as one batch
+        idx.clear(); chains.clear(); kids.clear(); pb.assign(1, 0); props.clear();
+        for (int c = 0; c < C; c++) {
+            mc::Req &r = mc::fibers[c].req;
+            if (mc::fibers[c].done || (r.kind != mc::EVAL && r.kind != mc::SWEEP_EVAL) || r.n <= 0) continue;
+            idx.push_back(c); chains.push_back(c); kids.push_back(r.kid);
+            props.insert(props.end(), r.props, r.props + r.n);
+            pb.push_back((int)props.size());
+        }
+        if (!idx.empty()) {
+            lsum.assign(props.size() + 1, 0.0);
+            const int rc = PFN(eval_batch)(p0.eng, (int)idx.size(), chains.data(), kids.data(), pb.data(), props.data(), lsum.data());
+            for (size_t k = 0; k < idx.size(); k++) {
+                mc::Req &r = mc::fibers[idx[k]].req;
+                if (rc != PF_OK) r.rc = rc;
+                for (int j = 0; j < r.n; j++) r.lsum[j] = lsum[(size_t)pb[k] + j];
+            }
+        }
+        // swap proposals (a few per cent of the steps): per chain
+        for (int c = 0; c < C; c++) {
+            mc::Req &r = mc::fibers[c].req;
+            if (mc::fibers[c].done || r.kind != mc::SWAPS) continue;
+            r.rc = PFN(eval_swaps)(p0.eng, c, r.view, r.n, r.swaps, r.lsum);
+        }
+        for (int c = 0; c < C; c++)
+            if (!mc::fibers[c].done && mc::fibers[c].req.kind == mc::EVAL && mc::fibers[c].req.n <= 0) mc::fibers[c].req.rc = PF_OK;
+    }
+    mc::active = false;
+    for (int c = 1; c < C; c++) { Ped &q = peds[c]; fclose(q.fEdge); fclose(q.fNode); fclose(q.fPed); fclose(q.fGeno); fclose(q.fLL); }
+    p0 = peds[0];
+}
+#endif
+
 int main(int argc, char **argv)
 {
     Opts o = GetCommLineOpts(argc, argv);
@@ -1611,9 +1870,11 @@ int main(int argc, char **argv)
         for (int r = 0; r < n; r++) unlink((o.dir + "/out/.pf_comm_" + nonce + "_" + std::to_string(r)).c_str());
         return rc;
     }
+    if (getenv("PEDFAC_CHAINS") && atoi(getenv("PEDFAC_CHAINS")) > 1) g_n_chains = atoi(getenv("PEDFAC_CHAINS"));
     g_shard_dir = o.dir + "/out";
     if (g_shard_rank > 0 && !freopen("/dev/null", "w", stdout)) return -1;
     Ped p;
+    long seed_a = 0, seed_b = 0;
     {   // _SeedFromFile@0x100027070
         long a = 0, b = 0;
         FILE *f = fopen(o.seedfile.c_str(), "r");
@@ -1626,6 +1887,7 @@ int main(int argc, char **argv)
             fclose(f);
         }
         rng::setall(a, b);
+        seed_a = a; seed_b = b;
     }
     {   // _PrepOutFiles@0x10001a3a0
         std::string out = o.dir + "/out";
@@ -1666,51 +1928,13 @@ int main(int argc, char **argv)
     p.observedSorted.resize(p.nObs);
     for (int i = 0; i < p.nObs; i++) p.observedSorted[i] = i;
     std::stable_sort(p.observedSorted.begin(), p.observedSorted.end(), [&](int a, int b) { return p.indiv[a].gen < p.indiv[b].gen; });   // qsort(_CompareGen)
-    printf("sample for %d iterations: -- \n", o.nIter);
-    // measurement aids (not part of the reference contract): PEDFAC_STATS=1 prints per-iteration
-    // counters and wall time to stderr; PEDFAC_MAX_STEPS=K stops after K Gibbs steps in total
-    const bool stats = getenv("PEDFAC_STATS") != nullptr;
-    p.check = getenv("PEDFAC_CHECK") != nullptr;             // PEDFAC_CHECK=1: re-propagate after every move and compare with its score
-    const long max_steps = getenv("PEDFAC_MAX_STEPS") ? atol(getenv("PEDFAC_MAX_STEPS")) : -1;
-    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
-    for (p.iter = 0; p.iter < o.nIter; p.iter++) {             // _main@0x10001a812-0x10001aaea
-        const double t_iter = now();
-        const long props0 = p.n_proposals, sweeps0 = p.n_sweeps, steps0 = p.n_steps, swaps0 = p.n_swaps, picked0 = p.n_swaps_picked;
-        uint64_t io0[2] = {0, 0};
-        PFN(io_bytes)(p.eng, &io0[0], &io0[1]);
-        p.unobsQueue.clear();
-        int qBeg = 0, qEnd = -1;
-        for (int k = 0; k < p.nObs; k++) {
-            const int id = p.observedSorted[k];
-            if (max_steps >= 0 && p.n_steps >= max_steps) break;
-            MCMC_sampling(p, o, id);
-            const bool last = k == p.nObs - 1;
-            if (!last && !(p.indiv[id].gen < p.indiv[p.observedSorted[k + 1]].gen)) continue;
-            const int gap = last ? p.nGen - p.indiv[id].gen : p.indiv[p.observedSorted[k + 1]].gen - p.indiv[id].gen;
-            for (int g = 1; g <= gap; g++) {
-                if (getenv("PEDFAC_DEBUG_CALLS")) fprintf(stderr, "pass g %d of %d window %d..%d queue %zu\n", g, gap, qBeg, qEnd, p.unobsQueue.size());
-                for (int q = qBeg; q < qEnd + 1; q++) {
-                    const int u = p.unobsQueue[q];
-                    if (!p.indiv[u].queued) continue;
-                    MCMC_sampling(p, o, u);
-                    p.indiv[u].queued = false;
-                }
-                if ((int)p.unobsQueue.size() - qEnd > 1) { qBeg = qEnd + 1; qEnd = (int)p.unobsQueue.size() - 1; }
-            }
-        }
-        printf("..%i\n", p.iter);
-        fflush(stdout);
-        if (stats)
-        {
-            uint64_t h2d = 0, d2h = 0;
-            PFN(io_bytes)(p.eng, &h2d, &d2h);
-            fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld swaps %ld swaps_picked %ld seconds %.6f h2d_bytes %llu d2h_bytes %llu\n", p.iter,
-                    p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, p.n_swaps - swaps0, p.n_swaps_picked - picked0, now() - t_iter,
-                    (unsigned long long)(h2d - io0[0]), (unsigned long long)(d2h - io0[1]));
-            fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view);
-            p.t_sweep = p.t_eval = p.t_view = 0;
-        }
-    }
+#ifndef PF_NO_COMM
+    if (g_n_chains > 1) RunChains(p, o, seed_a, seed_b);
+    else
+#else
+    if (g_n_chains > 1) { fprintf(stderr, "PEDFAC_CHAINS needs the CUDA build (batched engine calls)\n"); return -1; }
+#endif
+    SampleLoop(p, o);
     printf(".. DONE \n");
     fclose(p.fEdge); fclose(p.fNode); fclose(p.fPed); fclose(p.fGeno); fclose(p.fLL);
     PFN(destroy)(p.eng);

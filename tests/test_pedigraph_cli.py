@@ -261,3 +261,28 @@ def test_choice_survives_the_same_steps_trimming(tmp_path, case):
     frontend.write_run_dir(d, rd, seeds=seeds, max_unobs=unobs, max_age=2.0, observe_frac=ofrac)
     r = run(REF, rd, n_iter=iters, extra=("-s",), env={"PEDFAC_CHECK": "1", "PEDFAC_STATS": "1"})
     assert r.returncode == 0, r.stderr[-800:]
+
+
+@pytest.mark.gpu
+def test_gpu_chains_batched_in_one_process_equal_single_chain_runs(tmp_path):
+    """PEDFAC_CHAINS=C (BASELINE.json's last configuration at test size): C chains on one GPU, their
+    likelihood calls batched into one launch per round. Chain c must sample exactly what a
+    single-chain run samples with the seeds (a + c, b + c); chain 0 keeps the unchanged file layout."""
+    import os
+    C = 4
+    d = synth.simulate(160, 120, soft=True, seed=46)
+    rd = tmp_path / "multi"
+    frontend.write_run_dir(d, rd, seeds=(2590, 7579545))
+    r = run(GPU, rd, n_iter=3, env={"PEDFAC_CHAINS": str(C), "PEDFAC_STATS": "1"})
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert r.stdout.count(".. DONE") == 1 and "..2" in r.stdout          # one progress log: chain 0's
+    assert sum(1 for l in r.stderr.splitlines() if l.startswith("pedigraph-stats")) == 3 * C
+    for c in range(C):
+        one = tmp_path / f"single{c}"
+        frontend.write_run_dir(d, one, seeds=(2590 + c, 7579545 + c))
+        r1 = run(GPU, one, n_iter=3)
+        assert r1.returncode == 0, r1.stderr[-1500:]
+        got = rd / "out" if c == 0 else rd / "out" / f"chain{c}"
+        for name in ("ped.txt", "ll.txt", "historyNode.csv", "historyEdge.csv"):
+            assert (got / name).read_text() == (one / "out" / name).read_text(), (c, name)
+    assert (rd / "out" / "ped.txt").read_text() != (rd / "out" / "chain1" / "ped.txt").read_text()
