@@ -288,34 +288,49 @@ def parse_stats(stderr):
             kv = dict(zip(t[1::2], t[2::2]))
             out.append({"iter": int(kv["iter"]), "steps": int(kv["steps"]), "proposals": int(kv["proposals"]), "sweeps": int(kv["sweeps"]),
                         "swaps": int(kv.get("swaps", 0)), "swaps_picked": int(kv.get("swaps_picked", 0)), "seconds": float(kv["seconds"]),
-                        "h2d_bytes": int(kv.get("h2d_bytes", 0)), "d2h_bytes": int(kv.get("d2h_bytes", 0))})
+                        "h2d_bytes": int(kv.get("h2d_bytes", 0)), "d2h_bytes": int(kv.get("d2h_bytes", 0)), "chain": int(kv.get("chain", 0))})
     return out
 
 
-def run_chain(data, S, device):
+def run_chain(data, S, device, chains=1):
     """BASELINE.md's definition of the metric: one full MCMC iteration (every observed individual
     gets a Gibbs step, plus the unobserved parents it creates) timed after one warm-up iteration
-    from the all-singletons start, through the unchanged CLI + file contract."""
+    from the all-singletons start, through the unchanged CLI + file contract. chains > 1: that many
+    independent chains in the one process (PEDFAC_CHAINS), batched per round; proposals are summed
+    over the chains, the time is the wall time of the iteration (the chains run in lock step)."""
     import tempfile
     from pedfac_b200 import frontend
+    n_iter = 3 if chains == 1 else 2
     with tempfile.TemporaryDirectory() as tmp:
         rd = Path(tmp) / "run"
         frontend.write_run_dir(data, rd)
         env = dict(os.environ, PEDFAC_STATS="1", PEDFAC_DEVICE=str(device))
+        if chains > 1:
+            env["PEDFAC_CHAINS"] = str(chains)
         t0 = time.perf_counter()
-        r = subprocess.run([str(ROOT / "pedfac_b200" / "bin" / "pedigraph"), "-d", str(rd), "-n", "3", "-r", str(rd / "rand")],
+        r = subprocess.run([str(ROOT / "pedfac_b200" / "bin" / "pedigraph"), "-d", str(rd), "-n", str(n_iter), "-r", str(rd / "rand")],
                            capture_output=True, text=True, env=env)
         wall = time.perf_counter() - t0
         if r.returncode != 0:
             return {"error": r.stderr[-300:]}
-        st = parse_stats(r.stderr)
+        allst = parse_stats(r.stderr)
+        st = []
+        for it in sorted({x["iter"] for x in allst}):
+            rows = [x for x in allst if x["iter"] == it]
+            agg = dict(rows[0])
+            for k in ("steps", "proposals", "sweeps", "swaps", "swaps_picked"):
+                agg[k] = sum(x[k] for x in rows)
+            agg["seconds"] = max(x["seconds"] for x in rows)
+            agg["chains"] = len(rows)
+            st.append(agg)
         it = min(st[1:], key=lambda x: x["seconds"] / max(x["proposals"], 1))
-        return {"what": "pedigraph -n 3 via CLI + files; iteration 1 = warm-up from all singletons, the faster of iterations 2 and 3 reported (both listed in timed_iterations)",
-                "timed_iterations": st[1:], "swap_proposals": it["swaps"], "swaps_picked": it["swaps_picked"],
+        return {"what": f"pedigraph -n {n_iter} via CLI + files" + (f", {chains} chains in one process (PEDFAC_CHAINS)" if chains > 1 else "") +
+                        "; iteration 1 = warm-up from all singletons, the fastest later iteration reported (all listed in timed_iterations)",
+                "timed_iterations": st[1:], "swap_proposals": it["swaps"], "swaps_picked": it["swaps_picked"], "chains": chains,
                 "gibbs_steps": it["steps"], "proposals": it["proposals"], "sweeps": it["sweeps"], "seconds": it["seconds"],
                 "proposals_per_sec": it["proposals"] / it["seconds"], "gibbs_steps_per_sec": it["steps"] / it["seconds"],
                 "trio_evals_per_sec": it["proposals"] * S / it["seconds"], "first_iteration": st[0],
-                "h2d_bytes_per_gibbs_step": it["h2d_bytes"] / max(it["steps"], 1), "d2h_bytes_per_gibbs_step": it["d2h_bytes"] / max(it["steps"], 1),
+                "h2d_bytes_per_gibbs_step": it["h2d_bytes"] / max(it["steps"], 1) * (chains if chains > 1 else 1), "d2h_bytes_per_gibbs_step": it["d2h_bytes"] / max(it["steps"], 1) * (chains if chains > 1 else 1),
                 "process_wall_seconds": wall}
 
 
@@ -576,9 +591,9 @@ def main():
         # step through the host-buffer C ABI) — BASELINE.md's timing window. Where that cannot run
         # (sharded / batched workloads) e2e is the trace replay through the host-buffer C ABI.
         out["e2e"] = dict(out["replay_e2e"])
-        if world == 1 and chains == 1 and not args.no_chain and wl in ("A", "B"):
+        if world == 1 and not args.no_chain and wl in ("A", "B", "D"):
             full = data if R["shard"] == (0, S) else synth.simulate(n_ind, S, soft=soft, seed=46)
-            ch = run_chain(full, S, local_rank)
+            ch = run_chain(full, S, local_rank, chains=chains)
             out["chain"] = ch
             if "error" not in ch:
                 out["e2e"] = {"value": ch["proposals_per_sec"], "unit": unit, "h2d_bytes_per_step": ch["h2d_bytes_per_gibbs_step"],

@@ -496,7 +496,16 @@ struct Plan2 {
     void reset() { tasks.clear(); pool.clear(); emis.clear(); stage.clear(); groups.clear(); target_tasks_per_group = 1 << 30; fits = true; format = 0; }
     void begin_component()
     {
-        if (groups.empty() || groups.back().task_end >= target_tasks_per_group) {
+        // a group is one block's shared memory: whole components are appended to the open group until it
+        // has reached its share of the tasks, or a quarter of the shared memory (the largest component
+        // that fits at all needs about three quarters: it must still fit behind what is there)
+        bool open_new = groups.empty() || groups.back().task_end >= target_tasks_per_group;
+        if (!open_new) {
+            Sweep2Group g = groups.back();
+            g.task_begin = 0; g.pool_len = (int)pool.size() - g.pool_begin;
+            open_new = sweep2_smem_layout(g, 64).total > SWEEP2_SMEM_MAX / 4;
+        }
+        if (open_new) {
             Sweep2Group g{};
             g.pool_begin = (int)pool.size();
             g.emis_begin = (int)emis.size();
