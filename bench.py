@@ -180,14 +180,14 @@ def cpu_sample_loci(data, trace, budget_s, passes):
     return int(min(S, max(64, fit // 64 * 64)))
 
 
-def run_cpu_reference(data, trace, S_sample, budget_s, steps, warmup):
+def run_cpu_reference(data, trace, S_sample, budget_s, steps, warmup, opt="O2"):
     """Times the reference's own schedule — per Gibbs step: Propagating_msg over the dirty
     components, every proposal re-contracted over all loci, Propagating_msg again — on the first
     `S_sample` loci (cost is exactly linear in S) with the single thread the
     reference has. Returns proposals/s scaled to the full locus count, and a description."""
     from oracle.binding import OracleEngine
     S = data.n_loci
-    o = OracleEngine(S, trace.cap_i, trace.cap_m, locus_range=(0, S_sample))
+    o = OracleEngine(S, trace.cap_i, trace.cap_m, locus_range=(0, S_sample), opt=opt)
     synth.upload(o, data)
     o.sweep(trace.full_view)
 
@@ -217,7 +217,7 @@ def run_cpu_reference(data, trace, S_sample, budget_s, steps, warmup):
     dt = time.perf_counter() - t0
     value = tot_p / dt * (S_sample / S)
     sample = (f"{tot_s} Gibbs-step passes ({tot_p} proposals) of the same trace on the first {S_sample} of {S} loci, "
-              f"{dt:.1f} s, 1 thread, gcc -O2 oracle port; proposals/s scaled by {S_sample}/{S} (cost is linear in loci)")
+              f"{dt:.1f} s, 1 thread, gcc -{opt} oracle port; proposals/s scaled by {S_sample}/{S} (cost is linear in loci)")
     return value, dt / max(steps, 1) * 1e3, sample
 
 
@@ -228,7 +228,7 @@ MACHO = ROOT / "oracle" / "_ref" / "pedigraph_macho"
 REF_SAMPLE_INDIVIDUALS = 250
 
 
-def reference_sample(wl, tmp, also_gpu_device=None):
+def reference_sample(wl, tmp, also_gpu_device=None, all_cores=False):
     """The reference's own sampler on a bounded sample of workload `wl`: the same generator, seed,
     encoding and ALL loci, but REF_SAMPLE_INDIVIDUALS individuals (the binary needs ~25 s for them at
     config B; its start-up prefilter alone is quadratic in individuals), one MCMC iteration from the
@@ -262,6 +262,30 @@ def reference_sample(wl, tmp, also_gpu_device=None):
                       f"(same generator and seed; {n_ind} individuals would take the reference hours: its start-up prefilter is quadratic)"),
            "seconds": it["seconds"], "gibbs_steps": it["steps"], "proposals": it["proposals"], "process_wall_seconds": wall,
            "host_cores_available": cpu_count()}
+    if all_cores and use_ref:
+        # the best the CPU box could do: one independent chain of the reference per host core (different
+        # seeds, same sample), all at once
+        import shutil
+        n = cpu_count()
+        procs, t0 = [], time.perf_counter()
+        for c in range(n):
+            rc_dir = Path(tmp) / f"ref_sample_{c}"
+            shutil.copytree(rd, rc_dir, ignore=shutil.ignore_patterns("out"))
+            (rc_dir / "rand").write_text(f"{2590 + c} {7579545 + c} ")
+            procs.append(subprocess.Popen(["taskset", "-c", str(c), str(binary), "-d", str(rc_dir), "-n", "1", "-r", str(rc_dir / "rand")],
+                                          stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=env))
+        tot_p, worst = 0, 0.0
+        for pr in procs:
+            _, err = pr.communicate()
+            for line in err.splitlines():
+                if line.startswith("ref-stats"):
+                    kv = dict(zip(line.split()[1::2], line.split()[2::2]))
+                    tot_p += int(kv["proposals"]); worst = max(worst, float(kv["seconds"]))
+                    break
+        if worst > 0:
+            out["all_cores"] = {"cores": n, "value": tot_p / worst, "unit": "proposals/s",
+                                "what": f"{n} independent chains of the reference binary at once, one per host core (seeds 2590+c, 7579545+c): "
+                                        f"{tot_p} proposals in {worst:.1f} s (slowest chain), wall {time.perf_counter() - t0:.1f} s"}
     if also_gpu_device is not None:
         # the CUDA sampler on the very same run directory: same seed, so the same trace is required
         ref_ped = (rd / "out" / "ped.txt").read_text()
@@ -603,12 +627,15 @@ def main():
                               "trio_evals_per_sec": ch["trio_evals_per_sec"]}
         if world == 1 and not args.no_cpu_baseline:
             with tempfile.TemporaryDirectory() as tmp:
-                ref = reference_sample(wl, tmp, also_gpu_device=local_rank if chains == 1 else None)
+                ref = reference_sample(wl, tmp, also_gpu_device=local_rank if chains == 1 else None, all_cores=True)
             out["cpu_baseline"] = ref if "error" not in ref else None
             # the C port of the algorithm beside it (what round 1 used as the baseline): -O2 and -O0
             try:
                 v, _, sample = run_cpu_reference(data, trace, cpu_sample_loci(data, trace, args.cpu_budget, 1), args.cpu_budget, 1, 0)
                 out["cpu_port"] = {"value": v, "unit": unit, "cores": 1, "kind": "port", "sample": sample}
+                # the shipped reference binary is an -O0 build: the same port at -O0, on a 256-locus sample
+                v0, _, sample0 = run_cpu_reference(data, trace, min(S, 256), args.cpu_budget / 2, 1, 0, opt="O0")
+                out["cpu_port_O0"] = {"value": v0, "unit": unit, "cores": 1, "kind": "port", "sample": sample0}
             except Exception as ex:                     # reported, not swallowed
                 out["cpu_port"] = {"error": repr(ex)}
         else:

@@ -524,3 +524,56 @@ def test_gpu_config_d_scale_batch_equals_single_chain():
     slot = int(tr.steps[-1][1])
     assert (g.get_stub(slot, chain=n_chains - 1) == g.get_stub(slot, chain=0)).all()
     g.sweep_batch(chains, [tr.final_view] * n_chains)
+
+
+@pytest.mark.parametrize("fmt", ["hard", "dec16", "mixed"])
+def test_gpu_sweep2_general_records_match_oracle(fmt):
+    """The record shapes outside sweep2_kernel's common case, in each genotype format it is compiled
+    for: an individual with seven marriages (operands with more than three rows), sibships of 5, 9 and
+    14 kids (chunk pairs: KFOLD2 / KIDCHUNK2), a selfing marriage, kids with families of their own inside
+    a large sibship. Log-likelihoods, every stub and every prong against the oracle."""
+    rng = np.random.default_rng(5)
+    S, n = 70, 120
+    ped = Pedigree(n + 4, n)
+    g, o = Engine(S, n + 4, n), OracleEngine(S, n + 4, n)
+    eps, af = np.round(rng.uniform(0.005, 0.05, S), 3), np.round(rng.uniform(0.05, 0.5, S), 3)
+    for e in (g, o):
+        e.set_locus_params(eps, af)
+    for i in range(n):
+        ped.add_individual(i, founder=False)
+        kind = fmt if fmt != "mixed" else ["hard", "dec16", "f32", "none"][i % 4]
+        if rng.random() < 0.15:
+            continue                                        # unobserved
+        for e in (g, o):
+            if kind == "hard":
+                e.set_hard(i, np.random.default_rng(100 + i).integers(0, 4, S).astype(np.uint8))
+            elif kind == "dec16":
+                num = np.random.default_rng(100 + i).integers(0, 10001, (S, 3)).astype(np.uint16)
+                e.set_soft(i, num, "dec16", 10000)
+            elif kind == "f32":
+                e.set_soft(i, np.random.default_rng(100 + i).random((S, 3)).astype(np.float32), "f32")
+    nxt = iter(range(1, n))
+    take = lambda k: [next(nxt) for _ in range(k)]
+    m = 0
+    hub = 0                                                  # one father, seven wives
+    for k in (1, 2, 5, 1, 9, 3, 14):
+        wife = take(1)[0]
+        ped.add_marriage(m, hub, wife, take(k)); m += 1
+    # two kids of the 9-sibship get families of their own; one marriage is a selfing
+    kids9 = ped.marriages[4].kids
+    ped.add_marriage(m, kids9[6], take(1)[0], take(5)); m += 1
+    ped.add_marriage(m, take(1)[0], kids9[8], take(2)); m += 1
+    selfer = take(1)[0]
+    ped.add_marriage(m, selfer, selfer, take(3), selfing=True); m += 1
+    with_parents = {k for mm in ped.marriages.values() for k in mm.kids}
+    for i in range(n):
+        ped.founder[i] = ped.active[i] and i not in with_parents
+    view, _ = ped.view()
+    lg, lo = g.sweep(view), o.sweep(view)
+    np.testing.assert_allclose(lg, lo, rtol=1e-12, atol=1e-11)
+    for i in view.indiv:
+        np.testing.assert_allclose(g.get_stub(int(i)), o.get_stub(int(i)), rtol=1e-12, atol=1e-300)
+    for mm in view.marr:
+        np.testing.assert_allclose(g.get_prong(int(mm)), o.get_prong(int(mm)), rtol=1e-12, atol=1e-300)
+    st = g.plan_stats()
+    assert st["rows_smem"] == st["rows"]                    # planned by the second-generation builder, nothing spilled

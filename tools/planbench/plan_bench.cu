@@ -34,6 +34,21 @@ int main(int argc, char **argv)
         double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / vs.size();
         best = std::min(best, us);
     }
+    {   // the second-generation planner (emit2) on the same views
+        static Plan2 p2; static Plan dummy;
+        double best2 = 1e9;
+        for (int r = 0; r < reps; r++) {
+            auto t0 = std::chrono::steady_clock::now();
+            for (auto &x : vs) {
+                p2.reset(); p2.target_tasks_per_group = 256; p2.format = 2;
+                int max_up = 0;
+                int rc = plan_add_view(e, &x.v, 0, 0, dummy, max_up, false, SWEEP_LATENCY, nullptr, &p2);
+                if (rc) { printf("rc %d %s\n", rc, pf_last_error()); return 1; }
+            }
+            best2 = std::min(best2, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count() / vs.size());
+        }
+        printf("plan_add_view + emit2: %.1f us per view (best of %d), last plan: %zu tasks %zu pool words %zu groups\n", best2, reps, p2.tasks.size(), p2.pool.size(), p2.groups.size());
+    }
     e->host_prof = true; e->n_prof_calls = 1000;
     for (int r = 0; r < 100; r++) for (auto &x : vs) { plan.reset(); plan.target_tasks_per_group = 256; int mu = 0; plan_add_view(e, &x.v, 0, 0, plan, mu, false, SWEEP_LATENCY); }
     printf("phases us: adjacency %.1f traversals %.1f heights %.1f rows+items+emis %.1f emission %.1f\n", 1e6*e->t_ph[0]/(100*vs.size()), 1e6*e->t_ph[1]/(100*vs.size()), 1e6*e->t_ph[2]/(100*vs.size()), 1e6*e->t_ph[3]/(100*vs.size()), 1e6*e->t_ph[4]/(100*vs.size()));
