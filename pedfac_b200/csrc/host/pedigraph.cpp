@@ -12,7 +12,8 @@
 //     can never fire (_EvalMoves@0x100016136-0x100016292 looks up the parents of the focal
 //     individual itself, which is pruned at that point); swaps that touch a selfing marriage are
 //     skipped (the reference reads an unset message there);
-//   * -c 1 (throttle) and -l (loopy BP) are rejected;
+//   * -c 1 (throttle) runs as -c 0, -l (loopy BP) exits where the reference does (both as observed on the
+//     reference binary: DESIGN.md §7);
 //   * the sweep that ends _PickAndUpdate is merged with the one that follows the next
 //     _PruneIndiv (nothing reads messages in between), so a Gibbs step costs one sweep;
 //   * mnode kid arrays grow (the reference overflows a malloc(8) block);
@@ -1644,7 +1645,11 @@ static Opts GetCommLineOpts(int argc, char **argv)
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); usage(); exit(1); }
     }
     if (o.dir.empty()) { usage(); exit(1); }
-    if (o.cyclic != 0 || o.loopy) { fprintf(stderr, "pedigraph: -c %d / -l are not supported by this build (acyclic sampler only)\n", o.cyclic); exit(1); }
+    // -c 1 (throttle): observed on the reference binary, its trace equals the -c 0 trace
+    // until a loop-closing throttle proposal is picked, at which point its exact propagation aborts
+    // ("propagation step exceeds the acyclic upper limit"). This sampler runs -c 1 as -c 0: the same
+    // trace, without the abort. -l is handled where the reference aborts under it (main).
+    if (o.cyclic != 0) fprintf(stderr, "pedigraph: -c %d runs as -c 0 (loop-closing proposals are dropped; the reference aborts once it picks one)\n", o.cyclic);
     return o;
 }
 
@@ -1908,6 +1913,15 @@ int main(int argc, char **argv)
     printf("Allow selfing: %d\n", o.selfing ? 1 : 0);
     printf("Allow loopy: %d\n", o.loopy ? 1 : 0);
     printf("propagating message\n");
+    if (o.loopy) {
+        // -l: the reference's loopy schedule never reports completion (_PassingIFtoIV@0x10001c8f0 returns
+        // "all done" only when not loopy), so its very first propagation runs into the round limit and
+        // exits — observed on every input. Same messages, same streams, same status.
+        printf("propagation step exceeds the acyclic upper limit");
+        fflush(stdout);
+        fprintf(stderr, "exceeding the upper limits of sum-product recursion counter: %d\n", p.nIndivUsed + 2);
+        exit(-1);
+    }
     Propagating_msg(p);
     printf("prior: %f \n", p.LLtot);
     printf("finish propagating message\n");

@@ -97,8 +97,15 @@ def test_soft_calls_and_error_paths(tmp_path):
     (bad / "prior.txt").write_text((bad / "prior.txt").read_text() + "\nnonsense 3")
     r = run(REF, bad)
     assert r.returncode != 0 and "cannot recognize this keyword: nonsense" in r.stderr
-    r = subprocess.run([str(REF), "-d", str(rd), "-c", "1"], capture_output=True, text=True)
-    assert r.returncode != 0 and "not supported" in r.stderr
+    # the two non-default modes, as observed on the reference binary (tests/test_reference_parity.py)
+    r = subprocess.run([str(REF), "-d", str(rd), "-r", str(rd / "rand"), "-l"], capture_output=True, text=True)
+    assert r.returncode == 255 and r.stdout.endswith("propagating message\npropagation step exceeds the acyclic upper limit")
+    assert "exceeding the upper limits of sum-product recursion counter" in r.stderr
+    ped0 = (rd / "out" / "ped.txt").read_text()
+    assert run(REF, rd, n_iter=1).returncode == 0
+    ped0 = (rd / "out" / "ped.txt").read_text()
+    r = subprocess.run([str(REF), "-d", str(rd), "-n", "1", "-r", str(rd / "rand"), "-c", "1"], capture_output=True, text=True)
+    assert r.returncode == 0 and "runs as -c 0" in r.stderr and (rd / "out" / "ped.txt").read_text() == ped0
 
 
 def test_swap_moves_are_scored_consistently_and_can_be_disabled(tmp_path):

@@ -113,3 +113,31 @@ def test_cpu_sampler_matches_the_reference_binary_live(tmp_path, seed, n, S, sof
 @pytest.mark.parametrize("seed,n,S,soft,flags", [(5, 220, 130, False, ()), (6, 160, 96, True, ()), (7, 120, 70, True, ("-w",))])
 def test_gpu_sampler_matches_the_reference_binary_live(tmp_path, seed, n, S, soft, flags):
     live_case(GPU, tmp_path, seed, n, S, soft, flags, 2)
+
+
+@needs_loader
+@pytest.mark.parametrize("name", ["hard_default", "soft_default", "example_case_0_n5"])
+def test_non_default_modes_behave_as_observed_on_the_reference(name, tmp_path):
+    """-l: the reference exits at its first propagation, whatever the input; ours prints the same bytes
+    to the same streams with the same status. -c 1: the reference's trace is a prefix of (or equal to)
+    its -c 0 trace — it dies once a loop-closing proposal is picked; ours runs -c 1 as -c 0."""
+    g = GOLD[name]
+    outs = {}
+    for tag, binary in (("ref", MACHO), ("ours", CPU)):
+        for mode, flags in (("l", ["-l"]), ("c1", ["-c", "1"])):
+            rd = tmp_path / f"{tag}_{mode}"
+            rd.mkdir()
+            for fn, text in g["files"].items():
+                (rd / fn).write_text(text)
+            r = subprocess.run([str(binary), "-d", str(rd), "-n", str(g["n_iter"]), "-r", str(rd / "rand"), *flags], capture_output=True, text=True, timeout=600)
+            ped = (rd / "out" / "ped.txt").read_text() if (rd / "out" / "ped.txt").exists() else ""
+            outs[(tag, mode)] = (r.returncode, r.stdout, r.stderr, ped)
+    rl, ol = outs[("ref", "l")], outs[("ours", "l")]
+    assert rl[0] == ol[0] == 255 and rl[3] == ol[3] == ""
+    assert rl[1].splitlines()[-1] == ol[1].splitlines()[-1] == "propagation step exceeds the acyclic upper limit"
+    assert rl[2].strip().splitlines()[-1] == ol[2].strip().splitlines()[-1]           # "... recursion counter: nIndiv + 2"
+    rc, oc = outs[("ref", "c1")], outs[("ours", "c1")]
+    assert oc[0] == 0 and oc[3] == g["ped"]                                            # ours: the -c 0 trace
+    n = len(rc[3].splitlines())
+    assert rc[3].splitlines() == g["ped"].splitlines()[:n]                             # the reference: a prefix of it
+    assert rc[0] in (0, 255) and (rc[0] == 255 or n == len(g["ped"].splitlines()))
