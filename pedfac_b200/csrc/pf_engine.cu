@@ -117,6 +117,7 @@ struct pf_engine {
     std::vector<uint8_t> h_kind; std::vector<void *> h_eptr; std::vector<uint32_t> h_denom;
     std::vector<double> h_rcp;            // 1 / h_denom per slot (the sweep plans carry it)
     std::vector<uint8_t> soft_kind_of_row;  // kind the slot's soft row was allocated for
+    std::vector<void *> soft_rows_by_kind;  // [slot][kind]: rows already allocated for a slot, one per format
     bool tables_dirty = true;
     std::vector<SoftChunk> soft_chunks;
     std::vector<double> h_eps;            // local shard, for validation only
@@ -186,6 +187,9 @@ extern "C" int pf_destroy(pf_engine *e)
     cudaFree(e->d_kind); cudaFree(e->d_eptr); cudaFree(e->d_denom);
     for (auto &c : e->soft_chunks) cudaFree(c.base);
     e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release(); e->counters.release(); e->sweep_counter.release();
+    e->clockbuf.release();
+    for (auto &r : e->prof) { if (r.a) cudaEventDestroy(r.a); if (r.b) cudaEventDestroy(r.b); }
+    e->prof.clear();
     e->staging.release();
     if (e->h_result) cudaFreeHost(e->h_result);
     if (e->h_mail) cudaFreeHost(e->h_mail);
@@ -342,6 +346,9 @@ extern "C" int pf_set_locus_params(pf_engine *e, const double *eps, const double
 static int soft_row(pf_engine *e, int slot, uint8_t kind, size_t elem_bytes, void **out)
 {
     if (e->h_eptr[slot] && e->soft_kind_of_row[slot] == kind) { *out = e->h_eptr[slot]; return PF_OK; }
+    // a slot that changes its format (f32 -> dec16 -> f32 ...) gets one row per format, kept for reuse
+    if (e->soft_rows_by_kind.empty()) e->soft_rows_by_kind.assign((size_t)e->cfg.cap_indiv * 8, nullptr);
+    if (void *kept = e->soft_rows_by_kind[(size_t)slot * 8 + (kind & 7)]) { *out = kept; e->soft_kind_of_row[slot] = kind; return PF_OK; }
     const size_t bytes = ((size_t)3 * e->Sp * elem_bytes + 255) & ~(size_t)255;
     if (e->soft_chunks.empty() || e->soft_chunks.back().used + bytes > e->soft_chunks.back().cap) {
         SoftChunk c{};
@@ -354,6 +361,7 @@ static int soft_row(pf_engine *e, int slot, uint8_t kind, size_t elem_bytes, voi
     *out = c.base + c.used;
     c.used += bytes;
     e->soft_kind_of_row[slot] = kind;
+    e->soft_rows_by_kind[(size_t)slot * 8 + (kind & 7)] = *out;
     return PF_OK;
 }
 
