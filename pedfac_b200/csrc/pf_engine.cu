@@ -128,6 +128,12 @@ struct pf_engine {
     // mapped pinned mailbox for small results: [0] = sequence flag, [8..] = values (see publish_kernel)
     static constexpr int MAILBOX_MAX = 4096;
     unsigned long long *h_mail = nullptr, *d_mail = nullptr, mail_seq = 0;
+    int pub_want = 0;                 // set by a host-buffer entry point: doubles of the result vector the eval kernel should deliver itself
+    unsigned long long pub_armed = 0; // sequence number the eval kernel was armed with (0: fetch_result launches publish_kernel)
+    bool eval_zero_copy = true;       // PF_EVAL_ZEROCOPY=0: copy the eval plan to device memory instead of reading the pinned buffer
+    static constexpr size_t EVAL_ZERO_COPY_MAX = 16384;
+    DevBuf pubctr;
+    bool fused_publish = true;        // PF_FUSED_PUBLISH=0: always a separate publish launch
 
     // locus shards on several GPUs (pf_comm_*): peer-mapped mailboxes for the cross-GPU sum (xreduce_kernel)
     struct Comm {
@@ -187,7 +193,7 @@ extern "C" int pf_destroy(pf_engine *e)
     cudaFree(e->d_kind); cudaFree(e->d_eptr); cudaFree(e->d_denom);
     for (auto &c : e->soft_chunks) cudaFree(c.base);
     e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release(); e->counters.release(); e->sweep_counter.release();
-    e->clockbuf.release();
+    e->clockbuf.release(); e->pubctr.release();
     for (auto &r : e->prof) { if (r.a) cudaEventDestroy(r.a); if (r.b) cudaEventDestroy(r.b); }
     e->prof.clear();
     e->staging.release();
@@ -263,6 +269,8 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->sweep_clocks = getenv("PF_SWEEP_CLOCKS") != nullptr;
     if (const char *v2 = getenv("PF_SWEEP_V2")) e->sweep_v2 = v2[0] != '0';
     if (const char *v2 = getenv("PF_EVAL_SINGLES")) e->eval_singles = v2[0] != '0';
+    if (const char *v2 = getenv("PF_EVAL_ZEROCOPY")) e->eval_zero_copy = v2[0] != '0';
+    if (const char *v2 = getenv("PF_FUSED_PUBLISH")) e->fused_publish = v2[0] != '0';
     if (const char *fs = getenv("PF_SWEEP_SHAPE")) e->force_shape = fs[0] == 't' ? 2 : fs[0] == 'l' ? 1 : 0;
     *out = e;
     return PF_OK;
@@ -967,6 +975,9 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
 {
     Work2 &x2 = g_work2;
     const int nI = v->n_indiv, nM = v->n_marr;
+    const bool hp_on = e->host_prof && e->n_prof_calls >= 100;
+    double hp_t = hp_on ? host_now() : 0.0;
+    auto hp_mark = [&](int ph) { if (hp_on) { const double t = host_now(); e->t_ph[ph] += t - hp_t; hp_t = t; } };
     x2.kid_off.assign(nM + 1, 0); x2.kid_x.clear(); x2.n_inline.assign(nM, 0); x2.chunk_off.assign(nM, 0); x2.n_chunks.assign(nM, 0);
     x2.chunk_first.clear(); x2.chunk_n.clear(); x2.chunk_row.clear(); x2.chunk_level.clear();
     x2.lvl2.assign(nM, 0); x2.up_m_row.assign(nM, 0); x2.dn_row.assign(nI, -1); x2.park_row.assign(nM, -1); x2.emis_idx.assign(nI, -1);
@@ -985,6 +996,7 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
     }
     x2.kid_off[nM] = (int)x2.kid_x.size();
 
+    hp_mark(2);
     size_t bfs_pos = 0;
     for (size_t ri = 0; ri < w.roots.size(); ri++) {
         const int r = w.roots[ri];
@@ -1082,6 +1094,7 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
             }
         }
 
+        hp_mark(3);
         // ---- records ----
         bool rec_extras = false;                               // some operand of the record being built has more than three rows
         auto push_cmp = [&](int i, int m_ex, int first_row) {
@@ -1198,6 +1211,7 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
             }
         }
         G.pool_len = (int)pool.size() - G.pool_begin;
+        hp_mark(4);
         if (G.n_rows >= 0xffff) plan.fits = false;
         for (size_t b = mb; b < me; b++) if (x2.n_chunks[w.bfs_m[b]] > 255) plan.fits = false;
     }
@@ -1865,30 +1879,43 @@ static int comm_reduce(pf_engine *e, double *buf, int n, double *host_dst = null
     return PF_OK;
 }
 
+static bool ensure_mailbox(pf_engine *e)
+{
+    if (e->no_mailbox) return false;
+    if (!e->h_mail) {
+        void *hp = nullptr, *dp = nullptr;
+        if (cudaHostAlloc(&hp, (size_t)(pf_engine::MAILBOX_MAX + 8) * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (hp) cudaFreeHost(hp);
+            e->no_mailbox = true;
+            return false;
+        }
+        e->h_mail = static_cast<unsigned long long *>(hp); e->d_mail = static_cast<unsigned long long *>(dp);
+        e->h_mail[0] = 0;
+    }
+    return true;
+}
+
 static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2 = nullptr, int n2 = 0)
 {
     const int n1 = n;
     n += n2;
+    e->pub_want = 0;
     if (n <= 0) { CU(cudaStreamSynchronize(e->stream)); return PF_OK; }
     if (n <= pf_engine::MAILBOX_MAX && !e->no_mailbox) {
-        if (!e->h_mail) {
-            void *hp = nullptr, *dp = nullptr;
-            if (cudaHostAlloc(&hp, (size_t)(pf_engine::MAILBOX_MAX + 8) * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
-                cudaHostGetDevicePointer(&dp, hp, 0) != cudaSuccess) {
-                cudaGetLastError();
-                if (hp) cudaFreeHost(hp);
-                e->no_mailbox = true;
-            } else {
-                e->h_mail = static_cast<unsigned long long *>(hp); e->d_mail = static_cast<unsigned long long *>(dp);
-                e->h_mail[0] = 0;
-            }
-        }
+        ensure_mailbox(e);
         if (e->h_mail) {
-            const unsigned long long seq = ++e->mail_seq;
-            if (e->comm.on) {          // cross-GPU sum and delivery in one kernel
+            unsigned long long seq = e->pub_armed;
+            e->pub_armed = 0;
+            if (seq) {                        // the eval kernel's last block delivers: nothing to launch
+                if (seq != e->mail_seq) return fail(PF_ECUDA, "internal: mailbox sequence out of order");
+            } else if (e->comm.on) {          // cross-GPU sum and delivery in one kernel
+                seq = ++e->mail_seq;
                 int rc = comm_reduce(e, static_cast<double *>(e->result.p), n, reinterpret_cast<double *>(e->d_mail + 8), e->d_mail, seq);
                 if (rc) return rc;
             } else {
+                seq = ++e->mail_seq;
                 launch_publish(static_cast<const double *>(e->result.p), reinterpret_cast<double *>(e->d_mail + 8), n, e->d_mail, seq, e->stream);
                 e->launches++;
                 CU(cudaGetLastError());
@@ -1991,8 +2018,10 @@ extern "C" int pf_sweep_eval(pf_engine *e, int32_t chain, const pf_graph_view *v
     if (rc) return rc;
     if (n > 0) {
         const int32_t pb[2] = {0, n};
+        e->pub_want = n_out + n;          // the eval kernel delivers [ll_cc | lsum] itself
         rc = run_evals(e, 1, &chain, &kid, pb, props, static_cast<double *>(e->result.p) + n_out);
-        if (rc) return rc;
+        e->pub_want = 0;
+        if (rc) { e->pub_armed = 0; return rc; }
     }
     return fetch_result(e, ll_cc, n_out, lsum, n);
 }
@@ -2225,12 +2254,26 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
         CU(e->counters.reserve((size_t)group_blocks * sizeof(unsigned) * 2));
         CU(cudaMemsetAsync(e->counters.p, 0, e->counters.cap, e->stream));
     }
-    CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream)); e->io_h2d += blob;
-    CU(e->staging.mark(slot, e->stream));
+    // small proposal lists are read by the kernel straight from the pinned staging slot (one PCIe read
+    // per block instead of a copy engine launch in front of the kernel); large ones are copied
+    const bool zero_copy = e->eval_zero_copy && blob <= pf_engine::EVAL_ZERO_COPY_MAX;
+    const char *plan_dev = static_cast<const char *>(zero_copy ? hp : e->plan.p);
+    if (!zero_copy) CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    e->io_h2d += blob;
     EvalParams P;
     P.D = dev_view(e);
-    P.groups = reinterpret_cast<const EvalGroup *>(e->plan.p);
-    P.props = reinterpret_cast<const EvalProp *>(static_cast<char *>(e->plan.p) + off_props);
+    P.groups = reinterpret_cast<const EvalGroup *>(plan_dev);
+    P.props = reinterpret_cast<const EvalProp *>(plan_dev + off_props);
+    P.pub_src = nullptr; P.pub_dst = nullptr; P.pub_n = 0; P.pub_flag = nullptr; P.pub_seq = 0; P.pub_counter = nullptr;
+    if (e->pub_want > 0 && e->fused_publish && !e->comm.on && e->pub_want <= pf_engine::MAILBOX_MAX && ensure_mailbox(e)) {
+        if (!e->pubctr.p) { CU(e->pubctr.reserve(64)); CU(cudaMemsetAsync(e->pubctr.p, 0, 64, e->stream)); }
+        P.pub_src = static_cast<const double *>(e->result.p);
+        P.pub_dst = reinterpret_cast<double *>(e->d_mail + 8);
+        P.pub_n = e->pub_want;
+        P.pub_flag = e->d_mail;
+        P.pub_seq = e->pub_armed = ++e->mail_seq;
+        P.pub_counter = static_cast<unsigned *>(e->pubctr.p);
+    }
     P.n_groups = n_groups; P.n_props = n_props; P.chunk_loci = chunk_loci;
     P.partial = static_cast<double *>(e->partial.p);
     P.out = out_dev;
@@ -2239,6 +2282,7 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     launch_eval(P, n_chunks, e->stream);
     e->prof_end();
     e->launches++;
+    CU(e->staging.mark(slot, e->stream));
     if (e->host_prof && e->n_prof_calls > 100) e->t_evalprep += host_now() - t_e0;
     CU(cudaGetLastError());
     return PF_OK;
@@ -2252,8 +2296,10 @@ extern "C" int pf_eval_batch(pf_engine *e, int32_t n, const int32_t *chains, con
     if (n_props > 0 && (!props || !lsum)) return fail(PF_EINVAL, "null argument");
     CU(cudaSetDevice(e->cfg.device));
     CU(e->result.reserve((size_t)std::max(n_props, 1) * sizeof(double)));
+    e->pub_want = n_props;
     int rc = run_evals(e, n, chains, kids, prop_begin, props, static_cast<double *>(e->result.p));
-    if (rc) return rc;
+    e->pub_want = 0;
+    if (rc) { e->pub_armed = 0; return rc; }
     return fetch_result(e, lsum, n_props);
 }
 

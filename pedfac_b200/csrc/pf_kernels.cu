@@ -637,6 +637,24 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_c
             }
         }
     }
+    if (s_last && P.pub_flag != nullptr) {          // s_last is uniform over the block
+        __shared__ bool s_pub;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned t = atomicAdd(P.pub_counter, 1u);
+            s_pub = t == gridDim.y - 1;
+            if (s_pub) *P.pub_counter = 0;
+        }
+        __syncthreads();
+        if (s_pub) {
+            __threadfence();
+            for (int i = threadIdx.x; i < P.pub_n; i += blockDim.x) P.pub_dst[i] = __ldcg(P.pub_src + i);
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned long long *>(P.pub_flag) = P.pub_seq; __threadfence_system(); }
+        }
+    }
 }
 
 // resident eval blocks on the current device (SM count x blocks per SM from the occupancy

@@ -184,6 +184,12 @@ struct EvalParams {
     double *partial;        // [n_chunks][n_props]
     double *out;            // [n_props] sums over chunks (written by the last block of each column)
     unsigned *counters;     // [group blocks] arrival counters, zero between launches
+    // optional fused result delivery: the block that finishes the last column copies the call's whole
+    // result vector (pub_n doubles at pub_src: a preceding sweep's ll_cc and this launch's sums) to the
+    // host's mapped mailbox and raises its sequence flag — no publish launch
+    const double *pub_src; double *pub_dst; int pub_n;
+    unsigned long long *pub_flag, pub_seq;
+    unsigned *pub_counter;
 };
 
 struct ReduceParams {

@@ -5,6 +5,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -103,6 +104,10 @@ def test_two_rank_locus_sharding_matches_unsharded():
 def test_shard_ranges_tile_the_loci():
     for S in (1, 49, 50, 500, 2000, 10000, 10007):
         for world in (1, 2, 4, 8):
+            if (S + 49) // 50 < world:                     # fewer 50-locus blocks than ranks: refused, not an empty shard
+                with pytest.raises(ValueError):
+                    shard_range(S, 0, world)
+                continue
             r = [shard_range(S, k, world) for k in range(world)]
             assert r[0][0] == 0 and r[-1][1] == S
             assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))

@@ -50,8 +50,9 @@ int main(int argc, char **argv)
         printf("plan_add_view + emit2: %.1f us per view (best of %d), last plan: %zu tasks %zu pool words %zu groups\n", best2, reps, p2.tasks.size(), p2.pool.size(), p2.groups.size());
     }
     e->host_prof = true; e->n_prof_calls = 1000;
-    for (int r = 0; r < 100; r++) for (auto &x : vs) { plan.reset(); plan.target_tasks_per_group = 256; int mu = 0; plan_add_view(e, &x.v, 0, 0, plan, mu, false, SWEEP_LATENCY); }
-    printf("phases us: adjacency %.1f traversals %.1f heights %.1f rows+items+emis %.1f emission %.1f\n", 1e6*e->t_ph[0]/(100*vs.size()), 1e6*e->t_ph[1]/(100*vs.size()), 1e6*e->t_ph[2]/(100*vs.size()), 1e6*e->t_ph[3]/(100*vs.size()), 1e6*e->t_ph[4]/(100*vs.size()));
+    static Plan2 q2; static Plan dummy2;
+    for (int r = 0; r < 100; r++) for (auto &x : vs) { q2.reset(); q2.target_tasks_per_group = 256; q2.format = 2; int mu = 0; plan_add_view(e, &x.v, 0, 0, dummy2, mu, false, SWEEP_LATENCY, nullptr, &q2); }
+    printf("v2 phases us: adjacency %.1f traversals %.1f kid lists %.1f rows+levels %.1f records %.1f\n", 1e6*e->t_ph[0]/(100*vs.size()), 1e6*e->t_ph[1]/(100*vs.size()), 1e6*e->t_ph[2]/(100*vs.size()), 1e6*e->t_ph[3]/(100*vs.size()), 1e6*e->t_ph[4]/(100*vs.size()));
     printf("plan_add_view: %.1f us per view (best of %d), last plan: %zu tasks %zu pool ints %zu emis\n", best, reps, plan.tasks.size(), plan.pool.size(), plan.emis.size());
     return 0;
 }
