@@ -195,6 +195,19 @@ int pf_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_
 int pf_eval_swaps_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t n,
                       const pf_swap *swaps, double *lsum_dev);
 
+/* The whole first submission of a Gibbs step: pf_sweep_eval, and behind it the swap proposals of the
+ * step (≙ the swap block of _EvalMoves@0x100015989-0x100016651, whose enumeration also depends on the
+ * graph only) as in pf_eval_swaps on `swap_view`. ll_cc and lsum are returned as soon as the proposal
+ * kernel has finished; the swap proposals are planned on the host while the sweep runs, execute while
+ * the caller prepares its next call, and their n_swaps values are DEFERRED: they travel in the same
+ * delivery as the results of the next host-result call on this engine (pf_eval, pf_sweep, ...) and
+ * are then read with pf_deferred_results, which delivers them itself if no call has carried them.
+ * At most one set of deferred values may be outstanding. Values identical to pf_eval_swaps. */
+int pf_sweep_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc,
+                        int32_t kid, int32_t n, const pf_proposal *props, double *lsum,
+                        const pf_graph_view *swap_view, int32_t n_swaps, const pf_swap *swaps);
+int pf_deferred_results(pf_engine *e, int32_t n, double *lsum_swaps);
+
 /* ≙ _RefineParentOffPair@0x100014d20 (its N_obs^2 x S _CalculateLLByStubs calls), dense form:
  * for every kid k and every candidate c (c != kid) the score
  *     lsum(kid k; c as the single given parent, the other parent a new founder) + cand_bias[c]

@@ -47,6 +47,7 @@ struct pfo_engine {
     int *m_ne;              /* [capM] edge capacity of the stored message arrays */
     int *loc;               /* [capI] slot -> index in the current view, else -1 */
     char *arena; size_t arena_cap, arena_used;
+    double *deferred; int n_deferred;   /* swap values held for pfo_deferred_results */
 };
 
 static void *arena_get(pfo_engine *e, size_t bytes)
@@ -90,7 +91,7 @@ int pfo_destroy(pfo_engine *e)
     for (int m = 0; m < e->capM; m++) { free(e->prong[m]); free(e->m_in[m]); free(e->m_out[m]); }
     free(e->m_in); free(e->m_out); free(e->m_ne);
     free(e->eps); free(e->prior); free(e->emis); free(e->stub); free(e->prong); free(e->loc);
-    free(e->arena); free(e);
+    free(e->arena); free(e->deferred); free(e);
     return PF_OK;
 }
 
@@ -877,4 +878,31 @@ int pfo_io_bytes(const pfo_engine *e, uint64_t *h2d, uint64_t *d2h)
     if (h2d) *h2d = 0;
     if (d2h) *d2h = 0;
     return 0;
+}
+
+/* The CUDA library queues the swap proposals behind the sweep and the first proposals and hands their
+ * values over later; here the same entry points are the three calls in a row, the values kept until
+ * asked for. */
+int pfo_sweep_eval_swaps(pfo_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc, int32_t kid, int32_t n,
+                         const pf_proposal *props, double *lsum, const pf_graph_view *swap_view, int32_t n_swaps, const pf_swap *swaps)
+{
+    if (!e || n_swaps < 0) FAIL(PF_EINVAL, "null argument");
+    if (n_swaps > 0 && e->n_deferred > 0) FAIL(PF_EINVAL, "the swap results of an earlier pfo_sweep_eval_swaps were not collected");
+    int rc = pfo_sweep_eval(e, chain, view, ll_cc, kid, n, props, lsum);
+    if (rc != PF_OK || n_swaps == 0) return rc;
+    double *d = (double *)realloc(e->deferred, (size_t)n_swaps * sizeof(double));
+    if (!d) FAIL(PF_ENOMEM, "out of memory");
+    e->deferred = d;
+    rc = pfo_eval_swaps(e, chain, swap_view, n_swaps, swaps, d);
+    if (rc == PF_OK) e->n_deferred = n_swaps;
+    return rc;
+}
+
+int pfo_deferred_results(pfo_engine *e, int32_t n, double *lsum_swaps)
+{
+    if (!e || n < 0 || (n > 0 && !lsum_swaps)) FAIL(PF_EINVAL, "null argument");
+    if (n != e->n_deferred) FAIL(PF_EINVAL, "%d deferred results asked for, %d are held", n, e->n_deferred);
+    if (n > 0) memcpy(lsum_swaps, e->deferred, (size_t)n * sizeof(double));
+    e->n_deferred = 0;
+    return PF_OK;
 }

@@ -44,6 +44,9 @@ int pfo_eval(pfo_engine *e, int32_t chain, int32_t kid, int32_t n, const pf_prop
              double *lsum);
 int pfo_sweep_eval(pfo_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc,
                    int32_t kid, int32_t n, const pf_proposal *props, double *lsum);
+int pfo_sweep_eval_swaps(pfo_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc, int32_t kid, int32_t n,
+                         const pf_proposal *props, double *lsum, const pf_graph_view *swap_view, int32_t n_swaps, const pf_swap *swaps);
+int pfo_deferred_results(pfo_engine *e, int32_t n, double *lsum_swaps);
 int pfo_eval_swaps(pfo_engine *e, int32_t chain, const pf_graph_view *view, int32_t n,
                    const pf_swap *swaps, double *lsum);
 int pfo_prefilter(pfo_engine *e, int32_t chain, int32_t n_kids, const int32_t *kids,

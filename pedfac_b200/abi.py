@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "io_bytes", "comm_local_handle", "comm_connect", "comm_reduce_count", "comm_set_async", "comm_fence", "sweep_eval_dev", "profile", "profile_read", "plan_stats",
+    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "io_bytes", "comm_local_handle", "comm_connect", "comm_reduce_count", "comm_set_async", "comm_fence", "sweep_eval_dev", "sweep_eval_swaps", "deferred_results", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -104,6 +104,8 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("comm_reduce_count", C.c_int64, vp)
     sig("comm_set_async", C.c_int, vp, C.c_int32)
     sig("comm_fence", C.c_int, vp)
+    sig("sweep_eval_swaps", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), _f64p, C.c_int32, C.c_int32, vp, _f64p, C.POINTER(PfGraphView), C.c_int32, vp)
+    sig("deferred_results", C.c_int, vp, C.c_int32, _f64p)
     sig("sweep_eval_dev", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), C.c_int32, C.c_int32, vp, vp)
     sig("plan_stats", C.c_int, vp, _i32p)
     sig("profile", C.c_int, vp, C.c_int32)
@@ -270,6 +272,22 @@ class CEngine:
         self._check(self._fn("sweep_eval")(self._h, chain, C.byref(view.struct), ptr(ll, _f64p), kid, len(props),
                                            C.c_void_p(props.ctypes.data), ptr(out, _f64p)))
         return ll[:view.n_cc], out[:len(props)]
+
+    def sweep_eval_swaps(self, view: GraphView, kid: int, props, swap_view: GraphView, swaps, chain: int = 0):
+        """`pf_sweep_eval_swaps`: (ll_cc, lsum) now; the swap values are deferred (`deferred_results`)."""
+        props = make_proposals(props)
+        swaps = make_swaps(swaps)
+        ll = np.empty(max(view.n_cc, 1), dtype=np.float64)
+        out = np.empty(max(len(props), 1), dtype=np.float64)
+        self._check(self._fn("sweep_eval_swaps")(self._h, chain, C.byref(view.struct), ptr(ll, _f64p), kid, len(props),
+                                                 C.c_void_p(props.ctypes.data), ptr(out, _f64p),
+                                                 C.byref(swap_view.struct), len(swaps), C.c_void_p(swaps.ctypes.data)))
+        return ll[:view.n_cc], out[:len(props)]
+
+    def deferred_results(self, n: int) -> np.ndarray:
+        out = np.empty(max(n, 1), dtype=np.float64)
+        self._check(self._fn("deferred_results")(self._h, n, ptr(out, _f64p)))
+        return out[:n]
 
     def eval_swaps(self, view: GraphView, swaps, chain: int = 0) -> np.ndarray:
         swaps = make_swaps(swaps)

@@ -635,7 +635,9 @@ static void flush(Ped &p, int kid, Batch &b)
 
 // The pending sweep (_Propagating_msg after _PruneIndiv) and the first batch of proposals of the
 // same Gibbs step in one engine submission: the proposal list depends on the graph only.
-static void sweep_and_flush(Ped &p, int kid, Batch &b)
+struct SwapPlan;
+static int submit_step(Ped &p, const pf_graph_view *v, double *ll, int kid, Batch &b, double *lsum, SwapPlan *sp);
+static void sweep_and_flush(Ped &p, int kid, Batch &b, SwapPlan *sp)
 {
     if (p.nDirty == 0) { flush(p, kid, b); return; }
     const double t0 = now_s();
@@ -643,7 +645,7 @@ static void sweep_and_flush(Ped &p, int kid, Batch &b)
     dirty_view(p, vb);
     std::vector<double> ll(vb.labels.size() + 1), lsum(b.props.size() + 1);
     const double t1 = now_s();
-    if (eng_sweep_eval(p, &vb.v, ll.data(), kid, (int)b.props.size(), b.props.data(), lsum.data()) != PF_OK) die("sweep_eval failed");
+    if (submit_step(p, &vb.v, ll.data(), kid, b, lsum.data(), sp) != PF_OK) die("sweep_eval failed");
     p.t_view += t1 - t0; p.t_sweep += now_s() - t1;
     store_sweep(p, vb, ll);
     p.n_proposals += (long)b.props.size();
@@ -701,8 +703,18 @@ static bool by_ll_desc(const std::pair<int, double> &a, const std::pair<int, dou
 // marriage of the focal individual x whose other parent z has parents itself, exchange the fathers
 // (kind 1), the mothers (kind 2) or both (kind 3) between x's previous family and z's family; kinds
 // 1 and 2 come in two flavours (siblings stay / siblings move too). All swaps of a step are scored
-// by one engine call on the view of the three components involved.
-static void ProposeSwaps(Ped &p, int x, bool redPa, bool redMa)
+// by one engine call on the view of the three components involved. The list depends on the graph
+// only, so it is drawn up (PlanSwaps) before the step's first engine submission, which queues it
+// behind the sweep; the choices enter the list where the reference appends them (FinishSwaps).
+struct SwapPlan {
+    std::vector<pf_swap> sw;
+    std::vector<Choice> ch;
+    ViewBuf view;
+    int cx = -1, P = -1, Q = -1;
+    bool queued = false;            // submitted with the sweep: the values are the engine's deferred results
+};
+
+static void PlanSwaps(Ped &p, int x, bool redPa, bool redMa, SwapPlan &sp)
 {
     const int P = p.prev[0], Q = p.prev[1], M0 = p.prev[2];
     if (P < 0) return;
@@ -718,20 +730,18 @@ static void ProposeSwaps(Ped &p, int x, bool redPa, bool redMa)
         p.indiv[a].reductive = isReductiveParent(p, a);
         p.indiv[b].reductive = isReductiveParent(p, b);
     }
-    std::vector<pf_swap> sw;
     auto propose = [&](int kind, int z, int mz, int mx) {      // _ProposeSwapping@0x1000223d0
         auto add = [&](int move) {
-            sw.push_back(pf_swap{kind, move, x, z, mz, mx, P, Q, M0, 0});
+            sp.sw.push_back(pf_swap{kind, move, x, z, mz, mx, P, Q, M0, 0});
             Choice c{M0, P, Q, 0, 3};
             c.swapKind = kind; c.marrZ = mz; c.swapZ = move ? z : -1;
-            p.ch.push_back(c); p.chll.push_back(0.0);
+            sp.ch.push_back(c);
         };
         if (kind == 3) { add(1); return; }
         add(0);
         if (M0 == -1 && p.marr[mz].nEdges() == 3) return;      // @0x1000226c4-0x1000226f8
         add(1);
     };
-    const size_t first = p.ch.size();
     for (int mx : ix.M) {                                      // @0x100015bec-0x100016651
         const int z = spouse(mx);
         const int mz = parents_marr(z);
@@ -745,20 +755,38 @@ static void ProposeSwaps(Ped &p, int x, bool redPa, bool redMa)
         if (k2) { propose(2, z, mz, mx); if (k1) propose(3, z, mz, mx); }
         // kind 4 (pairs of x's marriages, @0x1000160da-0x100016638) never fires in the reference
     }
-    if (sw.empty()) return;
+    if (sp.sw.empty()) return;
     const double t0 = now_s();
+    sp.cx = cx; sp.P = P; sp.Q = Q;
     std::vector<char> want(p.nCC, 0);
     want[cx] = want[p.cc[P]] = want[p.cc[Q]] = 1;
-    ViewBuf b;
-    build_view(p, want, b);
-    std::vector<double> lsum(sw.size());
+    build_view(p, want, sp.view);
+    p.t_view += now_s() - t0;
+}
+
+static void FinishSwaps(Ped &p, SwapPlan &sp)
+{
+    if (sp.sw.empty()) return;
+    const size_t first = p.ch.size();
+    for (const Choice &c : sp.ch) { p.ch.push_back(c); p.chll.push_back(0.0); }
+    std::vector<double> lsum(sp.sw.size());
     const double t1 = now_s();
-    if (eng_eval_swaps(p, &b.v, (int)sw.size(), sw.data(), lsum.data()) != PF_OK) die("eval_swaps failed");
-    p.t_view += t1 - t0; p.t_eval += now_s() - t1;
-    p.n_proposals += (long)sw.size(); p.n_swaps += (long)sw.size();
-    const int cp = p.cc[P], cq = p.cc[Q];
-    for (size_t k = 0; k < sw.size(); k++)                      // _calculateBundlell@0x100022291-0x1000223a8
-        p.chll[first + k] = pf_compose_swap_ll(p.LLtot, lsum[k], p.LLcc[cx], p.LLcc[cp], cp != cq && cp != cx, p.LLcc[cq]);
+    if (sp.queued) {
+        if (PFN(deferred_results)(p.eng, (int)sp.sw.size(), lsum.data()) != PF_OK) die("deferred_results failed");
+    } else if (eng_eval_swaps(p, &sp.view.v, (int)sp.sw.size(), sp.sw.data(), lsum.data()) != PF_OK) die("eval_swaps failed");
+    p.t_eval += now_s() - t1;
+    p.n_proposals += (long)sp.sw.size(); p.n_swaps += (long)sp.sw.size();
+    const int cp = p.cc[sp.P], cq = p.cc[sp.Q];
+    for (size_t k = 0; k < sp.sw.size(); k++)                   // _calculateBundlell@0x100022291-0x1000223a8
+        p.chll[first + k] = pf_compose_swap_ll(p.LLtot, lsum[k], p.LLcc[sp.cx], p.LLcc[cp], cp != cq && cp != sp.cx, p.LLcc[cq]);
+}
+
+// the step's first submission: the pending sweep, the single-parent proposals and, queued behind them, the swaps
+static int submit_step(Ped &p, const pf_graph_view *v, double *ll, int kid, Batch &b, double *lsum, SwapPlan *sp)
+{
+    if (mc::active || !sp || sp->sw.empty()) return eng_sweep_eval(p, v, ll, kid, (int)b.props.size(), b.props.data(), lsum);
+    sp->queued = true;
+    return PFN(sweep_eval_swaps)(p.eng, p.chain, v, ll, kid, (int)b.props.size(), b.props.data(), lsum, &sp->view.v, (int)sp->sw.size(), sp->sw.data());
 }
 
 // _EvalMoves@0x100015010
@@ -784,7 +812,9 @@ static void EvalMoves(Ped &p, const Opts &o, int kid)
     }
     if (redPa) p.indivActive[ppa] = 1;
     if (redMa) p.indivActive[pma] = 1;
-    sweep_and_flush(p, kid, b);                                // single-parent scores are needed for the top-10 cut
+    SwapPlan sp;
+    if (!o.diswap) PlanSwaps(p, kid, redPa, redMa, sp);
+    sweep_and_flush(p, kid, b, &sp);                           // single-parent scores are needed for the top-10 cut
     for (int s = 0; s < 3; s++) {
         p.cand[s].clear();
         for (auto &cs : cand_slot[s]) p.cand[s].push_back({cs.first, p.chll[cs.second]});
@@ -811,7 +841,7 @@ static void EvalMoves(Ped &p, const Opts &o, int kid)
         add_choice(p, b, PF_PROP_PRONG, -1, -1, m);
     }
     flush(p, kid, b);
-    if (!o.diswap) ProposeSwaps(p, kid, redPa, redMa);
+    FinishSwaps(p, sp);
 }
 
 // _AddObsFracPrior@0x100019800

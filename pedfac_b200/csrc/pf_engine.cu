@@ -128,6 +128,9 @@ struct pf_engine {
     // mapped pinned mailbox for small results: [0] = sequence flag, [8..] = values (see publish_kernel)
     static constexpr int MAILBOX_MAX = 4096;
     unsigned long long *h_mail = nullptr, *d_mail = nullptr, mail_seq = 0;
+    // results of swap proposals queued by pf_sweep_eval_swaps, delivered with the next host-result call
+    DevBuf deferred; int n_deferred = 0, pub_armed_def = 0; std::vector<double> h_deferred;
+    cudaEvent_t fetch_event = nullptr;
     int pub_want = 0;                 // set by a host-buffer entry point: doubles of the result vector the eval kernel should deliver itself
     unsigned long long pub_armed = 0; // sequence number the eval kernel was armed with (0: fetch_result launches publish_kernel)
     bool eval_zero_copy = true;       // PF_EVAL_ZEROCOPY=0: copy the eval plan to device memory instead of reading the pinned buffer
@@ -193,7 +196,8 @@ extern "C" int pf_destroy(pf_engine *e)
     cudaFree(e->d_kind); cudaFree(e->d_eptr); cudaFree(e->d_denom);
     for (auto &c : e->soft_chunks) cudaFree(c.base);
     e->scratch.release(); e->plan.release(); e->partial.release(); e->result.release(); e->counters.release(); e->sweep_counter.release();
-    e->clockbuf.release(); e->pubctr.release();
+    e->clockbuf.release(); e->pubctr.release(); e->deferred.release();
+    if (e->fetch_event) cudaEventDestroy(e->fetch_event);
     for (auto &r : e->prof) { if (r.a) cudaEventDestroy(r.a); if (r.b) cudaEventDestroy(r.b); }
     e->prof.clear();
     e->staging.release();
@@ -1897,62 +1901,102 @@ static bool ensure_mailbox(pf_engine *e)
     return true;
 }
 
-static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2 = nullptr, int n2 = 0)
+// Delivery of a call's results to the host, in two halves so that more work can be queued behind the
+// kernels of the call before the host starts waiting. The result vector is [own results (n) | results
+// deferred by an earlier pf_sweep_eval_swaps (n_def)]: small vectors go through the mapped mailbox
+// (written by the eval kernel's last block when run_evals armed it, by the cross-GPU sum on a sharded
+// engine, else by publish_kernel), large ones through a copy.
+struct Fetch { int mode = 0, n = 0, n_def = 0; unsigned long long seq = 0; };
+
+static int reserve_result(pf_engine *e, int n_own)
 {
-    const int n1 = n;
-    n += n2;
+    CU(e->result.reserve((size_t)std::max(n_own + e->n_deferred, 1) * sizeof(double)));
+    return PF_OK;
+}
+
+static int fetch_begin(pf_engine *e, int n, Fetch &f)
+{
     e->pub_want = 0;
-    if (n <= 0) { CU(cudaStreamSynchronize(e->stream)); return PF_OK; }
-    if (n <= pf_engine::MAILBOX_MAX && !e->no_mailbox) {
-        ensure_mailbox(e);
-        if (e->h_mail) {
-            unsigned long long seq = e->pub_armed;
-            e->pub_armed = 0;
-            if (seq) {                        // the eval kernel's last block delivers: nothing to launch
-                if (seq != e->mail_seq) return fail(PF_ECUDA, "internal: mailbox sequence out of order");
-            } else if (e->comm.on) {          // cross-GPU sum and delivery in one kernel
-                seq = ++e->mail_seq;
-                int rc = comm_reduce(e, static_cast<double *>(e->result.p), n, reinterpret_cast<double *>(e->d_mail + 8), e->d_mail, seq);
-                if (rc) return rc;
-            } else {
-                seq = ++e->mail_seq;
-                launch_publish(static_cast<const double *>(e->result.p), reinterpret_cast<double *>(e->d_mail + 8), n, e->d_mail, seq, e->stream);
-                e->launches++;
-                CU(cudaGetLastError());
-            }
-            e->io_d2h += (size_t)n * sizeof(double) + 8;
-            const double t_w0 = e->host_prof ? host_now() : 0.0;
-            volatile unsigned long long *flag = e->h_mail;
-            for (unsigned spins = 1; *flag != seq; spins++) {
-                __builtin_ia32_pause();
-                if ((spins & 0x3fff) == 0) {                 // a faulting kernel never raises the flag
-                    const cudaError_t q = cudaStreamQuery(e->stream);
-                    if (q != cudaSuccess && q != cudaErrorNotReady) return fail(PF_ECUDA, "CUDA error while waiting for results: %s", cudaGetErrorString(q));
-                    if (q == cudaSuccess && *flag != seq) { CU(cudaStreamSynchronize(e->stream)); break; }
-                }
-            }
-            __atomic_thread_fence(__ATOMIC_ACQUIRE);
-            if (e->host_prof && e->n_prof_calls > 100) e->t_wait += host_now() - t_w0;
-            const double *vals = reinterpret_cast<const double *>(e->h_mail + 8);
-            if (n1 > 0) memcpy(host_out, vals, (size_t)n1 * sizeof(double));
-            if (n2 > 0) memcpy(host_out2, vals + n1, (size_t)n2 * sizeof(double));
-            return PF_OK;
+    const unsigned long long armed = e->pub_armed;
+    e->pub_armed = 0;
+    f.n = n;
+    f.n_def = armed ? e->pub_armed_def : e->n_deferred;
+    const int tot = n + f.n_def;
+    if (tot <= 0) { f.mode = 0; return PF_OK; }
+    if (!armed && f.n_def > 0)      // no kernel gathers the two pieces: append the deferred results behind this call's
+        CU(cudaMemcpyAsync(static_cast<double *>(e->result.p) + n, e->deferred.p, (size_t)f.n_def * sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    if (tot <= pf_engine::MAILBOX_MAX && ensure_mailbox(e)) {
+        f.mode = 1;
+        if (armed) {                      // the eval kernel's last block delivers: nothing to launch
+            if (armed != e->mail_seq) return fail(PF_ECUDA, "internal: mailbox sequence out of order");
+            f.seq = armed;
+        } else if (e->comm.on) {          // cross-GPU sum and delivery in one kernel
+            f.seq = ++e->mail_seq;
+            int rc = comm_reduce(e, static_cast<double *>(e->result.p), tot, reinterpret_cast<double *>(e->d_mail + 8), e->d_mail, f.seq);
+            if (rc) return rc;
+        } else {
+            f.seq = ++e->mail_seq;
+            launch_publish(static_cast<const double *>(e->result.p), reinterpret_cast<double *>(e->d_mail + 8), tot, e->d_mail, f.seq, e->stream);
+            e->launches++;
+            CU(cudaGetLastError());
         }
+        e->io_d2h += (size_t)tot * sizeof(double) + 8;
+        return PF_OK;
     }
-    if (e->comm.on) { int rc = comm_reduce(e, static_cast<double *>(e->result.p), n); if (rc) return rc; }
-    if ((size_t)n * sizeof(double) > e->h_result_cap) {
+    if (armed) return fail(PF_ECUDA, "internal: armed delivery without a mailbox");
+    f.mode = 2;
+    if (e->comm.on) { int rc = comm_reduce(e, static_cast<double *>(e->result.p), tot); if (rc) return rc; }
+    if ((size_t)tot * sizeof(double) > e->h_result_cap) {
         if (e->h_result) CU(cudaFreeHost(e->h_result));
         e->h_result = nullptr; e->h_result_cap = 0;
-        const size_t want = (size_t)n * sizeof(double) * 2 + 4096;
+        const size_t want = (size_t)tot * sizeof(double) * 2 + 4096;
         CU(cudaMallocHost(&e->h_result, want));
         e->h_result_cap = want;
     }
-    CU(cudaMemcpyAsync(e->h_result, e->result.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    e->io_d2h += (size_t)n * sizeof(double);
-    CU(cudaStreamSynchronize(e->stream));
-    if (n1 > 0) memcpy(host_out, e->h_result, (size_t)n1 * sizeof(double));
-    if (n2 > 0) memcpy(host_out2, e->h_result + n1, (size_t)n2 * sizeof(double));
+    CU(cudaMemcpyAsync(e->h_result, e->result.p, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    if (!e->fetch_event) CU(cudaEventCreateWithFlags(&e->fetch_event, cudaEventDisableTiming));
+    CU(cudaEventRecord(e->fetch_event, e->stream));
+    e->io_d2h += (size_t)tot * sizeof(double);
     return PF_OK;
+}
+
+static int fetch_end(pf_engine *e, const Fetch &f, double *host_out, int n1, double *host_out2 = nullptr, int n2 = 0)
+{
+    const double *vals = nullptr;
+    if (f.mode == 0) { CU(cudaStreamSynchronize(e->stream)); return PF_OK; }
+    if (f.mode == 1) {
+        const double t_w0 = e->host_prof ? host_now() : 0.0;
+        volatile unsigned long long *flag = e->h_mail;
+        for (unsigned spins = 1; *flag != f.seq; spins++) {
+            __builtin_ia32_pause();
+            if ((spins & 0x3fff) == 0) {                 // a faulting kernel never raises the flag
+                const cudaError_t q = cudaStreamQuery(e->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return fail(PF_ECUDA, "CUDA error while waiting for results: %s", cudaGetErrorString(q));
+                if (q == cudaSuccess && *flag != f.seq) { CU(cudaStreamSynchronize(e->stream)); break; }
+            }
+        }
+        __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        if (e->host_prof && e->n_prof_calls > 100) e->t_wait += host_now() - t_w0;
+        vals = reinterpret_cast<const double *>(e->h_mail + 8);
+    } else {
+        CU(cudaEventSynchronize(e->fetch_event));
+        vals = e->h_result;
+    }
+    if (n1 > 0) memcpy(host_out, vals, (size_t)n1 * sizeof(double));
+    if (n2 > 0) memcpy(host_out2, vals + n1, (size_t)n2 * sizeof(double));
+    if (f.n_def > 0) {
+        e->h_deferred.assign(vals + f.n, vals + f.n + f.n_def);
+        e->n_deferred = 0;
+    }
+    return PF_OK;
+}
+
+static int fetch_result(pf_engine *e, double *host_out, int n, double *host_out2 = nullptr, int n2 = 0)
+{
+    Fetch f;
+    int rc = fetch_begin(e, n + n2, f);
+    if (rc) return rc;
+    return fetch_end(e, f, host_out, n, host_out2, n2);
 }
 
 static int total_cc(int n, const pf_graph_view *views)
@@ -1968,9 +2012,9 @@ extern "C" int pf_sweep_batch(pf_engine *e, int32_t n, const int32_t *chains, co
     CU(cudaSetDevice(e->cfg.device));
     const int tot = total_cc(n, views);
     if (tot > 0 && !ll_cc) return fail(PF_EINVAL, "null output");
-    CU(e->result.reserve((size_t)std::max(tot, 1) * sizeof(double)));
     int n_out = 0;
-    int rc = run_sweeps(e, n, chains, views, static_cast<double *>(e->result.p), &n_out);
+    int rc = reserve_result(e, tot);
+    if (rc == PF_OK) rc = run_sweeps(e, n, chains, views, static_cast<double *>(e->result.p), &n_out);
     if (rc) return rc;
     return fetch_result(e, ll_cc, n_out);
 }
@@ -2005,16 +2049,21 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
 // One Gibbs step's first round trip in a single submission: the sweep of the dirty components and
 // the evaluation of the focal individual's single-parent proposals are enqueued back to back and
 // the host waits once (the proposal list depends on the graph only, not on the sweep's results).
-extern "C" int pf_sweep_eval(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc,
-                             int32_t kid, int32_t n, const pf_proposal *props, double *lsum)
+static int run_swaps(pf_engine *e, int chain, const pf_graph_view *view, int n, const pf_swap *swaps, double *out_dev);
+
+static int sweep_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc, int32_t kid, int32_t n,
+                            const pf_proposal *props, double *lsum, const pf_graph_view *swap_view, int32_t n_swaps, const pf_swap *swaps)
 {
-    if (!e || !view || n < 0) return fail(PF_EINVAL, "null argument");
-    if ((view->n_cc > 0 && !ll_cc) || (n > 0 && (!props || !lsum))) return fail(PF_EINVAL, "null argument");
+    if (!e || !view || n < 0 || n_swaps < 0) return fail(PF_EINVAL, "null argument");
+    if ((view->n_cc > 0 && !ll_cc) || (n > 0 && (!props || !lsum)) || (n_swaps > 0 && (!swap_view || !swaps))) return fail(PF_EINVAL, "null argument");
+    if (n_swaps > 0 && (e->n_deferred > 0 || !e->h_deferred.empty())) return fail(PF_EINVAL, "the swap results of an earlier pf_sweep_eval_swaps were not collected (pf_deferred_results)");
     CU(cudaSetDevice(e->cfg.device));
     const int n_cc = std::max(view->n_cc, 0);
-    CU(e->result.reserve((size_t)std::max(n_cc + n, 1) * sizeof(double)));
+    int rc = reserve_result(e, n_cc + n);
+    if (rc) return rc;
+    if (n_swaps > 0) CU(e->deferred.reserve((size_t)n_swaps * sizeof(double)));
     int n_out = 0;
-    int rc = run_sweeps(e, 1, &chain, view, static_cast<double *>(e->result.p), &n_out);
+    rc = run_sweeps(e, 1, &chain, view, static_cast<double *>(e->result.p), &n_out);
     if (rc) return rc;
     if (n > 0) {
         const int32_t pb[2] = {0, n};
@@ -2023,7 +2072,45 @@ extern "C" int pf_sweep_eval(pf_engine *e, int32_t chain, const pf_graph_view *v
         e->pub_want = 0;
         if (rc) { e->pub_armed = 0; return rc; }
     }
-    return fetch_result(e, ll_cc, n_out, lsum, n);
+    Fetch f;
+    rc = fetch_begin(e, n_out + n, f);
+    if (rc) return rc;
+    // the swap proposals are planned while the sweep and the proposal kernel run, and run behind them;
+    // their values travel with the results of the next call
+    int rc_swaps = PF_OK;
+    if (n_swaps > 0) {
+        rc_swaps = run_swaps(e, chain, swap_view, n_swaps, swaps, static_cast<double *>(e->deferred.p));
+        if (rc_swaps == PF_OK) e->n_deferred = n_swaps;
+    }
+    rc = fetch_end(e, f, ll_cc, n_out, lsum, n);
+    return rc ? rc : rc_swaps;
+}
+
+extern "C" int pf_sweep_eval(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc,
+                             int32_t kid, int32_t n, const pf_proposal *props, double *lsum)
+{
+    return sweep_eval_swaps(e, chain, view, ll_cc, kid, n, props, lsum, nullptr, 0, nullptr);
+}
+
+extern "C" int pf_sweep_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc, int32_t kid, int32_t n,
+                                   const pf_proposal *props, double *lsum, const pf_graph_view *swap_view, int32_t n_swaps, const pf_swap *swaps)
+{
+    return sweep_eval_swaps(e, chain, view, ll_cc, kid, n, props, lsum, swap_view, n_swaps, swaps);
+}
+
+extern "C" int pf_deferred_results(pf_engine *e, int32_t n, double *lsum_swaps)
+{
+    if (!e || n < 0 || (n > 0 && !lsum_swaps)) return fail(PF_EINVAL, "null argument");
+    CU(cudaSetDevice(e->cfg.device));
+    if (e->n_deferred > 0) {                       // no call has carried them yet: deliver them now
+        int rc = reserve_result(e, 0);
+        if (rc == PF_OK) rc = fetch_result(e, nullptr, 0);
+        if (rc) return rc;
+    }
+    if ((size_t)n != e->h_deferred.size()) return fail(PF_EINVAL, "%d deferred results asked for, %d are held", n, (int)e->h_deferred.size());
+    if (n > 0) memcpy(lsum_swaps, e->h_deferred.data(), (size_t)n * sizeof(double));
+    e->h_deferred.clear();
+    return PF_OK;
 }
 
 // the same with the results left on the device: out_dev = [ll_cc (view->n_cc) | lsum (n)], one
@@ -2159,8 +2246,8 @@ extern "C" int pf_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *v
     if (!e) return fail(PF_EINVAL, "null argument");
     if (n > 0 && !lsum) return fail(PF_EINVAL, "null output");
     CU(cudaSetDevice(e->cfg.device));
-    CU(e->result.reserve((size_t)std::max(n, 1) * sizeof(double)));
-    int rc = run_swaps(e, chain, view, n, swaps, static_cast<double *>(e->result.p));
+    int rc = reserve_result(e, n);
+    if (rc == PF_OK) rc = run_swaps(e, chain, view, n, swaps, static_cast<double *>(e->result.p));
     if (rc) return rc;
     return fetch_result(e, lsum, n);
 }
@@ -2265,11 +2352,13 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     P.groups = reinterpret_cast<const EvalGroup *>(plan_dev);
     P.props = reinterpret_cast<const EvalProp *>(plan_dev + off_props);
     P.pub_src = nullptr; P.pub_dst = nullptr; P.pub_n = 0; P.pub_flag = nullptr; P.pub_seq = 0; P.pub_counter = nullptr;
-    if (e->pub_want > 0 && e->fused_publish && !e->comm.on && e->pub_want <= pf_engine::MAILBOX_MAX && ensure_mailbox(e)) {
+    P.pub_src2 = nullptr; P.pub_n2 = 0;
+    if (e->pub_want > 0 && e->fused_publish && !e->comm.on && e->pub_want + e->n_deferred <= pf_engine::MAILBOX_MAX && ensure_mailbox(e)) {
         if (!e->pubctr.p) { CU(e->pubctr.reserve(64)); CU(cudaMemsetAsync(e->pubctr.p, 0, 64, e->stream)); }
         P.pub_src = static_cast<const double *>(e->result.p);
         P.pub_dst = reinterpret_cast<double *>(e->d_mail + 8);
         P.pub_n = e->pub_want;
+        P.pub_src2 = static_cast<const double *>(e->deferred.p); P.pub_n2 = e->pub_armed_def = e->n_deferred;
         P.pub_flag = e->d_mail;
         P.pub_seq = e->pub_armed = ++e->mail_seq;
         P.pub_counter = static_cast<unsigned *>(e->pubctr.p);
@@ -2295,9 +2384,10 @@ extern "C" int pf_eval_batch(pf_engine *e, int32_t n, const int32_t *chains, con
     const int n_props = prop_begin[n];
     if (n_props > 0 && (!props || !lsum)) return fail(PF_EINVAL, "null argument");
     CU(cudaSetDevice(e->cfg.device));
-    CU(e->result.reserve((size_t)std::max(n_props, 1) * sizeof(double)));
+    int rc = reserve_result(e, n_props);
+    if (rc) return rc;
     e->pub_want = n_props;
-    int rc = run_evals(e, n, chains, kids, prop_begin, props, static_cast<double *>(e->result.p));
+    rc = run_evals(e, n, chains, kids, prop_begin, props, static_cast<double *>(e->result.p));
     e->pub_want = 0;
     if (rc) { e->pub_armed = 0; return rc; }
     return fetch_result(e, lsum, n_props);

@@ -650,6 +650,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_c
         if (s_pub) {
             __threadfence();
             for (int i = threadIdx.x; i < P.pub_n; i += blockDim.x) P.pub_dst[i] = __ldcg(P.pub_src + i);
+            for (int i = threadIdx.x; i < P.pub_n2; i += blockDim.x) P.pub_dst[P.pub_n + i] = __ldcg(P.pub_src2 + i);
             __threadfence_system();
             __syncthreads();
             if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned long long *>(P.pub_flag) = P.pub_seq; __threadfence_system(); }

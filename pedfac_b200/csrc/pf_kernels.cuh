@@ -188,6 +188,7 @@ struct EvalParams {
     // result vector (pub_n doubles at pub_src: a preceding sweep's ll_cc and this launch's sums) to the
     // host's mapped mailbox and raises its sequence flag — no publish launch
     const double *pub_src; double *pub_dst; int pub_n;
+    const double *pub_src2; int pub_n2;            // a second piece, appended (deferred swap results)
     unsigned long long *pub_flag, pub_seq;
     unsigned *pub_counter;
 };

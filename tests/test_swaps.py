@@ -197,3 +197,61 @@ def test_gpu_swaps_with_very_large_sibships():
         np.testing.assert_allclose(gpu.eval_swaps(view3, swaps), ora.eval_swaps(view3, swaps), rtol=1e-11, atol=1e-9)
         for i in np.flatnonzero(psc.ped.active)[::9]:
             np.testing.assert_allclose(gpu.get_stub(int(i)), ora.get_stub(int(i)), rtol=1e-12)
+
+
+def check_deferred_swaps(eng, sc, max_cases=6):
+    """pf_sweep_eval_swaps returns (ll_cc, lsum) of pf_sweep_eval at once and hands the swap values over
+    later — with the next call's results, or on request — identical to pf_eval_swaps."""
+    from pedfac_b200 import PF_PROP_TRIO
+    n = 0
+    for psc, swaps, only, labels in pruned_cases(sc):
+        psc.upload(eng)
+        view_all, _ = psc.ped.view(labels)
+        view3, _ = psc.ped.view(labels, only=only)
+        x = swaps[0][2]
+        others = [int(i) for i in np.flatnonzero(psc.ped.active) if labels[i] != labels[x]]
+        props = [(PF_PROP_TRIO, -1, -1, -1)] + [(PF_PROP_TRIO, c, -1, -1) for c in others[:9]]
+        pairs = [(PF_PROP_TRIO, a, b, -1) for a, b in zip(others[:5], others[5:10])]
+        ll0 = eng.sweep(view_all).copy()
+        l0 = eng.eval(x, props).copy()
+        want = eng.eval_swaps(view3, swaps).copy()
+        # (a) the next call carries the deferred values
+        ll1, l1 = eng.sweep_eval_swaps(view_all, x, props, view3, swaps)
+        np.testing.assert_array_equal(ll1, ll0); np.testing.assert_array_equal(l1, l0)
+        if pairs:
+            lp = eng.eval(x, pairs)
+            np.testing.assert_array_equal(lp, eng.eval(x, pairs))
+        np.testing.assert_array_equal(eng.deferred_results(len(swaps)), want)
+        # (b) nothing in between: delivered on request; no proposals in the first submission either
+        ll2, l2 = eng.sweep_eval_swaps(view_all, x, [], view3, swaps)
+        np.testing.assert_array_equal(ll2, ll0); assert len(l2) == 0
+        np.testing.assert_array_equal(eng.deferred_results(len(swaps)), want)
+        # (c) one set at a time, and the count has to match
+        eng.sweep_eval_swaps(view_all, x, props, view3, swaps)
+        with pytest.raises(RuntimeError):
+            eng.sweep_eval_swaps(view_all, x, props, view3, swaps)
+        with pytest.raises(RuntimeError):
+            eng.deferred_results(len(swaps) + 1)
+        np.testing.assert_array_equal(eng.deferred_results(len(swaps)), want)
+        # (d) no swaps: plain pf_sweep_eval
+        ll3, l3 = eng.sweep_eval_swaps(view_all, x, props, view3, [])
+        np.testing.assert_array_equal(l3, l0)
+        assert len(eng.deferred_results(0)) == 0
+        n += 1
+        if n >= max_cases:
+            break
+    return n
+
+
+def test_oracle_deferred_swap_values():
+    rng = np.random.default_rng(950)
+    sc = random_forest(rng, 60, 9, n_marr_target=34, max_kids=3, kinds=("hard", "dec16", "none"), max_comp=30)
+    assert check_deferred_swaps(make_oracle(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr), sc) >= 2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(2))
+def test_gpu_deferred_swap_values(seed):
+    rng = np.random.default_rng(960 + seed)
+    sc = random_forest(rng, 200, 130, n_marr_target=120, max_kids=4, kinds=("hard", "dec16", "f32", "none"), max_comp=90)
+    assert check_deferred_swaps(make_gpu(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr), sc) >= 2
