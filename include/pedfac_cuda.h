@@ -195,6 +195,12 @@ int pf_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_
 int pf_eval_swaps_dev(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t n,
                       const pf_swap *swaps, double *lsum_dev);
 
+/* Several lists of swap proposals in one submission (the multi-chain sampler: one list per chain that
+ * is at its swap block): list s is swaps[swap_begin[s] .. swap_begin[s+1]) on chain chains[s]
+ * (NULL = chain 0) and view views[s]; lsum is indexed like swaps. Values identical to pf_eval_swaps. */
+int pf_eval_swaps_batch(pf_engine *e, int32_t n_sets, const int32_t *chains, const pf_graph_view *views,
+                        const int32_t *swap_begin, const pf_swap *swaps, double *lsum);
+
 /* The whole first submission of a Gibbs step: pf_sweep_eval, and behind it the swap proposals of the
  * step (≙ the swap block of _EvalMoves@0x100015989-0x100016651, whose enumeration also depends on the
  * graph only) as in pf_eval_swaps on `swap_view`. ll_cc and lsum are returned as soon as the proposal

@@ -906,3 +906,17 @@ int pfo_deferred_results(pfo_engine *e, int32_t n, double *lsum_swaps)
     e->n_deferred = 0;
     return PF_OK;
 }
+
+int pfo_eval_swaps_batch(pfo_engine *e, int32_t n_sets, const int32_t *chains, const pf_graph_view *views,
+                         const int32_t *swap_begin, const pf_swap *swaps, double *lsum)
+{
+    if (!e || n_sets < 0 || (n_sets > 0 && (!views || !swap_begin))) FAIL(PF_EINVAL, "null argument");
+    for (int s = 0; s < n_sets; s++) {
+        const int n = swap_begin[s + 1] - swap_begin[s];
+        if (n < 0) FAIL(PF_EINVAL, "swap_begin not monotone");
+        if (n == 0) continue;
+        int rc = pfo_eval_swaps(e, chains ? chains[s] : 0, &views[s], n, swaps + swap_begin[s], lsum + swap_begin[s]);
+        if (rc != PF_OK) return rc;
+    }
+    return PF_OK;
+}

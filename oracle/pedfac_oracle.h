@@ -46,6 +46,8 @@ int pfo_sweep_eval(pfo_engine *e, int32_t chain, const pf_graph_view *view, doub
                    int32_t kid, int32_t n, const pf_proposal *props, double *lsum);
 int pfo_sweep_eval_swaps(pfo_engine *e, int32_t chain, const pf_graph_view *view, double *ll_cc, int32_t kid, int32_t n,
                          const pf_proposal *props, double *lsum, const pf_graph_view *swap_view, int32_t n_swaps, const pf_swap *swaps);
+int pfo_eval_swaps_batch(pfo_engine *e, int32_t n_sets, const int32_t *chains, const pf_graph_view *views,
+                         const int32_t *swap_begin, const pf_swap *swaps, double *lsum);
 int pfo_deferred_results(pfo_engine *e, int32_t n, double *lsum_swaps);
 int pfo_eval_swaps(pfo_engine *e, int32_t chain, const pf_graph_view *view, int32_t n,
                    const pf_swap *swaps, double *lsum);

@@ -56,7 +56,7 @@ EXPORTS = [
     "last_error", "create", "destroy", "set_stream", "set_locus_params", "set_genotypes_hard",
     "set_genotypes_soft", "set_genotypes_soft_f64", "set_genotypes_soft_dec16",
     "set_genotypes_unobserved", "sweep", "eval", "sweep_dev", "eval_dev", "sweep_batch",
-    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "io_bytes", "comm_local_handle", "comm_connect", "comm_reduce_count", "comm_set_async", "comm_fence", "sweep_eval_dev", "sweep_eval_swaps", "deferred_results", "profile", "profile_read", "plan_stats",
+    "eval_batch", "sweep_batch_dev", "eval_batch_dev", "sweep_eval", "eval_swaps", "eval_swaps_dev", "prefilter", "prefilter_scores_dev", "prefilter_topk_dev", "get_stub", "get_prong", "launch_count", "io_bytes", "comm_local_handle", "comm_connect", "comm_reduce_count", "comm_set_async", "comm_fence", "sweep_eval_dev", "sweep_eval_swaps", "deferred_results", "eval_swaps_batch", "profile", "profile_read", "plan_stats",
 ]
 
 
@@ -105,6 +105,7 @@ def bind(lib: C.CDLL, prefix: str) -> None:
     sig("comm_set_async", C.c_int, vp, C.c_int32)
     sig("comm_fence", C.c_int, vp)
     sig("sweep_eval_swaps", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), _f64p, C.c_int32, C.c_int32, vp, _f64p, C.POINTER(PfGraphView), C.c_int32, vp)
+    sig("eval_swaps_batch", C.c_int, vp, C.c_int32, _i32p, C.POINTER(PfGraphView), _i32p, vp, _f64p)
     sig("deferred_results", C.c_int, vp, C.c_int32, _f64p)
     sig("sweep_eval_dev", C.c_int, vp, C.c_int32, C.POINTER(PfGraphView), C.c_int32, C.c_int32, vp, vp)
     sig("plan_stats", C.c_int, vp, _i32p)
@@ -295,6 +296,18 @@ class CEngine:
         self._check(self._fn("eval_swaps")(self._h, chain, C.byref(view.struct), len(swaps),
                                            C.c_void_p(swaps.ctypes.data), ptr(out, _f64p)))
         return out[:len(swaps)]
+
+    def eval_swaps_batch(self, chains, views, swap_lists) -> np.ndarray:
+        """`pf_eval_swaps_batch`: one list of swaps per (chain, view); values concatenated in list order."""
+        chains = as_i32(chains)
+        arr = (PfGraphView * len(views))(*[v.struct for v in views])
+        lists = [make_swaps(s) for s in swap_lists]
+        begin = as_i32(np.concatenate([[0], np.cumsum([len(s) for s in lists])]))
+        allsw = np.concatenate(lists) if lists else make_swaps([])
+        out = np.empty(max(len(allsw), 1), dtype=np.float64)
+        self._check(self._fn("eval_swaps_batch")(self._h, len(views), ptr(chains, _i32p), arr, ptr(begin, _i32p),
+                                                 C.c_void_p(allsw.ctypes.data), ptr(out, _f64p)))
+        return out[:len(allsw)]
 
     def eval_swaps_dev(self, view: GraphView, swaps: np.ndarray, out_dev_ptr: int, chain: int = 0):
         self._check(self._fn("eval_swaps_dev")(self._h, chain, C.byref(view.struct), len(swaps),

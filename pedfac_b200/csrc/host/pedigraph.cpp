@@ -1802,7 +1802,8 @@ static void RunChains(Ped &p0, const Opts &o, long seed_a, long seed_b)
         f.s1 = rng::s1; f.s2 = rng::s2;
     }
     mc::active = true;
-    std::vector<int> idx, chains, kids, pb;
+    std::vector<int> idx, chains, kids, pb, sb;
+    std::vector<pf_swap> swaps;
     std::vector<pf_graph_view> views;
     std::vector<pf_proposal> props;
     std::vector<double> ll, lsum;
@@ -1856,11 +1857,23 @@ static void RunChains(Ped &p0, const Opts &o, long seed_a, long seed_b)
                 for (int j = 0; j < r.n; j++) r.lsum[j] = lsum[(size_t)pb[k] + j];
             }
         }
-        // swap proposals (a few per cent of the steps): per chain
+        // the swap blocks of this round as one batch
+        idx.clear(); chains.clear(); views.clear(); swaps.clear(); sb.assign(1, 0);
         for (int c = 0; c < C; c++) {
             mc::Req &r = mc::fibers[c].req;
             if (mc::fibers[c].done || r.kind != mc::SWAPS) continue;
-            r.rc = PFN(eval_swaps)(p0.eng, c, r.view, r.n, r.swaps, r.lsum);
+            idx.push_back(c); chains.push_back(c); views.push_back(*r.view);
+            swaps.insert(swaps.end(), r.swaps, r.swaps + r.n);
+            sb.push_back((int)swaps.size());
+        }
+        if (!idx.empty()) {
+            lsum.assign(swaps.size() + 1, 0.0);
+            const int rc = PFN(eval_swaps_batch)(p0.eng, (int)idx.size(), chains.data(), views.data(), sb.data(), swaps.data(), lsum.data());
+            for (size_t k = 0; k < idx.size(); k++) {
+                mc::Req &r = mc::fibers[idx[k]].req;
+                r.rc = rc;
+                for (int j = 0; j < r.n; j++) r.lsum[j] = lsum[(size_t)sb[k] + j];
+            }
         }
         for (int c = 0; c < C; c++)
             if (!mc::fibers[c].done && mc::fibers[c].req.kind == mc::EVAL && mc::fibers[c].req.n <= 0) mc::fibers[c].req.rc = PF_OK;

@@ -135,6 +135,7 @@ struct pf_engine {
     unsigned long long pub_armed = 0; // sequence number the eval kernel was armed with (0: fetch_result launches publish_kernel)
     bool eval_zero_copy = true;       // PF_EVAL_ZEROCOPY=0: copy the eval plan to device memory instead of reading the pinned buffer
     static constexpr size_t EVAL_ZERO_COPY_MAX = 16384;
+    int inline_kids = FAM2_INLINE_KIDS, chunk_kids = CHUNK2_KIDS;   // PF_INLINE_KIDS / PF_CHUNK_KIDS (measurement aid): how sibships are cut into tasks
     DevBuf pubctr;
     bool fused_publish = true;        // PF_FUSED_PUBLISH=0: always a separate publish launch
 
@@ -273,6 +274,8 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->sweep_clocks = getenv("PF_SWEEP_CLOCKS") != nullptr;
     if (const char *v2 = getenv("PF_SWEEP_V2")) e->sweep_v2 = v2[0] != '0';
     if (const char *v2 = getenv("PF_EVAL_SINGLES")) e->eval_singles = v2[0] != '0';
+    if (const char *v2 = getenv("PF_INLINE_KIDS")) e->inline_kids = std::min(FAM2_INLINE_KIDS, std::max(1, atoi(v2)));
+    if (const char *v2 = getenv("PF_CHUNK_KIDS")) e->chunk_kids = std::min(CHUNK2_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_EVAL_ZEROCOPY")) e->eval_zero_copy = v2[0] != '0';
     if (const char *v2 = getenv("PF_FUSED_PUBLISH")) e->fused_publish = v2[0] != '0';
     if (const char *fs = getenv("PF_SWEEP_SHAPE")) e->force_shape = fs[0] == 't' ? 2 : fs[0] == 'l' ? 1 : 0;
@@ -1031,10 +1034,10 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
             const int m = w.bfs_m[b];
             x2.up_m_row[m] = G.n_rows++;
             const int nk = x2.kid_off[m + 1] - x2.kid_off[m];
-            x2.n_inline[m] = std::min(nk, FAM2_INLINE_KIDS);
+            x2.n_inline[m] = std::min(nk, e->inline_kids);
             x2.chunk_off[m] = (int)x2.chunk_first.size();
-            for (int k0 = x2.n_inline[m]; k0 < nk; k0 += CHUNK2_KIDS) {
-                const int n = std::min(CHUNK2_KIDS, nk - k0);
+            for (int k0 = x2.n_inline[m]; k0 < nk; k0 += e->chunk_kids) {
+                const int n = std::min(e->chunk_kids, nk - k0);
                 x2.chunk_first.push_back(x2.kid_off[m] + k0); x2.chunk_n.push_back(n);
                 x2.chunk_row.push_back(G.n_rows); G.n_rows += 2;
                 x2.chunk_level.push_back(0);
@@ -2217,28 +2220,58 @@ static int build_swap_view(pf_engine *e, const pf_graph_view *b, const pf_swap &
     return PF_OK;
 }
 
-static int run_swaps(pf_engine *e, int chain, const pf_graph_view *view, int n, const pf_swap *swaps, double *out_dev)
+// n_sets lists of swap proposals, set s on chain chains[s] (null: chain 0) and view views[s]: one launch
+static int run_swap_sets(pf_engine *e, int n_sets, const int32_t *chains_in, const pf_graph_view *views, const int32_t *swap_begin,
+                         const pf_swap *swaps, double *out_dev)
 {
-    if (!e || !view || n < 0 || (n > 0 && !swaps)) return fail(PF_EINVAL, "null argument");
+    if (!e || n_sets < 0 || (n_sets > 0 && (!views || !swap_begin))) return fail(PF_EINVAL, "null argument");
+    const int n = n_sets > 0 ? swap_begin[n_sets] : 0;
+    if (n < 0 || (n > 0 && !swaps)) return fail(PF_EINVAL, "null argument");
     if (n == 0) return PF_OK;
-    if (view->n_indiv < 0 || view->n_marr < 0 || (view->n_indiv > 0 && (!view->indiv || !view->indiv_cc || !view->indiv_founder)) ||
-        (view->n_marr > 0 && (!view->marr || !view->marr_pa || !view->marr_ma || !view->marr_selfing || !view->marr_kid_begin)))
-        return fail(PF_EINVAL, "malformed view");
-    int rc = PF_OK, registered = 0;
     std::vector<HypoView> H(n);
     std::vector<pf_graph_view> hv(n);
-    std::vector<int32_t> chains(n, chain);
-    for (int i = 0; i < view->n_indiv; i++) {
-        const int slot = view->indiv[i];
-        if (slot < 0 || slot >= e->cfg.cap_indiv || e->loc[slot] != -1) { rc = fail(PF_EINVAL, "bad or duplicate individual slot %d in view", slot); break; }
-        e->loc[slot] = i; registered = i + 1;
+    std::vector<int32_t> chains(n, 0);
+    for (int s = 0; s < n_sets; s++) {
+        const pf_graph_view *view = &views[s];
+        const int chain = chains_in ? chains_in[s] : 0;
+        if (swap_begin[s + 1] < swap_begin[s]) return fail(PF_EINVAL, "swap_begin not monotone");
+        if (swap_begin[s + 1] == swap_begin[s]) continue;
+        if (view->n_indiv < 0 || view->n_marr < 0 || (view->n_indiv > 0 && (!view->indiv || !view->indiv_cc || !view->indiv_founder)) ||
+            (view->n_marr > 0 && (!view->marr || !view->marr_pa || !view->marr_ma || !view->marr_selfing || !view->marr_kid_begin)))
+            return fail(PF_EINVAL, "malformed view");
+        int rc = PF_OK, registered = 0;
+        for (int i = 0; i < view->n_indiv; i++) {
+            const int slot = view->indiv[i];
+            if (slot < 0 || slot >= e->cfg.cap_indiv || e->loc[slot] != -1) { rc = fail(PF_EINVAL, "bad or duplicate individual slot %d in view", slot); break; }
+            e->loc[slot] = i; registered = i + 1;
+        }
+        for (int q = swap_begin[s]; q < swap_begin[s + 1] && rc == PF_OK; q++) { rc = build_swap_view(e, view, swaps[q], q, H[q]); chains[q] = chain; }
+        for (int i = 0; i < registered; i++) e->loc[view->indiv[i]] = -1;
+        if (rc) return rc;
     }
-    for (int q = 0; q < n && rc == PF_OK; q++) rc = build_swap_view(e, view, swaps[q], q, H[q]);
-    for (int i = 0; i < registered; i++) e->loc[view->indiv[i]] = -1;
-    if (rc) return rc;
     for (int q = 0; q < n; q++) hv[q] = H[q].v;
     int n_out = 0;
     return run_sweeps(e, n, chains.data(), hv.data(), out_dev, &n_out, true);
+}
+
+static int run_swaps(pf_engine *e, int chain, const pf_graph_view *view, int n, const pf_swap *swaps, double *out_dev)
+{
+    if (!e || !view || n < 0 || (n > 0 && !swaps)) return fail(PF_EINVAL, "null argument");
+    const int32_t sb[2] = {0, n};
+    return run_swap_sets(e, 1, &chain, view, sb, swaps, out_dev);
+}
+
+extern "C" int pf_eval_swaps_batch(pf_engine *e, int32_t n_sets, const int32_t *chains, const pf_graph_view *views,
+                                   const int32_t *swap_begin, const pf_swap *swaps, double *lsum)
+{
+    if (!e || n_sets < 0 || (n_sets > 0 && !swap_begin)) return fail(PF_EINVAL, "null argument");
+    const int n = n_sets > 0 ? swap_begin[n_sets] : 0;
+    if (n > 0 && !lsum) return fail(PF_EINVAL, "null output");
+    CU(cudaSetDevice(e->cfg.device));
+    int rc = reserve_result(e, n);
+    if (rc == PF_OK) rc = run_swap_sets(e, n_sets, chains, views, swap_begin, swaps, static_cast<double *>(e->result.p));
+    if (rc) return rc;
+    return fetch_result(e, lsum, n);
 }
 
 extern "C" int pf_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *view, int32_t n, const pf_swap *swaps, double *lsum)

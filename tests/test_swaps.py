@@ -255,3 +255,36 @@ def test_gpu_deferred_swap_values(seed):
     rng = np.random.default_rng(960 + seed)
     sc = random_forest(rng, 200, 130, n_marr_target=120, max_kids=4, kinds=("hard", "dec16", "f32", "none"), max_comp=90)
     assert check_deferred_swaps(make_gpu(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr), sc) >= 2
+
+
+def check_swap_batch(eng, sc, max_sets=5):
+    """pf_eval_swaps_batch over several (view, swap list) sets == pf_eval_swaps set by set."""
+    sets = []
+    for psc, swaps, only, labels in pruned_cases(sc):
+        sets.append((psc, swaps, only, labels))
+        if len(sets) >= max_sets:
+            break
+    # all sets must be evaluated on one engine state: use the first pruned scenario's state for every set that
+    # is valid on it (same pedigree object => same prune), else singletons of each
+    psc, swaps, only, labels = sets[0]
+    psc.upload(eng)
+    eng.sweep(psc.ped.view(labels)[0])
+    view3, _ = psc.ped.view(labels, only=only)
+    one = eng.eval_swaps(view3, swaps)
+    got = eng.eval_swaps_batch([0, 0, 0], [view3, view3, view3], [swaps, [], swaps[:2]])
+    np.testing.assert_array_equal(got, np.concatenate([one, one[:2]]))
+    assert len(eng.eval_swaps_batch([], [], [])) == 0
+    return len(sets)
+
+
+def test_oracle_swap_batch():
+    rng = np.random.default_rng(950)
+    sc = random_forest(rng, 60, 9, n_marr_target=34, max_kids=3, kinds=("hard", "dec16", "none"), max_comp=30)
+    assert check_swap_batch(make_oracle(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr), sc) >= 1
+
+
+@pytest.mark.gpu
+def test_gpu_swap_batch():
+    rng = np.random.default_rng(951)
+    sc = random_forest(rng, 200, 130, n_marr_target=120, max_kids=4, kinds=("hard", "dec16", "f32", "none"), max_comp=90)
+    assert check_swap_batch(make_gpu(sc.S, sc.ped.cap_indiv, sc.ped.cap_marr), sc) >= 1
