@@ -135,6 +135,7 @@ struct pf_engine {
     unsigned long long pub_armed = 0; // sequence number the eval kernel was armed with (0: fetch_result launches publish_kernel)
     bool eval_zero_copy = true;       // PF_EVAL_ZEROCOPY=0: copy the eval plan to device memory instead of reading the pinned buffer
     static constexpr size_t EVAL_ZERO_COPY_MAX = 16384;
+    bool swap_sites = true;           // PF_SWAP_SITES=0: every swap proposal as a hypothetical component of its own
     int inline_kids = FAM2_INLINE_KIDS, chunk_kids = CHUNK2_KIDS;   // PF_INLINE_KIDS / PF_CHUNK_KIDS (measurement aid): how sibships are cut into tasks
     DevBuf pubctr;
     bool fused_publish = true;        // PF_FUSED_PUBLISH=0: always a separate publish launch
@@ -274,6 +275,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->sweep_clocks = getenv("PF_SWEEP_CLOCKS") != nullptr;
     if (const char *v2 = getenv("PF_SWEEP_V2")) e->sweep_v2 = v2[0] != '0';
     if (const char *v2 = getenv("PF_EVAL_SINGLES")) e->eval_singles = v2[0] != '0';
+    if (const char *v2 = getenv("PF_SWAP_SITES")) e->swap_sites = v2[0] != '0';
     if (const char *v2 = getenv("PF_INLINE_KIDS")) e->inline_kids = std::min(FAM2_INLINE_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_CHUNK_KIDS")) e->chunk_kids = std::min(CHUNK2_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_EVAL_ZEROCOPY")) e->eval_zero_copy = v2[0] != '0';
@@ -550,9 +552,17 @@ static thread_local ViewWork g_work;
 // The band offset is fixed up by the caller once every view has been added. While a group is
 // being filled, SweepGroup::task_end counts its tasks and n_rows / emis_count its transient rows
 // and genotype entries.
-static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan2 &plan, ViewWork &w, int &max_up_levels, bool up_only);
+// A swap site: the swap proposals of one Gibbs step that rewire the same two families (same x, z and
+// marriages). The view handed to the planner is the hypothetical component of the first of them, listed
+// with x first (the tree is rooted there, not at its centre) and with n_cc = the number of variants; the
+// others differ only in which of the four parents and which of the two sibships go to which family, i.e.
+// in the three family tasks next to the root: emit2 adds those per variant and shares everything below.
+struct SwapVariantSpec { int za, zb, xa, xb, move; };      // parent slots of z's and x's new family; siblings moved?
+struct SwapSite { int marr_x_slot = -1; std::vector<SwapVariantSpec> var; };
 
-static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only, const SweepShape &shape, int *loc = nullptr, Plan2 *plan2 = nullptr)
+static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan2 &plan, ViewWork &w, int &max_up_levels, bool up_only, const SwapSite *site);
+
+static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan &plan, int &max_up_levels, bool up_only, const SweepShape &shape, int *loc = nullptr, Plan2 *plan2 = nullptr, const SwapSite *site = nullptr)
 {
     if (!loc) loc = e->loc.data();
     if (!v) return fail(PF_EINVAL, "null view");
@@ -655,7 +665,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
             rc = bfs(r0, label);
             if (rc) goto cleanup;
             int r = r0;
-            if (w.bfs_m.size() - m_from >= 3) {
+            if (w.bfs_m.size() - m_from >= 3 && !site) {
                 // re-root at the centre of the tree: the number of levels is the tree's radius
                 // instead of up to its diameter. Two more traversals: farthest node from r0, then
                 // the farthest from that one; the centre is half way along that path.
@@ -676,7 +686,7 @@ static int plan_add_view(pf_engine *e, const pf_graph_view *v, int chain, int ou
         for (int m = 0; m < nM; m++)
             if (!w.vis_m[m]) { rc = fail(PF_EINVAL, "marriage %d not reachable", v->marr[m]); goto cleanup; }
         hp_mark(1);
-        if (plan2) { rc = emit2(e, v, chain, out_base, *plan2, w, max_up_levels, up_only); goto cleanup; }
+        if (plan2) { rc = emit2(e, v, chain, out_base, *plan2, w, max_up_levels, up_only, site); goto cleanup; }
         // heights of the FAMILY_UP tasks, children first (reverse BFS order)
         int up_levels = 0;
         for (int b = (int)w.bfs_m.size() - 1; b >= 0; b--) {
@@ -974,11 +984,12 @@ struct Work2 {
     std::vector<int> lvl2, up_m_row, dn_row, park_row, emis_idx, depth2, cnt_d, cnt_t, rows;
     std::vector<char> in_chunk;
     std::vector<uint32_t> rec;
+    std::vector<uint32_t> famup_off; std::vector<int> famup_len;      // where the FAMUP2 record of each marriage went (swap sites)
 };
 }
 static thread_local Work2 g_work2;
 
-static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan2 &plan, ViewWork &w, int &max_up_levels, bool up_only)
+static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, Plan2 &plan, ViewWork &w, int &max_up_levels, bool up_only, const SwapSite *site)
 {
     Work2 &x2 = g_work2;
     const int nI = v->n_indiv, nM = v->n_marr;
@@ -989,6 +1000,8 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
     x2.chunk_first.clear(); x2.chunk_n.clear(); x2.chunk_row.clear(); x2.chunk_level.clear();
     x2.lvl2.assign(nM, 0); x2.up_m_row.assign(nM, 0); x2.dn_row.assign(nI, -1); x2.park_row.assign(nM, -1); x2.emis_idx.assign(nI, -1);
     x2.depth2.assign(nM, 0); x2.in_chunk.assign(nI, 0);
+    if (site) { x2.famup_off.assign(nM, 0); x2.famup_len.assign(nM, 0); }
+    uint32_t root_off = 0; int root_len = 0;
     std::vector<uint32_t> &pool = plan.pool, &rec = x2.rec;
     auto n_marr_of = [&](int i) { return w.adj_off[i + 1] - w.adj_off[i]; };
     // kids of every marriage below it (the up individual excluded), kids with marriages of their own first
@@ -1163,6 +1176,7 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
         rec.push_back(up_only ? (uint32_t)G.n_rows++ : 0u);
         push_cmp(r, -1, -1);
         add_task(-1);
+        root_off = plan.tasks.back().off; root_len = plan.tasks.back().cost;
 
         for (size_t b = mb; b < me; b++) {
             const int m = w.bfs_m[b], u = w.um[m];
@@ -1189,6 +1203,7 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
             for (int j = 0; j < nki; j++) push_cmp(x2.kid_x[k0 + j], m, -1);
             push_pairs(m);
             add_task(x2.lvl2[m]);
+            if (site) { x2.famup_off[m] = plan.tasks.back().off; x2.famup_len[m] = plan.tasks.back().cost; }
             if (up_only) continue;
 
             const int l = x2.depth2[m];
@@ -1217,6 +1232,90 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
                 add_task(-(2 + l));
             }
         }
+        if (site && site->var.size() > 1) {
+            // the other variants of a swap site: three family tasks and a root each, put together from
+            // the operands of the first variant's records (which is the view itself)
+            const int mZ = nM - 2, mX = nM - 1;
+            int mx = -1;
+            for (int j = 0; j < nM - 2; j++) if (v->marr[j] == site->marr_x_slot) mx = j;
+            if (!up_only || w.roots.size() != 1 || nM < 3 || mx < 0 || w.um[mX] != r || w.um[mx] != r || w.urole[mZ] != 2 || w.urole[mX] != 2 ||
+                w.Ui[w.um[mZ]] != mx || w.urole[mx] > 1 || v->marr_selfing[mZ] || v->marr_selfing[mX] || v->marr_selfing[mx])
+                return fail(PF_EINVAL, "internal: malformed swap site");
+            const size_t pb = (size_t)G.pool_begin;
+            auto grab = [&](uint32_t off, int len) { return std::vector<uint32_t>(pool.begin() + pb + off, pool.begin() + pb + off + len); };
+            const std::vector<uint32_t> recZ = grab(x2.famup_off[mZ], x2.famup_len[mZ]), recX = grab(x2.famup_off[mX], x2.famup_len[mX]),
+                                        recx = grab(x2.famup_off[mx], x2.famup_len[mx]), recR = grab(root_off, root_len);
+            const SwapVariantSpec &v0 = site->var[0];
+            auto parent_cmp = [&](int slot) -> const uint32_t * {
+                if (slot == v0.za) return &recZ[2];
+                if (slot == v0.zb) return &recZ[2 + CMP_WORDS];
+                if (slot == v0.xa) return &recX[2];
+                if (slot == v0.xb) return &recX[2 + CMP_WORDS];
+                return nullptr;
+            };
+            bool bad = false;
+            // replaces row `from` by `to` among the rows of the cmp at rec[pos..pos+2]
+            auto swap_row = [&](std::vector<uint32_t> &rc2, int pos, uint32_t from, uint32_t to) {
+                uint32_t &w1 = rc2[pos + 1], &w2 = rc2[pos + 2];
+                if ((w1 & 0xffffu) == from) { w1 = (w1 & 0xffff0000u) | to; return; }
+                if ((w1 >> 16) == from) { w1 = (w1 & 0xffffu) | to << 16; return; }
+                if ((w2 & 0xffffu) == from) { w2 = (w2 & 0xffff0000u) | to; return; }
+                const uint32_t extra = w2 >> 16;
+                if (!extra) { bad = true; return; }
+                const uint32_t n_more = pool[pb + extra];
+                const uint32_t at = (uint32_t)(pool.size() - pb);
+                if (at > 0xffffu) { plan.fits = false; return; }
+                bool found = false;
+                pool.push_back(n_more);
+                for (uint32_t j = 0; j < n_more; j++) {
+                    uint32_t row = pool[pb + extra + 1 + j];
+                    if (row == from) { row = to; found = true; }
+                    pool.push_back(row);
+                }
+                if (!found) bad = true;
+                w2 = (w2 & 0xffffu) | at << 16;
+            };
+            const uint32_t gen = (recZ[0] | recX[0]) & T2_GENERAL;
+            const int Lf = std::max(x2.lvl2[mZ], x2.lvl2[mX]), Lx = std::max(x2.lvl2[mx], Lf + 1);
+            max_up_levels = std::max(max_up_levels, Lx + 1);
+            const int kids_at = 2 + 2 * CMP_WORDS;
+            for (size_t vi = 1; vi < site->var.size(); vi++) {
+                const SwapVariantSpec &sv = site->var[vi];
+                const bool same = (sv.move != 0) == (v0.move != 0);
+                const std::vector<uint32_t> &kz = same ? recZ : recX, &kx = same ? recX : recZ;      // whose sibship goes where
+                const uint32_t rowZ = (uint32_t)G.n_rows++, rowX = (uint32_t)G.n_rows++, rowx = (uint32_t)G.n_rows++;
+                const uint32_t *cza = parent_cmp(sv.za), *czb = parent_cmp(sv.zb), *cxa = parent_cmp(sv.xa), *cxb = parent_cmp(sv.xb);
+                if (!cza || !czb || !cxa || !cxb) return fail(PF_EINVAL, "internal: swap variant names an unknown parent");
+                auto family = [&](const std::vector<uint32_t> &kids, uint32_t dest, const uint32_t *ca, const uint32_t *cb) {
+                    rec.clear();
+                    rec.push_back(T2_FAMUP | (2u << 1) << 8 | (kids[0] & 0xffff0000u) | gen);      // the up individual is a kid; nk and np of the sibship
+                    rec.push_back(dest);
+                    rec.insert(rec.end(), ca, ca + CMP_WORDS);
+                    rec.insert(rec.end(), cb, cb + CMP_WORDS);
+                    rec.insert(rec.end(), kids.begin() + kids_at, kids.end());
+                    add_task(Lf);
+                };
+                family(kz, rowZ, cza, czb);
+                family(kx, rowX, cxa, cxb);
+                {
+                    std::vector<uint32_t> r2 = recx;
+                    r2[1] = rowx;
+                    swap_row(r2, w.urole[mx] == 0 ? 2 + CMP_WORDS : 2, recZ[1], rowZ);          // z is the parent that is not x
+                    rec = r2;
+                    add_task(Lx);
+                }
+                {
+                    std::vector<uint32_t> r2 = recR;
+                    r2[2] = (uint32_t)(out_base + (int)vi);
+                    r2[3] = ROW2_TRASH;
+                    swap_row(r2, 4, recX[1], rowX);
+                    swap_row(r2, 4, recx[1], rowx);
+                    rec = r2;
+                    add_task(-1);
+                }
+                if (bad) return fail(PF_EINVAL, "internal: swap site rows not found");
+            }
+        }
         G.pool_len = (int)pool.size() - G.pool_begin;
         hp_mark(4);
         if (G.n_rows >= 0xffff) plan.fits = false;
@@ -1230,7 +1329,7 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
 // limits: the caller then runs the first-generation kernel, which can spill rows.
 constexpr int PF2_FALLBACK = 1000;
 
-static int run_sweeps2(pf_engine *e, int n, const int32_t *chains, const pf_graph_view *views, double *out_dev, int *n_out_total, bool up_only)
+static int run_sweeps2(pf_engine *e, int n, const int32_t *chains, const pf_graph_view *views, double *out_dev, int *n_out_total, bool up_only, const SwapSite *sites = nullptr)
 {
     const int n_tiles = (e->Sl + TILE_LOCI - 1) / TILE_LOCI;
     const double t_begin = e->host_prof ? host_now() : 0.0;
@@ -1290,7 +1389,7 @@ static int run_sweeps2(pf_engine *e, int n, const int32_t *chains, const pf_grap
                 P.plan.format = plan.format;
                 const int i0 = (int)((long long)n * t / T), i1 = (int)((long long)n * (t + 1) / T);
                 for (int i = i0; i < i1 && P.rc == PF_OK; i++) {
-                    P.rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, bases[i], tl_dummy, P.max_up, up_only, SWEEP_LATENCY, tl_loc.data(), &P.plan);
+                    P.rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, bases[i], tl_dummy, P.max_up, up_only, SWEEP_LATENCY, tl_loc.data(), &P.plan, sites ? &sites[i] : nullptr);
                     if (P.rc) P.err = g_err;
                 }
             });
@@ -1310,7 +1409,7 @@ static int run_sweeps2(pf_engine *e, int n, const int32_t *chains, const pf_grap
         out_base = bases[n];
     } else {
         for (int i = 0; i < n; i++) {
-            int rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, dummy, max_up, up_only, SWEEP_LATENCY, nullptr, &plan);
+            int rc = plan_add_view(e, &views[i], chains ? chains[i] : 0, out_base, dummy, max_up, up_only, SWEEP_LATENCY, nullptr, &plan, sites ? &sites[i] : nullptr);
             if (rc) return rc;
             out_base += views[i].n_cc;
         }
@@ -2147,6 +2246,7 @@ struct HypoView {
     std::vector<int> indiv, icc, marr, mpa, mma, kb, kids;
     std::vector<uint8_t> founder, selfing;
     pf_graph_view v;
+    int paz = -1, maz = -1;             // z's parents in the base view
     void finish()
     {
         v.n_indiv = (int)indiv.size(); v.indiv = indiv.data(); v.indiv_cc = icc.data(); v.indiv_founder = founder.data();
@@ -2165,8 +2265,10 @@ static int build_swap_view(pf_engine *e, const pf_graph_view *b, const pf_swap &
     if (w.kind < 1 || w.kind > 3 || (w.kind == 3 && !w.move_kids)) return fail(PF_EINVAL, "swap %d: bad kind", q);
     auto in_set = [&](int l) { return l == lx || l == lp || l == lq; };
     H.indiv.clear(); H.icc.clear(); H.founder.clear(); H.marr.clear(); H.mpa.clear(); H.mma.clear(); H.selfing.clear(); H.kids.clear(); H.kb.assign(1, 0);
+    // x first: a swap site's tree is rooted at the first individual listed
+    H.indiv.push_back(w.x); H.icc.push_back(0); H.founder.push_back(b->indiv_founder[e->loc[w.x]]);
     for (int i = 0; i < b->n_indiv; i++)
-        if (in_set(b->indiv_cc[i])) { H.indiv.push_back(b->indiv[i]); H.icc.push_back(0); H.founder.push_back(b->indiv_founder[i]); }
+        if (in_set(b->indiv_cc[i]) && b->indiv[i] != w.x) { H.indiv.push_back(b->indiv[i]); H.icc.push_back(0); H.founder.push_back(b->indiv_founder[i]); }
     int paz = -1, maz = -1;
     bool have_z = false, have_x = false, have_0 = w.prev_marr == -1;
     std::vector<int> Kz, K0;
@@ -2216,8 +2318,17 @@ static int build_swap_view(pf_engine *e, const pf_graph_view *b, const pf_swap &
     };
     emit(w.marr_z, za, zb, kids_z, w.z);
     emit(w.prev_marr == -1 ? w.marr_z : w.prev_marr, xa, xb, kids_x, w.x);   // the slot only names a prong row, which an upward sweep never writes
+    H.paz = paz; H.maz = maz;
     H.finish();
     return PF_OK;
+}
+
+static SwapVariantSpec swap_variant(const pf_swap &w, int paz, int maz)
+{
+    const int P = w.prev_pa, Q = w.prev_ma;
+    if (w.kind == 1) return SwapVariantSpec{P, maz, paz, Q, w.move_kids};
+    if (w.kind == 2) return SwapVariantSpec{paz, Q, P, maz, w.move_kids};
+    return SwapVariantSpec{P, Q, paz, maz, w.move_kids};
 }
 
 // n_sets lists of swap proposals, set s on chain chains[s] (null: chain 0) and view views[s]: one launch
@@ -2231,6 +2342,11 @@ static int run_swap_sets(pf_engine *e, int n_sets, const int32_t *chains_in, con
     std::vector<HypoView> H(n);
     std::vector<pf_graph_view> hv(n);
     std::vector<int32_t> chains(n, 0);
+    std::vector<int> site_first;                 // swaps that start a site (a run of swaps on the same two families)
+    auto same_site = [](const pf_swap &a, const pf_swap &b) {
+        return a.x == b.x && a.z == b.z && a.marr_z == b.marr_z && a.marr_x == b.marr_x && a.prev_pa == b.prev_pa && a.prev_ma == b.prev_ma && a.prev_marr == b.prev_marr;
+    };
+    const bool use_sites = e->sweep_v2 && e->swap_sites;
     for (int s = 0; s < n_sets; s++) {
         const pf_graph_view *view = &views[s];
         const int chain = chains_in ? chains_in[s] : 0;
@@ -2245,12 +2361,55 @@ static int run_swap_sets(pf_engine *e, int n_sets, const int32_t *chains_in, con
             if (slot < 0 || slot >= e->cfg.cap_indiv || e->loc[slot] != -1) { rc = fail(PF_EINVAL, "bad or duplicate individual slot %d in view", slot); break; }
             e->loc[slot] = i; registered = i + 1;
         }
-        for (int q = swap_begin[s]; q < swap_begin[s + 1] && rc == PF_OK; q++) { rc = build_swap_view(e, view, swaps[q], q, H[q]); chains[q] = chain; }
+        for (int q = swap_begin[s]; q < swap_begin[s + 1] && rc == PF_OK; q++) {
+            chains[q] = chain;
+            if (use_sites && q > swap_begin[s] && same_site(swaps[q], swaps[q - 1])) {      // a variant of the site before it: only its arguments are checked
+                const pf_swap &sw = swaps[q];
+                if (sw.kind < 1 || sw.kind > 3 || (sw.kind == 3 && !sw.move_kids)) rc = fail(PF_EINVAL, "swap %d: bad kind", q);
+                continue;
+            }
+            rc = build_swap_view(e, view, swaps[q], q, H[q]);
+            site_first.push_back(q);
+        }
         for (int i = 0; i < registered; i++) e->loc[view->indiv[i]] = -1;
         if (rc) return rc;
     }
-    for (int q = 0; q < n; q++) hv[q] = H[q].v;
     int n_out = 0;
+    if (use_sites) {
+        const int ns = (int)site_first.size();
+        std::vector<SwapSite> sites(ns);
+        std::vector<pf_graph_view> sv(ns);
+        std::vector<int32_t> sc(ns);
+        for (int k = 0; k < ns; k++) {
+            const int q0 = site_first[k], q1 = k + 1 < ns ? site_first[k + 1] : n;
+            sites[k].marr_x_slot = swaps[q0].marr_x;
+            for (int q = q0; q < q1; q++) sites[k].var.push_back(swap_variant(swaps[q], H[q0].paz, H[q0].maz));
+            sv[k] = H[q0].v;
+            sv[k].n_cc = q1 - q0;                 // one output per variant
+            sc[k] = chains[q0];
+        }
+        int rc = sync_tables(e);
+        if (rc) return rc;
+        rc = run_sweeps2(e, ns, sc.data(), sv.data(), out_dev, &n_out, true, sites.data());
+        if (rc != PF2_FALLBACK) return rc;
+        e->sweeps_v1_fallback++;
+        // does not fit the compiled kernel: one view per swap through the first-generation kernel
+        std::vector<char> have(n, 0);
+        for (int q : site_first) have[q] = 1;
+        // rebuild the views of the variants (their base views are no longer registered: redo set by set)
+        for (int s = 0; s < n_sets; s++) {
+            const pf_graph_view *view = &views[s];
+            bool any = false;
+            for (int q = swap_begin[s]; q < swap_begin[s + 1]; q++) any = any || !have[q];
+            if (!any) continue;
+            for (int i = 0; i < view->n_indiv; i++) e->loc[view->indiv[i]] = i;
+            int rc2 = PF_OK;
+            for (int q = swap_begin[s]; q < swap_begin[s + 1] && rc2 == PF_OK; q++) if (!have[q]) rc2 = build_swap_view(e, view, swaps[q], q, H[q]);
+            for (int i = 0; i < view->n_indiv; i++) e->loc[view->indiv[i]] = -1;
+            if (rc2) return rc2;
+        }
+    }
+    for (int q = 0; q < n; q++) hv[q] = H[q].v;
     return run_sweeps(e, n, chains.data(), hv.data(), out_dev, &n_out, true);
 }
 
