@@ -331,6 +331,7 @@ def run_chain(data, S, device, chains=1):
         env = dict(os.environ, PEDFAC_STATS="1", PEDFAC_DEVICE=str(device))
         if chains > 1:
             env["PEDFAC_CHAINS"] = str(chains)
+            env.setdefault("PEDFAC_THREADS", str(max(1, min(8, (os.cpu_count() or 1) // 2, chains // 4))))
         t0 = time.perf_counter()
         r = subprocess.run([str(ROOT / "pedfac_b200" / "bin" / "pedigraph"), "-d", str(rd), "-n", str(n_iter), "-r", str(rd / "rand")],
                            capture_output=True, text=True, env=env)
@@ -348,7 +349,7 @@ def run_chain(data, S, device, chains=1):
             agg["chains"] = len(rows)
             st.append(agg)
         it = min(st[1:], key=lambda x: x["seconds"] / max(x["proposals"], 1))
-        return {"what": f"pedigraph -n {n_iter} via CLI + files" + (f", {chains} chains in one process (PEDFAC_CHAINS)" if chains > 1 else "") +
+        return {"what": f"pedigraph -n {n_iter} via CLI + files" + (f", {chains} chains in one process (PEDFAC_CHAINS) on {env.get('PEDFAC_THREADS')} scheduler threads (PEDFAC_THREADS)" if chains > 1 else "") +
                         "; iteration 1 = warm-up from all singletons, the fastest later iteration reported (all listed in timed_iterations)",
                 "timed_iterations": st[1:], "swap_proposals": it["swaps"], "swaps_picked": it["swaps_picked"], "chains": chains,
                 "gibbs_steps": it["steps"], "proposals": it["proposals"], "sweeps": it["sweeps"], "seconds": it["seconds"],

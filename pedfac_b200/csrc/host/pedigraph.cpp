@@ -43,6 +43,7 @@
 #include <unistd.h>
 #include <vector>
 #include <cstdarg>
+#include <thread>
 
 #define PF_CAT2(a, b) a##b
 #define PF_CAT(a, b) PF_CAT2(a, b)
@@ -56,7 +57,7 @@
 // generator 1 is ever current, so setall() reduces to loading the two seeds
 // (_setall@0x10002a2d8, _ignlgi@0x100029fa3, _ranf@0x10002b838, _genunf@0x10002e948, _genbet@0x10002accf).
 // stdout of the chains other than chain 0 (PEDFAC_CHAINS) is dropped: one program, one progress log
-static bool g_quiet = false;
+static thread_local bool g_quiet = false;   // per scheduler thread (PEDFAC_THREADS)
 static int out_printf(const char *fmt, ...)
 {
     if (g_quiet) return 0;
@@ -69,7 +70,7 @@ static int out_printf(const char *fmt, ...)
 #define printf out_printf
 
 namespace rng {
-static long s1 = 1234567890L, s2 = 123456789L;
+static thread_local long s1 = 1234567890L, s2 = 123456789L;   // one stream per scheduler thread; fibers swap theirs in and out
 static const long m1 = 2147483563L, m2 = 2147483399L, a1 = 40014L, a2 = 40692L;
 
 static void setall(long iseed1, long iseed2) { s1 = iseed1; s2 = iseed2; }
@@ -99,8 +100,8 @@ static float genbet(float aa, float bb)
 {
     const double expmax = 89.0;
     const float infnty = 1.0E38f;
-    static float olda = -1.0f, oldb = -1.0f;
-    static float result, a, alpha, b, beta, delta, gamma, k1, k2, r, s, t, u1, u2, v, w, y, z;
+    static thread_local float olda = -1.0f, oldb = -1.0f;
+    static thread_local float result, a, alpha, b, beta, delta, gamma, k1, k2, r, s, t, u1, u2, v, w, y, z;
     const bool qsame = olda == aa && oldb == bb;
     if (!qsame) {
         if (aa <= 0.0 || bb <= 0.0) {
@@ -214,7 +215,8 @@ struct Ped {
     // candidate lists by sex (0 unknown, 1 male, 2 female)
     std::vector<std::pair<int, double>> cand[3];
     PF_ENGINE_T *eng = nullptr;
-    int chain = 0;                                   // row block of this chain inside the engine (PEDFAC_CHAINS)
+    int chain = 0;                                   // row block of this chain inside its engine (PEDFAC_CHAINS)
+    int chain_id = 0;                                // its number among all chains of the run (seeds, output directory)
     FILE *fNode = nullptr, *fEdge = nullptr, *fPed = nullptr, *fGeno = nullptr, *fLL = nullptr;
     long n_proposals = 0, n_sweeps = 0, n_steps = 0, n_swaps = 0, n_swaps_picked = 0;
     bool underflow_warned = false; long underflow_steps = 0;
@@ -549,10 +551,11 @@ enum Kind { NONE = 0, SWEEP, EVAL, SWEEP_EVAL, SWAPS };
 struct Req { Kind kind = NONE; const pf_graph_view *view = nullptr; double *ll = nullptr; int kid = -1, n = 0;
              const pf_proposal *props = nullptr; double *lsum = nullptr; const pf_swap *swaps = nullptr; int rc = 0; };
 struct Fiber { ucontext_t ctx; void *stack = nullptr; Req req; bool done = false; long s1 = 0, s2 = 0; int chain = 0; };
-static bool active = false;
-static int current = -1;
-static std::vector<Fiber> fibers;
-static ucontext_t sched_ctx;
+// one scheduler per thread (PEDFAC_THREADS): its fibers are the chains base .. base + fibers.size() - 1
+static thread_local bool active = false;
+static thread_local int current = -1, base = 0;
+static thread_local std::vector<Fiber> fibers;
+static thread_local ucontext_t sched_ctx;
 
 static int post(const Req &r)
 {
@@ -1261,6 +1264,12 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
 // same moves. Rank 0 writes the output files and stdout; the others write under out/.shard<r>/.
 static int g_shard_rank = 0, g_shard_world = 1;
 static int g_n_chains = 1;               // PEDFAC_CHAINS: independent chains batched on this GPU
+static int g_n_threads = 1;              // PEDFAC_THREADS: scheduler threads the chains are dealt to, one engine each
+// what was uploaded to the first engine, kept to fill the engines of the other scheduler threads
+struct Upload { int slot, kind; std::vector<uint8_t> codes; std::vector<uint16_t> num; std::vector<double> lik; };
+static std::vector<Upload> g_uploads;
+static pf_config g_cfg;
+static int chains_of_thread(int t) { return (g_n_chains * (t + 1)) / g_n_threads - (g_n_chains * t) / g_n_threads; }
 static std::string g_shard_dir;          // where the ranks exchange their mailbox handles
 
 #ifndef PF_NO_COMM
@@ -1438,12 +1447,13 @@ static void ReadGeno(Ped &p, const std::string &path)
 
     pf_config cfg{};
     cfg.n_loci = p.S; cfg.locus_begin = 0; cfg.locus_end = p.S; cfg.cap_indiv = p.capIndiv; cfg.cap_marr = p.capMarr;
-    cfg.n_chains = g_n_chains; cfg.device = getenv("PEDFAC_DEVICE") ? atoi(getenv("PEDFAC_DEVICE")) : 0;
+    cfg.n_chains = chains_of_thread(0); cfg.device = getenv("PEDFAC_DEVICE") ? atoi(getenv("PEDFAC_DEVICE")) : 0;
     if (g_shard_world > 1) {                                  // this process owns one slice of the loci (see main)
         cfg.locus_begin = (int)((long long)p.S * g_shard_rank / g_shard_world);
         cfg.locus_end = (int)((long long)p.S * (g_shard_rank + 1) / g_shard_world);
         if (cfg.locus_end <= cfg.locus_begin) die("more GPU shards than loci");
     }
+    g_cfg = cfg;
     if (PFN(create)(&p.eng, &cfg) != PF_OK) die("cannot create the likelihood engine");
     ConnectShards(p);
     if (PFN(set_locus_params)(p.eng, p.eps.data(), p.afreq.data()) != PF_OK) die("set_locus_params");
@@ -1532,6 +1542,11 @@ static void ReadGeno(Ped &p, const std::string &path)
             else if (dec_ok) rc = PFN(set_genotypes_soft_dec16)(p.eng, slot, num.data(), 10000);
             else rc = PFN(set_genotypes_soft_f64)(p.eng, slot, lik.data());   // mixed rows: exact doubles
             if (rc != PF_OK) die("genotype upload failed");
+            if (g_n_threads > 1) {
+                Upload u; u.slot = slot; u.kind = !soft ? 0 : dec_ok ? 1 : 2;
+                if (u.kind == 0) u.codes = codes; else if (u.kind == 1) u.num = num; else u.lik = lik;
+                g_uploads.push_back(std::move(u));
+            }
         }
         row++;
     }
@@ -1725,8 +1740,8 @@ static void SampleLoop(Ped &p, const Opts &o)
             PFN(io_bytes)(p.eng, &h2d, &d2h);
             fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld swaps %ld swaps_picked %ld seconds %.6f h2d_bytes %llu d2h_bytes %llu chain %d\n", p.iter,
                     p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, p.n_swaps - swaps0, p.n_swaps_picked - picked0, now() - t_iter,
-                    (unsigned long long)(h2d - io0[0]), (unsigned long long)(d2h - io0[1]), p.chain);
-            if (p.chain == 0) fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view);
+                    (unsigned long long)(h2d - io0[0]), (unsigned long long)(d2h - io0[1]), p.chain_id);
+            if (p.chain_id == 0) fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view);
             p.t_sweep = p.t_eval = p.t_view = 0;
         }
     }
@@ -1738,12 +1753,13 @@ static void SampleLoop(Ped &p, const Opts &o)
 static std::vector<Ped> *g_peds = nullptr;
 static const Opts *g_opts = nullptr;
 
-static void fiber_entry(int c)
+static void fiber_entry(int c)                     // c: global chain number
 {
     SampleLoop((*g_peds)[c], *g_opts);
-    mc::fibers[c].done = true;
-    mc::fibers[c].req.kind = mc::NONE;
-    swapcontext(&mc::fibers[c].ctx, &mc::sched_ctx);
+    mc::Fiber &f = mc::fibers[c - mc::base];
+    f.done = true;
+    f.req.kind = mc::NONE;
+    swapcontext(&f.ctx, &mc::sched_ctx);
 }
 
 static bool open_outputs(Ped &p, const std::string &out)
@@ -1768,37 +1784,24 @@ static void copy_file_so_far(FILE *from, const std::string &path_from, FILE *to)
     }
 }
 
-// Runs C chains to the end. `p0` is chain 0, set up to the point where sampling starts (files read,
-// initial sweep and prefilter done); the other chains start as copies of it with their own row block in
-// the engine (everything dirty, so their first Gibbs step propagates it), RNG stream and output files
-// under out/chain<c>/.
-static void RunChains(Ped &p0, const Opts &o, long seed_a, long seed_b)
+// One scheduler: runs the chains c0 .. c1-1 (fibers of this thread) to the end on `eng`, batching the
+// requests of a round into one engine submission per kind.
+static void RunGroup(PF_ENGINE_T *eng, int c0, int c1, long seed_a, long seed_b)
 {
-    const int C = g_n_chains;
-    std::vector<Ped> peds(C);
-    peds[0] = p0;
-    const std::string out0 = o.dir + "/out";
-    for (int c = 1; c < C; c++) {
-        peds[c] = p0;
-        Ped &q = peds[c];
-        q.chain = c;
-        if (!open_outputs(q, out0 + "/chain" + std::to_string(c))) { fprintf(stderr, "cannot open output files of chain %d\n", c); exit(-1); }
-        copy_file_so_far(p0.fNode, out0 + "/historyNode.csv", q.fNode);
-        copy_file_so_far(p0.fEdge, out0 + "/historyEdge.csv", q.fEdge);
-        for (int k = 0; k < q.nCC; k++) mark_dirty(q, k);
-    }
-    g_peds = &peds; g_opts = &o;
+    const int C = c1 - c0;
+    mc::base = c0;
+    mc::fibers.clear();
     mc::fibers.resize(C);
     const size_t stack_bytes = (size_t)16 << 20;
-    for (int c = 0; c < C; c++) {
-        mc::Fiber &f = mc::fibers[c];
-        f.chain = c;
+    for (int k = 0; k < C; k++) {
+        mc::Fiber &f = mc::fibers[k];
+        f.chain = c0 + k;
         f.stack = mmap(nullptr, stack_bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
         if (f.stack == MAP_FAILED) { perror("mmap"); exit(-1); }
         getcontext(&f.ctx);
         f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = stack_bytes; f.ctx.uc_link = &mc::sched_ctx;
-        makecontext(&f.ctx, (void (*)())fiber_entry, 1, c);
-        rng::setall(seed_a + c, seed_b + c);
+        makecontext(&f.ctx, (void (*)())fiber_entry, 1, c0 + k);
+        rng::setall(seed_a + c0 + k, seed_b + c0 + k);
         f.s1 = rng::s1; f.s2 = rng::s2;
     }
     mc::active = true;
@@ -1809,31 +1812,31 @@ static void RunChains(Ped &p0, const Opts &o, long seed_a, long seed_b)
     std::vector<double> ll, lsum;
     for (;;) {
         int alive = 0;
-        for (int c = 0; c < C; c++) {
-            mc::Fiber &f = mc::fibers[c];
+        for (int k = 0; k < C; k++) {
+            mc::Fiber &f = mc::fibers[k];
             if (f.done) continue;
-            mc::current = c; g_quiet = c != 0;
+            mc::current = k; g_quiet = c0 + k != 0;
             rng::s1 = f.s1; rng::s2 = f.s2;
             swapcontext(&mc::sched_ctx, &f.ctx);
             f.s1 = rng::s1; f.s2 = rng::s2;
             if (!f.done) alive++;
         }
-        g_quiet = false;
+        g_quiet = c0 != 0;
         if (alive == 0) break;
         // the sweeps of this round (SWEEP and the sweep half of SWEEP_EVAL) as one batch
         idx.clear(); chains.clear(); views.clear();
         size_t n_ll = 0;
-        for (int c = 0; c < C; c++) {
-            mc::Req &r = mc::fibers[c].req;
-            if (mc::fibers[c].done || (r.kind != mc::SWEEP && r.kind != mc::SWEEP_EVAL)) continue;
-            idx.push_back(c); chains.push_back(c); views.push_back(*r.view); n_ll += (size_t)std::max(r.view->n_cc, 0);
+        for (int k = 0; k < C; k++) {
+            mc::Req &r = mc::fibers[k].req;
+            if (mc::fibers[k].done || (r.kind != mc::SWEEP && r.kind != mc::SWEEP_EVAL)) continue;
+            idx.push_back(k); chains.push_back(k); views.push_back(*r.view); n_ll += (size_t)std::max(r.view->n_cc, 0);
         }
         if (!idx.empty()) {
             ll.assign(n_ll + 1, 0.0);
-            const int rc = PFN(sweep_batch)(p0.eng, (int)idx.size(), chains.data(), views.data(), ll.data());
+            const int rc = PFN(sweep_batch)(eng, (int)idx.size(), chains.data(), views.data(), ll.data());
             size_t at = 0;
-            for (int c : idx) {
-                mc::Req &r = mc::fibers[c].req;
+            for (int k : idx) {
+                mc::Req &r = mc::fibers[k].req;
                 r.rc = rc;
                 for (int j = 0; j < r.view->n_cc; j++) r.ll[j] = ll[at + j];
                 at += (size_t)std::max(r.view->n_cc, 0);
@@ -1841,45 +1844,94 @@ static void RunChains(Ped &p0, const Opts &o, long seed_a, long seed_b)
         }
         // the proposal lists of this round (EVAL and the eval half of SWEEP_EVAL) as one batch
         idx.clear(); chains.clear(); kids.clear(); pb.assign(1, 0); props.clear();
-        for (int c = 0; c < C; c++) {
-            mc::Req &r = mc::fibers[c].req;
-            if (mc::fibers[c].done || (r.kind != mc::EVAL && r.kind != mc::SWEEP_EVAL) || r.n <= 0) continue;
-            idx.push_back(c); chains.push_back(c); kids.push_back(r.kid);
+        for (int k = 0; k < C; k++) {
+            mc::Req &r = mc::fibers[k].req;
+            if (mc::fibers[k].done || (r.kind != mc::EVAL && r.kind != mc::SWEEP_EVAL) || r.n <= 0) continue;
+            idx.push_back(k); chains.push_back(k); kids.push_back(r.kid);
             props.insert(props.end(), r.props, r.props + r.n);
             pb.push_back((int)props.size());
         }
         if (!idx.empty()) {
             lsum.assign(props.size() + 1, 0.0);
-            const int rc = PFN(eval_batch)(p0.eng, (int)idx.size(), chains.data(), kids.data(), pb.data(), props.data(), lsum.data());
-            for (size_t k = 0; k < idx.size(); k++) {
-                mc::Req &r = mc::fibers[idx[k]].req;
+            const int rc = PFN(eval_batch)(eng, (int)idx.size(), chains.data(), kids.data(), pb.data(), props.data(), lsum.data());
+            for (size_t q = 0; q < idx.size(); q++) {
+                mc::Req &r = mc::fibers[idx[q]].req;
                 if (rc != PF_OK) r.rc = rc;
-                for (int j = 0; j < r.n; j++) r.lsum[j] = lsum[(size_t)pb[k] + j];
+                for (int j = 0; j < r.n; j++) r.lsum[j] = lsum[(size_t)pb[q] + j];
             }
         }
         // the swap blocks of this round as one batch
         idx.clear(); chains.clear(); views.clear(); swaps.clear(); sb.assign(1, 0);
-        for (int c = 0; c < C; c++) {
-            mc::Req &r = mc::fibers[c].req;
-            if (mc::fibers[c].done || r.kind != mc::SWAPS) continue;
-            idx.push_back(c); chains.push_back(c); views.push_back(*r.view);
+        for (int k = 0; k < C; k++) {
+            mc::Req &r = mc::fibers[k].req;
+            if (mc::fibers[k].done || r.kind != mc::SWAPS) continue;
+            idx.push_back(k); chains.push_back(k); views.push_back(*r.view);
             swaps.insert(swaps.end(), r.swaps, r.swaps + r.n);
             sb.push_back((int)swaps.size());
         }
         if (!idx.empty()) {
             lsum.assign(swaps.size() + 1, 0.0);
-            const int rc = PFN(eval_swaps_batch)(p0.eng, (int)idx.size(), chains.data(), views.data(), sb.data(), swaps.data(), lsum.data());
-            for (size_t k = 0; k < idx.size(); k++) {
-                mc::Req &r = mc::fibers[idx[k]].req;
+            const int rc = PFN(eval_swaps_batch)(eng, (int)idx.size(), chains.data(), views.data(), sb.data(), swaps.data(), lsum.data());
+            for (size_t q = 0; q < idx.size(); q++) {
+                mc::Req &r = mc::fibers[idx[q]].req;
                 r.rc = rc;
-                for (int j = 0; j < r.n; j++) r.lsum[j] = lsum[(size_t)sb[k] + j];
+                for (int j = 0; j < r.n; j++) r.lsum[j] = lsum[(size_t)sb[q] + j];
             }
         }
-        for (int c = 0; c < C; c++)
-            if (!mc::fibers[c].done && mc::fibers[c].req.kind == mc::EVAL && mc::fibers[c].req.n <= 0) mc::fibers[c].req.rc = PF_OK;
+        for (int k = 0; k < C; k++)
+            if (!mc::fibers[k].done && mc::fibers[k].req.kind == mc::EVAL && mc::fibers[k].req.n <= 0) mc::fibers[k].req.rc = PF_OK;
     }
     mc::active = false;
+    for (int k = 0; k < C; k++) munmap(mc::fibers[k].stack, stack_bytes);
+    mc::fibers.clear();
+}
+
+// Runs all chains to the end. `p0` is chain 0, set up to the point where sampling starts (files read,
+// initial sweep and prefilter done); the other chains start as copies of it with their own row block in
+// an engine (everything dirty, so their first Gibbs step propagates it), RNG stream and output files
+// under out/chain<c>/. PEDFAC_THREADS=T deals the chains to T scheduler threads, each with an engine of
+// its own on the same GPU (the genotype tables are uploaded to each): host chain logic of one group
+// overlaps the kernels of the others.
+static void RunChains(Ped &p0, const Opts &o, long seed_a, long seed_b)
+{
+    const int C = g_n_chains, T = g_n_threads;
+    std::vector<PF_ENGINE_T *> eng(T, nullptr);
+    eng[0] = p0.eng;
+    for (int t = 1; t < T; t++) {
+        pf_config cfg = g_cfg;
+        cfg.n_chains = chains_of_thread(t);
+        if (PFN(create)(&eng[t], &cfg) != PF_OK) die("cannot create the likelihood engine of a scheduler thread");
+        if (PFN(set_locus_params)(eng[t], p0.eps.data(), p0.afreq.data()) != PF_OK) die("set_locus_params");
+        for (const Upload &u : g_uploads) {
+            const int rc = u.kind == 0 ? PFN(set_genotypes_hard)(eng[t], u.slot, u.codes.data())
+                         : u.kind == 1 ? PFN(set_genotypes_soft_dec16)(eng[t], u.slot, u.num.data(), 10000)
+                                       : PFN(set_genotypes_soft_f64)(eng[t], u.slot, u.lik.data());
+            if (rc != PF_OK) die("genotype upload failed");
+        }
+    }
+    g_uploads.clear(); g_uploads.shrink_to_fit();
+    std::vector<Ped> peds(C);
+    const std::string out0 = o.dir + "/out";
+    std::vector<int> first(T + 1, 0);
+    for (int t = 0; t < T; t++) first[t + 1] = first[t] + chains_of_thread(t);
+    for (int t = 0; t < T; t++)
+        for (int c = first[t]; c < first[t + 1]; c++) {
+            peds[c] = p0;
+            Ped &q = peds[c];
+            q.chain = c - first[t]; q.chain_id = c; q.eng = eng[t];
+            if (c == 0) continue;
+            if (!open_outputs(q, out0 + "/chain" + std::to_string(c))) { fprintf(stderr, "cannot open output files of chain %d\n", c); exit(-1); }
+            copy_file_so_far(p0.fNode, out0 + "/historyNode.csv", q.fNode);
+            copy_file_so_far(p0.fEdge, out0 + "/historyEdge.csv", q.fEdge);
+            for (int k = 0; k < q.nCC; k++) mark_dirty(q, k);
+        }
+    g_peds = &peds; g_opts = &o;
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; t++) th.emplace_back([&, t]() { RunGroup(eng[t], first[t], first[t + 1], seed_a, seed_b); });
+    RunGroup(eng[0], first[0], first[1], seed_a, seed_b);
+    for (auto &x : th) x.join();
     for (int c = 1; c < C; c++) { Ped &q = peds[c]; fclose(q.fEdge); fclose(q.fNode); fclose(q.fPed); fclose(q.fGeno); fclose(q.fLL); }
+    for (int t = 1; t < T; t++) PFN(destroy)(eng[t]);
     p0 = peds[0];
 }
 #endif
@@ -1919,6 +1971,7 @@ int main(int argc, char **argv)
         return rc;
     }
     if (getenv("PEDFAC_CHAINS") && atoi(getenv("PEDFAC_CHAINS")) > 1) g_n_chains = atoi(getenv("PEDFAC_CHAINS"));
+    if (getenv("PEDFAC_THREADS")) g_n_threads = std::max(1, std::min(atoi(getenv("PEDFAC_THREADS")), g_n_chains));
     g_shard_dir = o.dir + "/out";
     if (g_shard_rank > 0 && !freopen("/dev/null", "w", stdout)) return -1;
     Ped p;

@@ -271,16 +271,19 @@ def test_choice_survives_the_same_steps_trimming(tmp_path, case):
 
 
 @pytest.mark.gpu
-def test_gpu_chains_batched_in_one_process_equal_single_chain_runs(tmp_path):
+@pytest.mark.parametrize("threads", [1, 3])
+def test_gpu_chains_batched_in_one_process_equal_single_chain_runs(tmp_path, threads):
     """PEDFAC_CHAINS=C (BASELINE.json's last configuration at test size): C chains on one GPU, their
     likelihood calls batched into one launch per round. Chain c must sample exactly what a
-    single-chain run samples with the seeds (a + c, b + c); chain 0 keeps the unchanged file layout."""
+    single-chain run samples with the seeds (a + c, b + c); chain 0 keeps the unchanged file layout.
+    PEDFAC_THREADS deals the chains to scheduler threads with an engine each (here 3 threads for 4
+    chains: groups of 1, 1 and 2): same traces."""
     import os
     C = 4
     d = synth.simulate(160, 120, soft=True, seed=46)
     rd = tmp_path / "multi"
     frontend.write_run_dir(d, rd, seeds=(2590, 7579545))
-    r = run(GPU, rd, n_iter=3, env={"PEDFAC_CHAINS": str(C), "PEDFAC_STATS": "1"})
+    r = run(GPU, rd, n_iter=3, env={"PEDFAC_CHAINS": str(C), "PEDFAC_STATS": "1", "PEDFAC_THREADS": str(threads)})
     assert r.returncode == 0, r.stderr[-1500:]
     assert r.stdout.count(".. DONE") == 1 and "..2" in r.stdout          # one progress log: chain 0's
     assert sum(1 for l in r.stderr.splitlines() if l.startswith("pedigraph-stats")) == 3 * C
