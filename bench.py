@@ -331,7 +331,7 @@ def run_chain(data, S, device, chains=1):
         env = dict(os.environ, PEDFAC_STATS="1", PEDFAC_DEVICE=str(device))
         if chains > 1:
             env["PEDFAC_CHAINS"] = str(chains)
-            env.setdefault("PEDFAC_THREADS", str(max(1, min(8, (os.cpu_count() or 1) // 2, chains // 4))))
+            env.setdefault("PEDFAC_THREADS", str(max(1, min(12, cpu_count() - 4, chains // 4))))
         t0 = time.perf_counter()
         r = subprocess.run([str(ROOT / "pedfac_b200" / "bin" / "pedigraph"), "-d", str(rd), "-n", str(n_iter), "-r", str(rd / "rand")],
                            capture_output=True, text=True, env=env)

@@ -133,7 +133,8 @@ struct pf_engine {
     cudaEvent_t fetch_event = nullptr;
     int pub_want = 0;                 // set by a host-buffer entry point: doubles of the result vector the eval kernel should deliver itself
     unsigned long long pub_armed = 0; // sequence number the eval kernel was armed with (0: fetch_result launches publish_kernel)
-    bool eval_zero_copy = true;       // PF_EVAL_ZEROCOPY=0: copy the eval plan to device memory instead of reading the pinned buffer
+    bool eval_zero_copy = false;      // PF_EVAL_ZEROCOPY=1 (measurement aid): the kernel reads small eval plans from the pinned buffer. Off:
+                                      // in-kernel PCIe reads made the kernel 6 us longer on one box and 28 us longer on another
     static constexpr size_t EVAL_ZERO_COPY_MAX = 16384;
     bool swap_sites = true;           // PF_SWAP_SITES=0: every swap proposal as a hypothetical component of its own
     int inline_kids = FAM2_INLINE_KIDS, chunk_kids = CHUNK2_KIDS;   // PF_INLINE_KIDS / PF_CHUNK_KIDS (measurement aid): how sibships are cut into tasks
@@ -2533,8 +2534,8 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
         CU(e->counters.reserve((size_t)group_blocks * sizeof(unsigned) * 2));
         CU(cudaMemsetAsync(e->counters.p, 0, e->counters.cap, e->stream));
     }
-    // small proposal lists are read by the kernel straight from the pinned staging slot (one PCIe read
-    // per block instead of a copy engine launch in front of the kernel); large ones are copied
+    // the plan is copied to device memory in front of the kernel (PF_EVAL_ZEROCOPY=1: small lists are read
+    // by the kernel straight from the pinned staging slot instead)
     const bool zero_copy = e->eval_zero_copy && blob <= pf_engine::EVAL_ZERO_COPY_MAX;
     const char *plan_dev = static_cast<const char *>(zero_copy ? hp : e->plan.p);
     if (!zero_copy) CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
