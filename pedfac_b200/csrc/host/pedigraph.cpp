@@ -222,6 +222,7 @@ struct Ped {
     bool underflow_warned = false; long underflow_steps = 0;
     bool check = false;                              // PEDFAC_CHECK: verify every picked move against the next sweep
     std::vector<double> chll_data;
+    double t_prune = 0, t_moves = 0, t_pick = 0;     // seconds in _PruneIndiv, _EvalMoves (engine calls included), _AddObsFracPrior + _PickAndUpdate
     double t_sweep = 0, t_eval = 0, t_view = 0;      // seconds inside the engine calls / building views (PEDFAC_STATS)
 };
 
@@ -1190,7 +1191,9 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
 {
     static const bool dbg_calls = getenv("PEDFAC_DEBUG_CALLS") != nullptr;
     if (dbg_calls) fprintf(stderr, "call %d gen %d deg %d\n", id, p.indiv[id].gen, p.indiv[id].unobsDegree);
-    if (getenv("PEDFAC_DEBUG_STATE")) {                       // same format as oracle/macho_run.c's PEDFAC_REF_DUMP
+    static const bool dbg_state = getenv("PEDFAC_DEBUG_STATE") != nullptr, dbg_ll = getenv("PEDFAC_DEBUG_LL") != nullptr, dbg_step = getenv("PEDFAC_DEBUG") != nullptr;
+    static const char *dump_pre = getenv("PEDFAC_DUMP_PRE"), *dump_kid = getenv("PEDFAC_DUMP_KID");
+    if (dbg_state) {                                          // same format as oracle/macho_run.c's PEDFAC_REF_DUMP
         fprintf(stderr, "state before %d nCC %d\n", id, p.nCC);
         for (int i = 0; i < p.nIndivUsed; i++) {
             if (!p.indivActive[i]) continue;
@@ -1210,13 +1213,17 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
     if (!(p.indiv[id].unobsDegree <= p.maxUnobsLayer)) return;
     p.t++;
     p.n_steps++;
+    const double t_0 = now_s();
     PruneIndiv(p, id);
     if (p.check) CheckInvariants(p, "PruneIndiv", id);
+    const double t_1 = now_s();
     EvalMoves(p, o, id);                                       // runs the pending sweep together with its first batch
+    const double t_2 = now_s();
+    p.t_prune += t_1 - t_0; p.t_moves += t_2 - t_1;
     p.t++;
     if (p.check) p.chll_data = p.chll;
-    if (getenv("PEDFAC_DUMP_PRE") && getenv("PEDFAC_DUMP_KID") && atoi(getenv("PEDFAC_DUMP_KID")) == id) DumpState(p, getenv("PEDFAC_DUMP_PRE"));   // last visit wins
-    if (getenv("PEDFAC_DEBUG_LL")) {                          // same format as oracle/macho_run.c's PEDFAC_REF_DUMP_LL
+    if (dump_pre && dump_kid && atoi(dump_kid) == id) DumpState(p, dump_pre);   // last visit wins
+    if (dbg_ll) {                          // same format as oracle/macho_run.c's PEDFAC_REF_DUMP_LL
         fprintf(stderr, "choices kid %d n %zu\n", id, p.ch.size());
         for (size_t k = 0; k < p.ch.size(); k++)
             fprintf(stderr, "c %zu ids %d %d %d %d %.17g\n", k, p.ch[k].mnode, p.ch[k].pa, p.ch[k].ma, p.ch[k].selfing, p.chll[k]);
@@ -1224,7 +1231,8 @@ static void MCMC_sampling(Ped &p, const Opts &o, int id)
     AddObsFracPrior(p, id);
     const int dbg_prev[3] = {p.prev[0], p.prev[1], p.prev[2]};
     PickAndUpdate(p, id);
-    if (getenv("PEDFAC_DEBUG")) fprintf(stderr, "step iter %d kid %d prev %d %d %d -> new %d %d %d self %d picked %d kind %d\n", p.iter, id, dbg_prev[0], dbg_prev[1], dbg_prev[2], p.neu[0], p.neu[1], p.neu[2], p.neu[3], p.picked, p.picked >= 0 ? p.ch[p.picked].kind : -1);
+    p.t_pick += now_s() - t_2;
+    if (dbg_step) fprintf(stderr, "step iter %d kid %d prev %d %d %d -> new %d %d %d self %d picked %d kind %d\n", p.iter, id, dbg_prev[0], dbg_prev[1], dbg_prev[2], p.neu[0], p.neu[1], p.neu[2], p.neu[3], p.picked, p.picked >= 0 ? p.ch[p.picked].kind : -1);
     if (p.check) CheckInvariants(p, "PickAndUpdate", id);
     if (p.check && p.picked >= 0 && !p.ch.empty()) {
         // the log-likelihood a proposal was scored with is the total the pedigree has once the move
@@ -1741,8 +1749,8 @@ static void SampleLoop(Ped &p, const Opts &o)
             fprintf(stderr, "pedigraph-stats iter %d steps %ld proposals %ld sweeps %ld swaps %ld swaps_picked %ld seconds %.6f h2d_bytes %llu d2h_bytes %llu chain %d\n", p.iter,
                     p.n_steps - steps0, p.n_proposals - props0, p.n_sweeps - sweeps0, p.n_swaps - swaps0, p.n_swaps_picked - picked0, now() - t_iter,
                     (unsigned long long)(h2d - io0[0]), (unsigned long long)(d2h - io0[1]), p.chain_id);
-            if (p.chain_id == 0) fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view);
-            p.t_sweep = p.t_eval = p.t_view = 0;
+            if (p.chain_id == 0) fprintf(stderr, "pedigraph-time iter %d sweep_call %.6f eval_call %.6f view_build %.6f prune %.6f moves %.6f pick %.6f\n", p.iter, p.t_sweep, p.t_eval, p.t_view, p.t_prune, p.t_moves, p.t_pick);
+            p.t_sweep = p.t_eval = p.t_view = p.t_prune = p.t_moves = p.t_pick = 0;
         }
     }
 }
