@@ -104,3 +104,20 @@ def test_run_pedfac_end_to_end_on_the_cpu_build(tmp_path):
     assert tot > 10 and ok / tot > 0.85
     with pytest.raises(ValueError, match="observe.frac"):
         rp.run_pedfac(g, output_path=str(tmp_path), observe_frac=1.5, binary=REF)
+
+
+def test_min_age_only_changes_the_generation_column(tmp_path):
+    """R/renderGeno.R:226-238 writes no maxAge / minAge line: min.age and max.age act on the R side
+    only, through gen = floor((max year - year) / min.age). The sampler then sees generation units and
+    its own age window stays at the binary's defaults (1, 1)."""
+    p = tmp_path / "genotype.txt"
+    p.write_text(FIXTURE)
+    param = {"geno.path": p, "output.path": tmp_path, "observe.frac": 0.8, "max.unobs": 1, "max.gen": 0,
+             "min.age": 2, "max.age": 2, "geno.err": 0.02, "marker.path": ""}
+    rp.write_intermed_geno(param)
+    rows = [ln.split() for ln in (tmp_path / "geno.txt").read_text().splitlines()]
+    assert [r[3] for r in rows] == ["1", "1", "1", "0", "0"]                    # floor((1990 - year) / 2)
+    keys = [ln.split(" ", 1)[0] for ln in (tmp_path / "prior.txt").read_text().splitlines()]
+    assert "maxAge" not in keys and "minAge" not in keys
+    prior = dict(ln.split(" ", 1) for ln in (tmp_path / "prior.txt").read_text().splitlines())
+    assert prior["nGen"] == "2"
