@@ -201,6 +201,8 @@ struct Ped {
     std::vector<char> indivActive, marrActive;
     std::vector<int> cc, ccDirty;
     int nCC = 0, nDirty = 0;
+    std::vector<std::vector<int>> ccMem;             // the active individuals of every component label (kept from CheckPed on): the
+                                                     // reference scans all individuals wherever this is walked
     std::vector<double> LLcc;
     double LLtot = 0;
     std::vector<int> freeIndiv, freeMarr;
@@ -264,12 +266,13 @@ static void mark_dirty(Ped &p, int label)
 static void label_component(Ped &p, int start, int label)
 {
     std::vector<int> stack{start};
-    p.cc[start] = label;
+    std::vector<int> &mem = p.ccMem[label];
+    p.cc[start] = label; mem.push_back(start);
     while (!stack.empty()) {
         const int i = stack.back(); stack.pop_back();
         for (int m : p.indiv[i].M) {
             const Marr &mm = p.marr[m];
-            auto visit = [&](int y) { if (p.cc[y] != label) { p.cc[y] = label; stack.push_back(y); } };
+            auto visit = [&](int y) { if (p.cc[y] != label) { p.cc[y] = label; mem.push_back(y); stack.push_back(y); } };
             visit(mm.pa);
             if (!mm.selfing) visit(mm.ma);
             for (int k : mm.kids) visit(k);
@@ -281,24 +284,25 @@ static void label_component(Ped &p, int start, int label)
 static void UpdateConComp(Ped &p, int id)
 {
     const int old = p.cc[id];
-    bool any = false;
-    for (int i = 0; i < p.nIndivUsed; i++)
-        if (p.indivActive[i] && p.cc[i] == old) { p.cc[i] = -5; any = true; }
-    if (!any) {
+    std::vector<int> mem;
+    mem.swap(p.ccMem[old]);
+    for (int i : mem) p.cc[i] = -5;
+    if (mem.empty()) {
         if (p.ccDirty[old] == 1) p.nDirty--;
         p.ccDirty[old] = 0;
         if (p.nCC - 1 != old) {
-            for (int i = 0; i < p.nIndivUsed; i++)
-                if (p.indivActive[i] && p.cc[i] == p.nCC - 1) p.cc[i] = old;
+            p.ccMem[old].swap(p.ccMem[p.nCC - 1]);
+            for (int i : p.ccMem[old]) p.cc[i] = old;
             if (p.ccDirty[p.nCC - 1] == 1) { p.ccDirty[old] = 1; p.ccDirty[p.nCC - 1] = 0; }
             p.LLcc[old] = p.LLcc[p.nCC - 1];
         }
         p.nCC--;
         return;
     }
+    std::sort(mem.begin(), mem.end());                  // the reference's scan order: by slot
     int found = 0, label = old;
-    for (int i = 0; i < p.nIndivUsed; i++) {
-        if (!p.indivActive[i] || p.cc[i] != -5) continue;
+    for (int i : mem) {
+        if (p.cc[i] != -5) continue;
         label_component(p, i, label);
         found++;
         if (found == 1) {
@@ -321,11 +325,11 @@ static void AssignConComp(Ped &p, int a, int b)
         if (p.ccDirty[lo] == 1) p.nDirty--;
         p.ccDirty[lo] = 1; p.ccDirty[hi] = 0;
     }
-    for (int i = 0; i < p.nIndivUsed; i++)
-        if (p.indivActive[i] && p.cc[i] == hi) p.cc[i] = lo;
+    for (int i : p.ccMem[hi]) { p.cc[i] = lo; p.ccMem[lo].push_back(i); }
+    p.ccMem[hi].clear();
     if (p.nCC - 1 != hi) {
-        for (int i = 0; i < p.nIndivUsed; i++)
-            if (p.indivActive[i] && p.cc[i] == p.nCC - 1) p.cc[i] = hi;
+        p.ccMem[hi].swap(p.ccMem[p.nCC - 1]);
+        for (int i : p.ccMem[hi]) p.cc[i] = hi;
         if (p.ccDirty[p.nCC - 1] == 1) { p.ccDirty[hi] = 1; p.ccDirty[p.nCC - 1] = 0; }
         p.LLcc[hi] = p.LLcc[p.nCC - 1];
     }
@@ -431,6 +435,10 @@ static void TrimPed(Ped &p, int x)
     if (ix.M.size() > 1) return;
     if (ix.M.size() == 1 && ix.edge[0] < 2) return;
     p.indivActive[x] = 0;
+    if (p.cc[x] >= 0) {
+        std::vector<int> &mem = p.ccMem[p.cc[x]];
+        for (size_t k = 0; k < mem.size(); k++) if (mem[k] == x) { mem[k] = mem.back(); mem.pop_back(); break; }
+    }
     ix.queued = false;
     p.freeIndiv.push_back(x);
     p.nIndivPerGen[ix.gen]--;
@@ -482,12 +490,18 @@ static void build_view(Ped &p, const std::vector<char> &want, ViewBuf &b)
     std::vector<int> local(p.nCC, -1);
     for (int c = 0; c < p.nCC; c++)
         if (want[c]) { local[c] = (int)b.labels.size(); b.labels.push_back(c); }
-    for (int i = 0; i < p.nIndivUsed; i++) {
-        if (!p.indivActive[i] || local[p.cc[i]] < 0) continue;
-        b.indiv.push_back(i); b.icc.push_back(local[p.cc[i]]); b.founder.push_back(p.indiv[i].founder ? 1 : 0);
+    // individuals and marriages in slot order, as the reference's scans list them
+    for (int c : b.labels) b.indiv.insert(b.indiv.end(), p.ccMem[c].begin(), p.ccMem[c].end());
+    std::sort(b.indiv.begin(), b.indiv.end());
+    for (int i : b.indiv) {
+        b.icc.push_back(local[p.cc[i]]); b.founder.push_back(p.indiv[i].founder ? 1 : 0);
+        for (int m : p.indiv[i].M) if (p.marr[m].pa == i && p.marrActive[m]) b.marr.push_back(m);
     }
-    for (int m = 0; m < p.nMarrUsed; m++) {
-        if (!p.marrActive[m] || local[p.cc[p.marr[m].pa]] < 0) continue;
+    std::sort(b.marr.begin(), b.marr.end());
+    b.marr.erase(std::unique(b.marr.begin(), b.marr.end()), b.marr.end());
+    const std::vector<int> ms = b.marr;
+    b.marr.clear();
+    for (int m : ms) {
         const Marr &mm = p.marr[m];
         b.marr.push_back(m); b.mpa.push_back(mm.pa); b.mma.push_back(mm.ma); b.selfing.push_back(mm.selfing ? 1 : 0);
         b.kids.insert(b.kids.end(), mm.kids.begin(), mm.kids.end());
@@ -938,6 +952,7 @@ static void AttachUnobsIndiv(Ped &p, int slot, int kid, int m, int edge)
     x.userID = p.maxID + slot;
     p.indivActive[slot] = 1;
     p.cc[slot] = p.cc[kid];
+    if (p.cc[slot] >= 0) p.ccMem[p.cc[slot]].push_back(slot);
     x.M = {m}; x.edge = {edge};
 }
 
@@ -1184,6 +1199,14 @@ static void CheckInvariants(Ped &p, const char *where, int id)
             if (x != i) bad("edge index does not point back", i, m);
         }
     }
+    // the member lists hold exactly the active individuals of every label
+    long listed = 0, active = 0;
+    for (int c = 0; c < (int)p.ccMem.size(); c++) {
+        if (c >= p.nCC && !p.ccMem[c].empty()) bad("members listed under a retired label", c, (int)p.ccMem[c].size());
+        for (int i : p.ccMem[c]) { if (!p.indivActive[i] || p.cc[i] != c) bad("stale entry in a component's member list", c, i); listed++; }
+    }
+    for (int i = 0; i < p.nIndivUsed; i++) active += p.indivActive[i] ? 1 : 0;
+    if (listed != active) bad("member lists and active individuals differ in number", (int)listed, (int)active);
 }
 
 // _MCMC_sampling@0x100019ec0
@@ -1604,6 +1627,7 @@ static void ReadMarriages(Ped &p, const std::string &path)
 static void CheckPed(Ped &p)
 {
     p.nCC = 0; p.nDirty = 0;
+    p.ccMem.assign(p.capIndiv + 2, {});
     for (int i = 0; i < p.nIndivUsed; i++) {
         if (!p.indivActive[i] || p.cc[i] != -1) continue;
         label_component(p, i, p.nCC);
