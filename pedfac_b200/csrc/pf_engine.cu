@@ -136,6 +136,7 @@ struct pf_engine {
     bool eval_zero_copy = false;      // PF_EVAL_ZEROCOPY=1 (measurement aid): the kernel reads small eval plans from the pinned buffer. Off:
                                       // in-kernel PCIe reads made the kernel 6 us longer on one box and 28 us longer on another
     static constexpr size_t EVAL_ZERO_COPY_MAX = 16384;
+    int eval_min_chunk = PF_EVAL_MIN_CHUNK;   // PF_EVAL_MIN_CHUNK (measurement aid): fewest loci per proposal-kernel chunk
     bool swap_sites = true;           // PF_SWAP_SITES=0: every swap proposal as a hypothetical component of its own
     int inline_kids = FAM2_INLINE_KIDS, chunk_kids = CHUNK2_KIDS;   // PF_INLINE_KIDS / PF_CHUNK_KIDS (measurement aid): how sibships are cut into tasks
     DevBuf pubctr;
@@ -276,6 +277,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     e->sweep_clocks = getenv("PF_SWEEP_CLOCKS") != nullptr;
     if (const char *v2 = getenv("PF_SWEEP_V2")) e->sweep_v2 = v2[0] != '0';
     if (const char *v2 = getenv("PF_EVAL_SINGLES")) e->eval_singles = v2[0] != '0';
+    if (const char *v2 = getenv("PF_EVAL_MIN_CHUNK")) e->eval_min_chunk = std::max(32, atoi(v2) / 32 * 32);
     if (const char *v2 = getenv("PF_SWAP_SITES")) e->swap_sites = v2[0] != '0';
     if (const char *v2 = getenv("PF_INLINE_KIDS")) e->inline_kids = std::min(FAM2_INLINE_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_CHUNK_KIDS")) e->chunk_kids = std::min(CHUNK2_KIDS, std::max(1, atoi(v2)));
@@ -1515,8 +1517,13 @@ static int run_sweeps2(pf_engine *e, int n, const int32_t *chains, const pf_grap
     CU(e->partial.reserve((size_t)n_tiles * std::max(out_base, 1) * sizeof(double)));
     CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream)); e->io_h2d += blob;
     CU(e->staging.mark(slot, e->stream));
-    // a component label without individuals has no ROOT task: its sum is 0, as in the oracle
-    CU(cudaMemsetAsync(e->partial.p, 0, (size_t)n_tiles * out_base * sizeof(double), e->stream));
+    // a component label without individuals has no ROOT task: its sum is 0, as in the oracle. Otherwise
+    // every partial sum is written by its ROOT task and the memset (a launch on the critical path) is not needed
+    {
+        int n_roots = 0;
+        for (auto &t : plan.tasks) n_roots += (plan.pool[(size_t)plan.groups[t.group].pool_begin + t.off] & 0xffu) == T2_ROOT ? 1 : 0;
+        if (n_roots != out_base) CU(cudaMemsetAsync(e->partial.p, 0, (size_t)n_tiles * out_base * sizeof(double), e->stream));
+    }
 
     Sweep2Params P;
     P.D = dev_view(e);
@@ -2518,7 +2525,7 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     // least 4 lane-iterations per chunk, at most 128 (the running mantissa product needs
     // renormalising only every 512 factors)
     const int group_blocks = (n_groups + EVAL_WARPS - 1) / EVAL_WARPS;
-    const int max_chunks = std::max(1, (e->Sl + PF_EVAL_MIN_CHUNK - 1) / PF_EVAL_MIN_CHUNK);
+    const int max_chunks = std::max(1, (e->Sl + e->eval_min_chunk - 1) / e->eval_min_chunk);
     if (e->eval_capacity <= 0) e->eval_capacity = eval_resident_blocks();
     const int waves = (group_blocks + e->eval_capacity - 1) / e->eval_capacity;    // > 1 only for huge proposal lists
     int n_chunks = std::max(1, std::min(max_chunks, waves * e->eval_capacity / group_blocks));
