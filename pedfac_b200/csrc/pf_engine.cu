@@ -139,7 +139,8 @@ struct pf_engine {
     int eval_min_chunk = PF_EVAL_MIN_CHUNK;   // PF_EVAL_MIN_CHUNK (measurement aid): fewest loci per proposal-kernel chunk
     bool swap_sites = true;           // PF_SWAP_SITES=0: every swap proposal as a hypothetical component of its own
     int inline_kids = FAM2_INLINE_KIDS, chunk_kids = CHUNK2_KIDS;   // PF_INLINE_KIDS / PF_CHUNK_KIDS (measurement aid): how sibships are cut into tasks
-    DevBuf pubctr;
+    DevBuf pubctr; bool pubctr_stale = true;
+    bool eval_inline = true;          // PF_EVAL_INLINE=0: always copy the eval plan to device memory
     bool fused_publish = true;        // PF_FUSED_PUBLISH=0: always a separate publish launch
 
     // locus shards on several GPUs (pf_comm_*): peer-mapped mailboxes for the cross-GPU sum (xreduce_kernel)
@@ -282,6 +283,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     if (const char *v2 = getenv("PF_INLINE_KIDS")) e->inline_kids = std::min(FAM2_INLINE_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_CHUNK_KIDS")) e->chunk_kids = std::min(CHUNK2_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_EVAL_ZEROCOPY")) e->eval_zero_copy = v2[0] != '0';
+    if (const char *v2 = getenv("PF_EVAL_INLINE")) e->eval_inline = v2[0] != '0';
     if (const char *v2 = getenv("PF_FUSED_PUBLISH")) e->fused_publish = v2[0] != '0';
     if (const char *fs = getenv("PF_SWEEP_SHAPE")) e->force_shape = fs[0] == 't' ? 2 : fs[0] == 'l' ? 1 : 0;
     *out = e;
@@ -2086,6 +2088,10 @@ static int fetch_end(pf_engine *e, const Fetch &f, double *host_out, int n1, dou
             }
         }
         __atomic_thread_fence(__ATOMIC_ACQUIRE);
+        if (*flag != f.seq) {                              // the stream is idle and nobody delivered: never hand out stale values
+            e->pubctr_stale = true;
+            return fail(PF_ECUDA, "internal: the results of this call were not delivered (mailbox sequence %llu, expected %llu)", (unsigned long long)*flag, f.seq);
+        }
         if (e->host_prof && e->n_prof_calls > 100) e->t_wait += host_now() - t_w0;
         vals = reinterpret_cast<const double *>(e->h_mail + 8);
     } else {
@@ -2180,7 +2186,7 @@ static int sweep_eval_swaps(pf_engine *e, int32_t chain, const pf_graph_view *vi
         e->pub_want = n_out + n;          // the eval kernel delivers [ll_cc | lsum] itself
         rc = run_evals(e, 1, &chain, &kid, pb, props, static_cast<double *>(e->result.p) + n_out);
         e->pub_want = 0;
-        if (rc) { e->pub_armed = 0; return rc; }
+        if (rc) { e->pub_armed = 0; e->pubctr_stale = true; return rc; }
     }
     Fetch f;
     rc = fetch_begin(e, n_out + n, f);
@@ -2543,9 +2549,11 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     }
     // the plan is copied to device memory in front of the kernel (PF_EVAL_ZEROCOPY=1: small lists are read
     // by the kernel straight from the pinned staging slot instead)
-    const bool zero_copy = e->eval_zero_copy && blob <= pf_engine::EVAL_ZERO_COPY_MAX;
+    // small plans travel in the kernel's parameter space (launch_eval_inline): nothing to copy
+    const bool inline_plan = e->eval_inline && blob <= (size_t)EVAL_INLINE_MAX;
+    const bool zero_copy = !inline_plan && e->eval_zero_copy && blob <= pf_engine::EVAL_ZERO_COPY_MAX;
     const char *plan_dev = static_cast<const char *>(zero_copy ? hp : e->plan.p);
-    if (!zero_copy) CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
+    if (!zero_copy && !inline_plan) CU(cudaMemcpyAsync(e->plan.p, hp, blob, cudaMemcpyHostToDevice, e->stream));
     e->io_h2d += blob;
     EvalParams P;
     P.D = dev_view(e);
@@ -2554,7 +2562,8 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     P.pub_src = nullptr; P.pub_dst = nullptr; P.pub_n = 0; P.pub_flag = nullptr; P.pub_seq = 0; P.pub_counter = nullptr;
     P.pub_src2 = nullptr; P.pub_n2 = 0;
     if (e->pub_want > 0 && e->fused_publish && !e->comm.on && e->pub_want + e->n_deferred <= pf_engine::MAILBOX_MAX && ensure_mailbox(e)) {
-        if (!e->pubctr.p) { CU(e->pubctr.reserve(64)); CU(cudaMemsetAsync(e->pubctr.p, 0, 64, e->stream)); }
+        if (!e->pubctr.p) { CU(e->pubctr.reserve(64)); e->pubctr_stale = true; }
+        if (e->pubctr_stale) { CU(cudaMemsetAsync(e->pubctr.p, 0, 64, e->stream)); e->pubctr_stale = false; }   // after a failed call the arrival counter may be anywhere
         P.pub_src = static_cast<const double *>(e->result.p);
         P.pub_dst = reinterpret_cast<double *>(e->d_mail + 8);
         P.pub_n = e->pub_want;
@@ -2568,7 +2577,7 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     P.out = out_dev;
     P.counters = static_cast<unsigned *>(e->counters.p);
     e->prof_begin(1);
-    launch_eval(P, n_chunks, e->stream);
+    if (!inline_plan || !launch_eval_inline(P, hp, blob, off_props, n_chunks, e->stream)) launch_eval(P, n_chunks, e->stream);
     e->prof_end();
     e->launches++;
     CU(e->staging.mark(slot, e->stream));
@@ -2589,7 +2598,7 @@ extern "C" int pf_eval_batch(pf_engine *e, int32_t n, const int32_t *chains, con
     e->pub_want = n_props;
     rc = run_evals(e, n, chains, kids, prop_begin, props, static_cast<double *>(e->result.p));
     e->pub_want = 0;
-    if (rc) { e->pub_armed = 0; return rc; }
+    if (rc) { e->pub_armed = 0; e->pubctr_stale = true; return rc; }
     return fetch_result(e, lsum, n_props);
 }
 

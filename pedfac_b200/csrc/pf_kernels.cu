@@ -602,7 +602,7 @@ __device__ __forceinline__ void eval_singles2(const EvalParams &P, const EvalGro
     }
 }
 
-__global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_constant__ EvalParams P)
+__device__ __forceinline__ void eval_body(const EvalParams &P)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gi = blockIdx.y * EVAL_WARPS + warp;
@@ -656,6 +656,44 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_c
             if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned long long *>(P.pub_flag) = P.pub_seq; __threadfence_system(); }
         }
     }
+}
+
+__global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_constant__ EvalParams P) { eval_body(P); }
+
+// Small proposal lists travel in the kernel's parameter space (up to 28 KB; the limit is 32 764 bytes
+// since CUDA 12.1): no copy-engine launch in front of the kernel and no PCIe read inside it. The address
+// of a __grid_constant__ parameter is a valid generic pointer to read through.
+template <int BYTES>
+struct EvalInline { EvalParams P; unsigned off_props; alignas(16) unsigned char blob[BYTES]; };
+
+template <int BYTES>
+__global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel_inl(const __grid_constant__ EvalInline<BYTES> A)
+{
+    EvalParams P = A.P;
+    P.groups = reinterpret_cast<const EvalGroup *>(A.blob);
+    P.props = reinterpret_cast<const EvalProp *>(A.blob + A.off_props);
+    eval_body(P);
+}
+
+template <int BYTES>
+static void launch_eval_inl(const EvalParams &P, const void *blob, size_t bytes, size_t off_props, dim3 grid, cudaStream_t st)
+{
+    static thread_local EvalInline<BYTES> A;           // built in place: 16 KB on the stack of a fiber would be unkind
+    A.P = P; A.off_props = (unsigned)off_props;
+    memcpy(A.blob, blob, bytes);
+    eval_kernel_inl<BYTES><<<grid, EVAL_WARPS * 32, 0, st>>>(A);
+}
+
+bool launch_eval_inline(const EvalParams &P, const void *blob, size_t bytes, size_t off_props, int n_chunks, cudaStream_t st)
+{
+    dim3 grid(n_chunks, (P.n_groups + EVAL_WARPS - 1) / EVAL_WARPS);
+    if (bytes <= 2048) launch_eval_inl<2048>(P, blob, bytes, off_props, grid, st);
+    else if (bytes <= 4096) launch_eval_inl<4096>(P, blob, bytes, off_props, grid, st);
+    else if (bytes <= 8192) launch_eval_inl<8192>(P, blob, bytes, off_props, grid, st);
+    else if (bytes <= 16384) launch_eval_inl<16384>(P, blob, bytes, off_props, grid, st);
+    else if (bytes <= EVAL_INLINE_MAX) launch_eval_inl<EVAL_INLINE_MAX>(P, blob, bytes, off_props, grid, st);
+    else return false;
+    return true;
 }
 
 // resident eval blocks on the current device (SM count x blocks per SM from the occupancy

@@ -217,6 +217,9 @@ void launch_xreduce(const XReduceParams &X, cudaStream_t st);
 void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged, bool throughput_shape, cudaStream_t st);
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st);
 int eval_resident_blocks();
+constexpr int EVAL_INLINE_MAX = 28672;
+// the plan (groups, then proposals at off_props) inside the kernel's parameters; false: too large, nothing launched
+bool launch_eval_inline(const EvalParams &P, const void *blob, size_t bytes, size_t off_props, int n_chunks, cudaStream_t st);
 void launch_reduce(const ReduceParams &P, cudaStream_t st);
 void launch_publish(const double *src, double *dst_mapped, int n, unsigned long long *flag_mapped, unsigned long long seq, cudaStream_t st);
 
