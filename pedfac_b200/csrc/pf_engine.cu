@@ -283,6 +283,7 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     if (const char *v2 = getenv("PF_INLINE_KIDS")) e->inline_kids = std::min(FAM2_INLINE_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_CHUNK_KIDS")) e->chunk_kids = std::min(CHUNK2_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_EVAL_ZEROCOPY")) e->eval_zero_copy = v2[0] != '0';
+    if (const char *v2 = getenv("PF_PDL")) set_eval_pdl(v2[0] != '0');
     if (const char *v2 = getenv("PF_EVAL_INLINE")) e->eval_inline = v2[0] != '0';
     if (const char *v2 = getenv("PF_FUSED_PUBLISH")) e->fused_publish = v2[0] != '0';
     if (const char *fs = getenv("PF_SWEEP_SHAPE")) e->force_shape = fs[0] == 't' ? 2 : fs[0] == 'l' ? 1 : 0;

@@ -602,6 +602,7 @@ __device__ __forceinline__ void eval_singles2(const EvalParams &P, const EvalGro
     }
 }
 
+template <bool DEPENDENT>
 __device__ __forceinline__ void eval_body(const EvalParams &P)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -609,6 +610,9 @@ __device__ __forceinline__ void eval_body(const EvalParams &P)
     const int chunk = blockIdx.x;
     EvalGroup g{ROW_PRIOR, 0, 0, 0};
     if (gi < P.n_groups) g = P.groups[gi];
+    // launched as a programmatic dependent of the kernel in front of it (the sweep that writes the rows
+    // read below): the blocks are resident and their plan is loaded while that kernel drains
+    if (DEPENDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (g.single) eval_singles2(P, g, chunk, lane);
     else eval_group<EVAL_G, false>(P, g, chunk, lane);
 
@@ -658,11 +662,14 @@ __device__ __forceinline__ void eval_body(const EvalParams &P)
     }
 }
 
-__global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_constant__ EvalParams P) { eval_body(P); }
+__global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel(const __grid_constant__ EvalParams P) { eval_body<false>(P); }
 
 // Small proposal lists travel in the kernel's parameter space (up to 28 KB; the limit is 32 764 bytes
 // since CUDA 12.1): no copy-engine launch in front of the kernel and no PCIe read inside it. The address
 // of a __grid_constant__ parameter is a valid generic pointer to read through.
+static bool g_eval_pdl = true;       // PF_PDL=0: plain stream order
+void set_eval_pdl(bool on) { g_eval_pdl = on; }
+
 template <int BYTES>
 struct EvalInline { EvalParams P; unsigned off_props; alignas(16) unsigned char blob[BYTES]; };
 
@@ -672,7 +679,7 @@ __global__ void __launch_bounds__(EVAL_WARPS * 32, 4) eval_kernel_inl(const __gr
     EvalParams P = A.P;
     P.groups = reinterpret_cast<const EvalGroup *>(A.blob);
     P.props = reinterpret_cast<const EvalProp *>(A.blob + A.off_props);
-    eval_body(P);
+    eval_body<true>(P);
 }
 
 template <int BYTES>
@@ -681,7 +688,13 @@ static void launch_eval_inl(const EvalParams &P, const void *blob, size_t bytes,
     static thread_local EvalInline<BYTES> A;           // built in place: 16 KB on the stack of a fiber would be unkind
     A.P = P; A.off_props = (unsigned)off_props;
     memcpy(A.blob, blob, bytes);
-    eval_kernel_inl<BYTES><<<grid, EVAL_WARPS * 32, 0, st>>>(A);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(EVAL_WARPS * 32); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_eval_pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, eval_kernel_inl<BYTES>, A);
 }
 
 bool launch_eval_inline(const EvalParams &P, const void *blob, size_t bytes, size_t off_props, int n_chunks, cudaStream_t st)

@@ -218,6 +218,7 @@ void launch_sweep(const SweepParams &P, int n_tiles, int smem_bytes, bool staged
 void launch_eval(const EvalParams &P, int n_chunks, cudaStream_t st);
 int eval_resident_blocks();
 constexpr int EVAL_INLINE_MAX = 28672;
+void set_eval_pdl(bool on);
 // the plan (groups, then proposals at off_props) inside the kernel's parameters; false: too large, nothing launched
 bool launch_eval_inline(const EvalParams &P, const void *blob, size_t bytes, size_t off_props, int n_chunks, cudaStream_t st);
 void launch_reduce(const ReduceParams &P, cudaStream_t st);

@@ -347,6 +347,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS) sweep2_kernel(const __
 {
     extern __shared__ __align__(16) char smem[];
     __shared__ __align__(8) unsigned long long s_bar;
+    // a proposal kernel queued behind this sweep as a programmatic dependent may become resident now; it
+    // waits (griddepcontrol.wait) for this grid to complete before it reads a row
+    asm volatile("griddepcontrol.launch_dependents;");
     const DevView &D = P.D;
     const int tile = blockIdx.x;
     const Sweep2Group G = P.groups[blockIdx.y];
