@@ -987,7 +987,7 @@ cleanup:
 namespace {
 struct Work2 {
     std::vector<int> kid_off, kid_x, n_inline, chunk_off, n_chunks, chunk_first, chunk_n, chunk_row, chunk_level;
-    std::vector<int> lvl2, up_m_row, dn_row, park_row, emis_idx, depth2, cnt_d, cnt_t, rows;
+    std::vector<int> lvl2, up_m_row, dn_row, emis_idx, depth2, cnt_d, cnt_t, rows;
     std::vector<char> in_chunk;
     std::vector<uint32_t> rec;
     std::vector<uint32_t> famup_off; std::vector<int> famup_len;      // where the FAMUP2 record of each marriage went (swap sites)
@@ -1004,7 +1004,7 @@ static int emit2(pf_engine *e, const pf_graph_view *v, int chain, int out_base, 
     auto hp_mark = [&](int ph) { if (hp_on) { const double t = host_now(); e->t_ph[ph] += t - hp_t; hp_t = t; } };
     x2.kid_off.assign(nM + 1, 0); x2.kid_x.clear(); x2.n_inline.assign(nM, 0); x2.chunk_off.assign(nM, 0); x2.n_chunks.assign(nM, 0);
     x2.chunk_first.clear(); x2.chunk_n.clear(); x2.chunk_row.clear(); x2.chunk_level.clear();
-    x2.lvl2.assign(nM, 0); x2.up_m_row.assign(nM, 0); x2.dn_row.assign(nI, -1); x2.park_row.assign(nM, -1); x2.emis_idx.assign(nI, -1);
+    x2.lvl2.assign(nM, 0); x2.up_m_row.assign(nM, 0); x2.dn_row.assign(nI, -1); x2.emis_idx.assign(nI, -1);
     x2.depth2.assign(nM, 0); x2.in_chunk.assign(nI, 0);
     if (site) { x2.famup_off.assign(nM, 0); x2.famup_len.assign(nM, 0); }
     uint32_t root_off = 0; int root_len = 0;

@@ -11,7 +11,8 @@
 //     "cmp" operand of three words. That removes the up_i rows, the leaf cache rows and the LEAF_IN /
 //     KFOLD level of the first sweep: a component needs one row per marriage plus two small banks;
 //   * a family task multiplies up to four kids in line; only larger sibships use chunk tasks
-//     (KFOLD2 at the up band, KIDCHUNK2 one level below FAMDOWN2) and parked rows;
+//     (KFOLD2 at the up band; KIDCHUNK2 at the level of the marriage's FAMDOWN2 and independent of it: it
+//     re-composes the parents' messages itself, so nothing is parked between the two);
 //   * a block's warps are alone on their schedulers, so a sweep is bound by instruction issue and
 //     instruction fetch (ncu: stall_no_inst first, then stall_wait): task bodies are straight-line
 //     code, one instance per number of kids, whose only branches are warp-uniform tests of the
