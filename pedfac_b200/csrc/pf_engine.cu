@@ -140,6 +140,7 @@ struct pf_engine {
     bool swap_sites = true;           // PF_SWAP_SITES=0: every swap proposal as a hypothetical component of its own
     int inline_kids = FAM2_INLINE_KIDS, chunk_kids = CHUNK2_KIDS;   // PF_INLINE_KIDS / PF_CHUNK_KIDS (measurement aid): how sibships are cut into tasks
     DevBuf pubctr; bool pubctr_stale = true;
+    int eval_small_group = 4, eval_small_props = 1024;   // PF_EVAL_GROUP / PF_EVAL_SMALL_PROPS
     bool eval_inline = true;          // PF_EVAL_INLINE=0: always copy the eval plan to device memory
     bool fused_publish = true;        // PF_FUSED_PUBLISH=0: always a separate publish launch
 
@@ -284,6 +285,8 @@ extern "C" int pf_create(pf_engine **out, const pf_config *cfg)
     if (const char *v2 = getenv("PF_CHUNK_KIDS")) e->chunk_kids = std::min(CHUNK2_KIDS, std::max(1, atoi(v2)));
     if (const char *v2 = getenv("PF_EVAL_ZEROCOPY")) e->eval_zero_copy = v2[0] != '0';
     if (const char *v2 = getenv("PF_PDL")) set_eval_pdl(v2[0] != '0');
+    if (const char *v2 = getenv("PF_EVAL_GROUP")) e->eval_small_group = std::max(1, std::min(4, atoi(v2)));
+    if (const char *v2 = getenv("PF_EVAL_SMALL_PROPS")) e->eval_small_props = std::max(0, atoi(v2));
     if (const char *v2 = getenv("PF_EVAL_INLINE")) e->eval_inline = v2[0] != '0';
     if (const char *v2 = getenv("PF_FUSED_PUBLISH")) e->fused_publish = v2[0] != '0';
     if (const char *fs = getenv("PF_SWEEP_SHAPE")) e->force_shape = fs[0] == 't' ? 2 : fs[0] == 'l' ? 1 : 0;
@@ -2484,12 +2487,15 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
     for (int i = 0; i < n; i++)
         if (prop_begin[i + 1] < prop_begin[i]) return fail(PF_EINVAL, "prop_begin not monotone");
     auto is_single = [&](const pf_proposal &q) { return e->eval_singles && q.kind == PF_PROP_TRIO && (q.pa < 0 || q.ma < 0); };
+    // proposals per warp: 4, or fewer for a short list (PF_EVAL_GROUP, measurement aid) so that more warps share it
+    const int per_s = n_props <= e->eval_small_props ? std::min(e->eval_small_group, EVAL_GS) : EVAL_GS;
+    const int per_g = n_props <= e->eval_small_props ? std::min(e->eval_small_group, EVAL_G) : EVAL_G;
     int n_groups = 0;
     for (int i = 0; i < n; i++) {
         int ns = 0;
         for (int p = prop_begin[i]; p < prop_begin[i + 1]; p++) ns += is_single(props[p]) ? 1 : 0;
         const int ng = prop_begin[i + 1] - prop_begin[i] - ns;
-        n_groups += (ns + EVAL_GS - 1) / EVAL_GS + (ng + EVAL_G - 1) / EVAL_G;
+        n_groups += (ns + per_s - 1) / per_s + (ng + per_g - 1) / per_g;
     }
     const size_t bytes_groups = (size_t)n_groups * sizeof(EvalGroup);
     const size_t off_props = (bytes_groups + 15) & ~(size_t)15;
@@ -2522,7 +2528,7 @@ static int run_evals(pf_engine *e, int n, const int32_t *chains, const int32_t *
                 }
                 hq[pos++] = d;
             }
-            const int per = pass == 0 ? EVAL_GS : EVAL_G;
+            const int per = pass == 0 ? per_s : per_g;
             for (int b = first; b < pos; b += per)
                 hg[gi++] = EvalGroup{e->stub_row(chain, kid), b, std::min(per, pos - b), pass == 0 ? 1 : 0};
         }
