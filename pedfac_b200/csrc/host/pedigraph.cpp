@@ -201,6 +201,7 @@ struct Ped {
     std::vector<char> indivActive, marrActive;
     std::vector<int> cc, ccDirty;
     int nCC = 0, nDirty = 0;
+    std::vector<int> marked;                         // marriage slots whose `mark` is set (see the prong block of EvalMoves)
     std::vector<std::vector<int>> ccMem;             // the active individuals of every component label (kept from CheckPed on): the
                                                      // reference scans all individuals wherever this is walked
     std::vector<double> LLcc;
@@ -709,7 +710,11 @@ static bool checkMatchingCC(Ped &p, int pa, int ma, int kid)
         const Indiv &ip = p.indiv[pa];
         for (size_t k = 0; k < ip.M.size(); k++) {
             if (ip.edge[k] > 1) continue;
-            if (p.marr[ip.M[k]].ma == ma) { p.marr[ip.M[k]].mark = true; break; }
+            if (p.marr[ip.M[k]].ma == ma) {
+                if (!p.marr[ip.M[k]].mark) p.marked.push_back(ip.M[k]);
+                p.marr[ip.M[k]].mark = true;
+                break;
+            }
         }
     }
     return true;
@@ -848,15 +853,29 @@ static void EvalMoves(Ped &p, const Opts &o, int kid)
         for (auto &u : p.cand[0]) pair(u.first, f.first);
     for (size_t i = 0; i + 1 < p.cand[0].size(); i++)
         for (size_t j = i + 1; j < p.cand[0].size(); j++) pair(p.cand[0][i].first, p.cand[0][j].first);
-    for (int m = 0; m < p.nMarrUsed; m++) {                    // prong proposals for marked marriages
-        if (!p.marrActive[m]) continue;
-        Marr &mm = p.marr[m];
-        const double g1 = p.indiv[mm.pa].genTime - kt, g2 = p.indiv[mm.ma].genTime - kt;
-        if (g1 > p.maxAge || p.minAge > g1 || g2 > p.maxAge || p.minAge > g2) continue;
-        if (!mm.mark) continue;
-        mm.mark = false;
-        if (p.cc[mm.pa] == ck) continue;
-        add_choice(p, b, PF_PROP_PRONG, -1, -1, m);
+    // prong proposals for marked marriages. The reference scans every marriage slot in order and tests
+    // "active", the age window and the mark in that order, so a mark survives on a marriage that is
+    // inactive or outside this kid's window; the marks are few, so they are kept in a list (p.marked)
+    // and only those slots are visited, in slot order, with the same tests
+    if (!p.marked.empty()) {
+        std::sort(p.marked.begin(), p.marked.end());
+        p.marked.erase(std::unique(p.marked.begin(), p.marked.end()), p.marked.end());
+        size_t kept = 0;
+        for (size_t q = 0; q < p.marked.size(); q++) {
+            const int m = p.marked[q];
+            Marr &mm = p.marr[m];
+            if (!mm.mark) continue;                            // cleared since (marriage dissolved or slot reused)
+            bool stays = !p.marrActive[m] || m >= p.nMarrUsed;
+            if (!stays) {
+                const double g1 = p.indiv[mm.pa].genTime - kt, g2 = p.indiv[mm.ma].genTime - kt;
+                stays = g1 > p.maxAge || p.minAge > g1 || g2 > p.maxAge || p.minAge > g2;
+            }
+            if (stays) { p.marked[kept++] = m; continue; }
+            mm.mark = false;
+            if (p.cc[mm.pa] == ck) continue;
+            add_choice(p, b, PF_PROP_PRONG, -1, -1, m);
+        }
+        p.marked.resize(kept);
     }
     flush(p, kid, b);
     FinishSwaps(p, sp);
