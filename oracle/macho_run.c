@@ -225,6 +225,15 @@ static void on_trap(int sig, siginfo_t *si, void *uc_) {
         *(uint64_t *)g[REG_RSP] = (uint64_t)g[REG_RBP];
         return;
     }
+    /* PEDFAC_REF_DUMP_CMP=1 with `_compareLLonGC@0x1000201c0` traced: both (id, ll) operands of every
+     * comparison qsort makes (prefilter ranking, top-10 cuts) at full precision — how ties were examined */
+    if ((unsigned long)g[REG_RIP] - 1 == 0x1000201c0ul && getenv("PEDFAC_REF_DUMP_CMP")) {
+        const char *a = (const char *)g[REG_RDI], *b = (const char *)g[REG_RSI];
+        fprintf(stderr, "ref-cmp %d %.17g | %d %.17g\n", *(const int *)a, *(const double *)(a + 8), *(const int *)b, *(const double *)(b + 8));
+        g[REG_RSP] -= 8;
+        *(uint64_t *)g[REG_RSP] = (uint64_t)g[REG_RBP];
+        return;
+    }
     fprintf(stderr, "ref-call 0x%lx rdi=%ld rsi=%ld rdx=%ld rcx=%ld r8=%ld\n", (unsigned long)g[REG_RIP] - 1,
             (long)g[REG_RDI], (long)g[REG_RSI], (long)g[REG_RDX], (long)g[REG_RCX], (long)g[REG_R8]);
     g[REG_RSP] -= 8;

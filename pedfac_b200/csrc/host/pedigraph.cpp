@@ -1698,6 +1698,11 @@ static void RefineParentOffPair(Ped &p)
                     auto &pc = p.parentCand[ks[k]];
                     pc.clear();
                     for (int t = 0; t < K; t++) if (slot[k * K + t] >= 0) pc.push_back(slot[k * K + t]);
+                    if (getenv("PEDFAC_DEBUG_CAND")) {
+                        fprintf(stderr, "cand kid %d:", ks[k]);
+                        for (int t = 0; t < K; t++) if (slot[k * K + t] >= 0) fprintf(stderr, " %d(%.17g)", slot[k * K + t], score[k * K + t]);
+                        fprintf(stderr, "\n");
+                    }
                 }
             };
             std::vector<int> plain;
